@@ -1,0 +1,127 @@
+// chain_args.h -- launch-argument structures shared by the host code and the sm_100a kernels.
+//
+// One streaming "chain" = [input-rate mixer] -> [FIR, decimate by M] -> [demod-rate oscillator]
+// -> [demodulator front map] -> [recursive sections].  Every
+// reference block on the hot path is a degenerate chain, so there is exactly one kernel family.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace orion {
+
+constexpr int kThreads     = 128;   // threads per CTA (4 warps); one tile = kThreads * NPT outputs
+constexpr int kMaxSections = 8;     // recursive sections per chain (LR4 = 2, LpDc = 3, + post sections)
+constexpr int kMaxTapTable = 2560;  // float capacity of the polyphase tap table held in the parameter bank
+constexpr int kMaxRowSamples = 96;  // R * Mb limit of the shared-memory staged FIR (row <= 768 B + pad)
+
+enum : int { SEC_BIQUAD = 1, SEC_DC = 2, SEC_ONEPOLE = 3 };
+enum : int { OP_NONE = 0, OP_SQRT = 1, OP_SCALE = 2 };
+enum : int { MIX_NONE = 0, MIX_ROTATE = 1, MIX_NCO = 2 };
+enum : int { FIR_NONE = 0, FIR_DECIM = 1, FIR_IQ = 2 };
+enum : int { DEMOD_NONE = 0, DEMOD_FM = 1, DEMOD_PM = 2, DEMOD_AM = 3, DEMOD_AM_ABS = 4,
+             DEMOD_SSB = 5, DEMOD_CW = 6, DEMOD_USB = 7, DEMOD_F32 = 8 /* f32 in -> sections only */ };
+enum : int { FRONT_DIRECT = 0,   // no FIR: items are read straight from global memory
+             FRONT_STAGED = 1,   // polyphase FIR on a TMA / cooperatively staged shared-memory tile
+             FRONT_GLOBAL = 2 }; // any-shape FIR evaluated from global memory (large M, huge tap sets)
+
+// One first/second-order recursive section.  Coefficients are the reference's f32 values;
+// the per-sample arithmetic in sec_step() follows the reference op for op.
+struct SecParam {
+    int   type;        // SEC_*
+    int   post_op;     // OP_* applied to the section's output before the next section
+    float c[5];        // BIQUAD: b0,b1,b2,a1,a2 | DC: r | ONEPOLE: a, (1-a)
+    float post_scale;  // OP_SCALE factor
+};
+
+// 2x2 state-transition powers used by the chunked parallel scan (row-major a00,a01,a10,a11),
+// computed on the host in f64 from the f32 coefficients and rounded once.  n = items per
+// thread, T = kThreads * n = items per tile.
+struct SecTables {
+    float4 lv[5];     // A^(n*2^l), l = 0..4        (warp-level Kogge-Stone scan)
+    float4 lane[32];  // A^(n*lane)                  (carry into a lane's chunk)
+    float4 warp[4];   // A^(32*n*w), w = 0..3        (carry into a warp); warp[1] = one-warp step
+    float4 lb[32];    // A^(T*k), k = 0..31          (inter-tile look-back)
+    float4 lb32;      // A^(32*T)
+    float4 tile;      // A^T
+};
+
+// Oscillator (Rotator / Nco).  Phase is a 64-bit fraction of a turn:
+//   phase(k) = phase0 + step * (k - k0),
+// where k counts next() calls since the last reset (the reference advances BEFORE use, so item i
+// of a fresh block sees k = i + 1; rotator.rs:44-61).  step = angle(w_f32) / 2pi, w_f32 being the
+// reference's f32-rounded (cos, sin) step, so the closed form tracks the reference recurrence to
+// its rounding noise.
+struct NcoParam {
+    unsigned long long step;
+    unsigned long long phase0;
+    unsigned long long k0;
+    unsigned long long kbase;   // k of item 0 of this call, minus 1  (k = kbase + idx + 1)
+    float wre, wim;             // unit (cos, sin) of the step angle, for short in-thread recurrences
+    float amp_delta;            // ln|w_f32|: |z_k| = 1 + (k mod 1024) * amp_delta (renormalised every 1024)
+    float pad;
+};
+
+struct CarryState {              // streaming state carried between process() calls (device memory)
+    float2 prev;                 // discriminator previous sample (fm.rs:16, pm.rs:16)
+    float2 sec[kMaxSections];    // recursive-section states
+    float2 pad;
+};
+
+struct TileLink {                // one per (tile, section): decoupled look-back record
+    float2 agg;                  // end state of this tile from a zero start state
+    float2 incl;                 // true end state
+    unsigned int status;         // (epoch << 2) | {0 none, 1 agg valid, 2 agg+incl valid}
+    unsigned int pad[3];
+};
+
+struct ChainArgs {
+    const void *in;              // C32 (or f32 when demod == DEMOD_F32), call-relative item 0
+    void       *out;             // f32, or C32 when demod == DEMOD_NONE
+    long long   n_in;            // input items consumed by this call
+    long long   n_out;           // outputs produced by this call
+    // FIR history: the H input samples preceding item 0 (ping-pong across calls)
+    const float2 *hist_in;
+    float2       *hist_out;
+    int   H;
+    // input-rate mixer
+    int   mix;
+    NcoParam pre;
+    // FIR in generic causal form  y[j] = sum_{t < Lg} g[t] * x[M*j - t]
+    int   fir;
+    int   M;
+    int   Lg;
+    const float *g;              // device copy of g[]
+    // staged polyphase plan (FRONT_STAGED)
+    int   Mb;                    // samples per block (even) = M * U
+    int   O;                     // block origin offset (even, >= M*(U-1))
+    int   P_pad;                 // tap steps (multiple of R)
+    int   HR;                    // halo rows = P_pad / R
+    int   row_samples;           // R * Mb
+    int   row_pitch;             // bytes, odd multiple of 16
+    int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
+    long long tma_row0;          // global row index of tensor-map row 0
+    long long tma_rows;          // rows the tensor map covers
+    // demodulator
+    int   demod;
+    int   translate;             // FM: multiply by conj(post phasor) first (fm.rs:34-37)
+    float k, k1, k2;
+    NcoParam post;               // demod-rate oscillator (FM translate / SSB BFO / USB mix)
+    // recursive sections
+    int   nsec;
+    SecParam sec[kMaxSections];
+    const SecTables *tabs;       // [nsec]
+    // carried state, ping-pong across calls
+    const CarryState *carry_in;
+    CarryState       *carry_out;
+    // inter-tile links
+    TileLink *links;             // [ntiles][kMaxSections]
+    unsigned long long *ticket;
+    unsigned long long  ticket_base;
+    unsigned int epoch;
+    int   ntiles;
+    int   serial;                // debug: tiles run one after another (grid = 1)
+    int  *err_flag;
+    float2 taps2[kMaxTapTable / 2];   // [u][q][c] -> (g[t0], g[t0-1]); see DESIGN.md "staged FIR"
+};
+
+}  // namespace orion

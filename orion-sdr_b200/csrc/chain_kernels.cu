@@ -1,0 +1,728 @@
+// chain_kernels.cu -- the sm_100a streaming-chain kernel family.
+//
+//   [input-rate mixer] -> [FIR, keep every M-th] -> [demod-rate oscillator] -> [demod front map]
+//   -> [recursive sections]                                       one launch, one pass over HBM.
+//
+// Work decomposition (DESIGN.md "kernel"): the output stream is cut into tiles of
+// kThreads*NPT items; a CTA takes tiles in ticket order (persistent, dynamic), every thread owns
+// NPT = R*U CONSECUTIVE output items, so that
+//   * the polyphase FIR slides an R-deep register window over the staged input (each staged
+//     sample is read once per thread and reused R times),
+//   * the discriminator needs one neighbour value per thread,
+//   * every recursive section is a per-thread serial recursion (the reference's exact
+//     arithmetic) stitched together by a block-level state-space scan and an inter-tile
+//     decoupled look-back.
+// Input staging: one cp.async.bulk.tensor (TMA) per interior tile into a padded row layout;
+// edge tiles (FIR history / ragged tail) use a cooperative loader into the same layout.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (FMA only where written).
+#include "chain_args.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace orion {
+
+#define DEV __device__ __forceinline__
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+DEV float2 mv(const float4 m, const float2 v) {              // 2x2 (row-major) times vector
+    return make_float2(fmaf(m.x, v.x, m.y * v.y), fmaf(m.z, v.x, m.w * v.y));
+}
+DEV float4 mm(const float4 a, const float4 b) {              // a * b
+    return make_float4(fmaf(a.x, b.x, a.y * b.z), fmaf(a.x, b.y, a.y * b.w),
+                       fmaf(a.z, b.x, a.w * b.z), fmaf(a.z, b.y, a.w * b.w));
+}
+DEV float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEV unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+DEV float2 ld_cg_f2(const float2 *p) { return __ldcg(p); }
+
+// mbarrier / TMA (PTX ISA: mbarrier, cp.async.bulk.tensor)
+DEV void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+DEV void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+DEV bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
+DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// oscillator: closed-form phase from the absolute call counter (NcoParam in chain_args.h)
+// ----------------------------------------------------------------------------------------------
+DEV float2 nco_unit(const NcoParam &p, unsigned long long k) {
+    const unsigned long long ph = p.phase0 + p.step * (k - p.k0);
+    // top 32 bits as a signed fraction of pi in [-1, 1); the low word refines it to ~2^-40 turn
+    const int hi = (int)(unsigned)(ph >> 32);
+    const float xh = (float)hi;                                   // rounded to 24 bits
+    const long long rem = ((long long)ph >> 8) - ((long long)xh << 24);   // exact remainder, 2^-56 turn units
+    const float x = xh * 4.656612873077393e-10f;                  // * 2^-31  (units of pi)
+    float s, c;
+    sincospif(x, &s, &c);
+    // first-order correction for the bits the float conversion dropped: d = rem * 2^-55 * pi
+    const float d = (float)rem * (3.14159265358979f * 2.7755575615628914e-17f);
+    return make_float2(fmaf(-s, d, c), fmaf(c, d, s));
+}
+// |z_k| of the reference recurrence: |w_f32|^(k mod 1024), renormalised to 1 every 1024 steps
+DEV float nco_amp(const NcoParam &p, unsigned long long k) {
+    return fmaf((float)(unsigned)(k & 1023ull), p.amp_delta, 1.0f);
+}
+DEV float2 nco_phasor(const NcoParam &p, unsigned long long k) {
+    const float2 u = nco_unit(p, k);
+    const float a = nco_amp(p, k);
+    return make_float2(u.x * a, u.y * a);
+}
+DEV float2 scale2(float2 z, float a) { return make_float2(z.x * a, z.y * a); }
+DEV float2 cmul_fma(float2 z, float2 w) {   // phasor advance, reference form (rotator.rs:46-47)
+    return make_float2(fmaf(z.x, w.x, -(z.y * w.y)), fmaf(z.y, w.x, z.x * w.y));
+}
+
+// input-rate mixers
+DEV float2 mix_apply(int mix, float2 x, float2 p) {
+    if (mix == MIX_ROTATE)                                         // rotator.rs:74-84
+        return make_float2(fmaf(x.x, p.x, -(x.y * p.y)), fmaf(x.y, p.x, x.x * p.y));
+    return make_float2(x.x * p.x - x.y * p.y, x.x * p.y + x.y * p.x);   // nco.rs:63-66
+}
+
+// util.rs:305-322, op for op
+DEV float atan2_approx(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool sw = ax < ay;
+    const float mn = sw ? ax : ay, mx = sw ? ay : ax;
+    const float r = mn / (mx + 1.1920929e-07f);
+    const float r2 = r * r;
+    float phi = r * (0.78539816339744830962f + r2 * (-0.2447f + r2 * 0.0663f));
+    if (sw) phi = 1.57079632679489661923f - phi;
+    const float sgn = (y < 0.0f) ? -1.0f : 1.0f;
+    if (x < 0.0f) return (3.14159265358979323846f - phi) * sgn;
+    return phi * sgn;
+}
+
+// one recursive-section step, reference arithmetic (iir.rs:34-40, iir.rs:160-163, cw.rs:38-39)
+DEV float sec_step(const SecParam &P, float x, float &s0, float &s1) {
+    float y;
+    if (P.type == SEC_BIQUAD) {
+        y = fmaf(x, P.c[0], s0);
+        s0 = fmaf(x, P.c[1], s1) - P.c[3] * y;
+        s1 = x * P.c[2] - P.c[4] * y;
+    } else if (P.type == SEC_DC) {            // y = x - x1 + r*y1 ; s0 = x1, s1 = y1
+        y = (x - s0) + P.c[0] * s1;
+        s0 = x;
+        s1 = y;
+    } else {                                  // y = a*y + (1-a)*x ; s0 = y
+        y = P.c[0] * s0 + P.c[1] * x;
+        s0 = y;
+    }
+    return y;
+}
+DEV float post_apply(const SecParam &P, float y) {
+    if (P.post_op == OP_SQRT) return sqrtf(y);
+    if (P.post_op == OP_SCALE) return y * P.post_scale;
+    return y;
+}
+
+// virtual input stream: FIR history for negative indices, zeros past the end of the call
+DEV float2 load_x(const ChainArgs &a, long long s) {
+    if (s < 0) {
+        const long long h = s + a.H;
+        return h >= 0 ? __ldg(a.hist_in + h) : make_float2(0.f, 0.f);
+    }
+    if (s < a.n_in) return __ldg(reinterpret_cast<const float2 *>(a.in) + s);
+    return make_float2(0.f, 0.f);
+}
+DEV float2 load_x_mixed(const ChainArgs &a, long long s) {
+    float2 x = load_x(a, s);
+    if (a.mix != MIX_NONE) x = mix_apply(a.mix, x, nco_phasor(a.pre, a.pre.kbase + (unsigned long long)s + 1ull));
+    return x;
+}
+
+struct __align__(16) Shared {
+    unsigned long long mbar;
+    long long tile;
+    float2 zlast[kThreads];
+    float2 wtot[4];
+    float2 spre[4];
+    float2 s_tile_in;
+    float2 zhalo;
+};
+
+// ----------------------------------------------------------------------------------------------
+// inter-tile decoupled look-back for one section (warp 0, all lanes).  Returns the section state
+// at the start of `tile`.
+// ----------------------------------------------------------------------------------------------
+DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int s, int lane) {
+    float2 acc = make_float2(0.f, 0.f);
+    float4 M = make_float4(1.f, 0.f, 0.f, 1.f);     // A^(T * 32 * window)
+    long long base = tile - 1;
+    const float4 lbk = T->lb[lane];
+    for (;;) {
+        const long long idx = base - lane;
+        const TileLink *lk = a.links + (idx >= 0 ? idx : 0) * kMaxSections + s;
+        unsigned st = 0;
+        int first_incl = 32;
+        int spins = 0;
+        for (;;) {
+            bool ready, incl;
+            if (idx >= 0) {
+                st = ld_acquire_u32(&lk->status);
+                ready = (st >> 2) == a.epoch && (st & 3u) != 0u;
+                incl = ready && (st & 3u) == 2u;
+            } else {                       // virtual tile -1 = state carried in from the last call
+                ready = true;
+                incl = true;
+            }
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
+            const unsigned ready_mask = __ballot_sync(0xffffffffu, ready);
+            first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+            const unsigned need = (first_incl >= 31) ? 0xffffffffu : ((2u << first_incl) - 1u);
+            if ((ready_mask & need) == need) break;
+            if (++spins > (1 << 21)) {     // watchdog: never hang the device
+                if (lane == 0) atomicExch(a.err_flag, 1);
+                return acc;
+            }
+            __nanosleep(20);
+        }
+        float2 term = make_float2(0.f, 0.f);
+        if (lane <= first_incl) {
+            float2 pay;
+            if (idx < 0) pay = (idx == -1) ? a.carry_in->sec[s] : make_float2(0.f, 0.f);
+            else pay = (lane == first_incl) ? ld_cg_f2(&lk->incl) : ld_cg_f2(&lk->agg);
+            term = mv(M, mv(lbk, pay));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
+            term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
+        }
+        acc = add2(acc, term);
+        if (first_incl < 32) break;
+        M = mm(M, T->lb32);
+        base -= 32;
+    }
+    return acc;
+}
+
+DEV void publish(const ChainArgs &a, long long tile, int s, float2 v, bool inclusive) {
+    TileLink *lk = a.links + tile * kMaxSections + s;
+    if (inclusive) __stcg(&lk->incl, v); else __stcg(&lk->agg, v);
+    __threadfence();
+    st_release_u32(&lk->status, (a.epoch << 2) | (inclusive ? 2u : 1u));
+}
+
+// ----------------------------------------------------------------------------------------------
+// staged-tile geometry (FRONT_STAGED)
+//   global row G covers samples [row_samples*G + O - Mb + 2, +row_samples)   (call-relative)
+//   tile t stages rows G0 .. G0+rows-1 with G0 = t*kThreads - HR, rows = kThreads + HR
+// ----------------------------------------------------------------------------------------------
+DEV long long row_start_sample(const ChainArgs &a, long long G) {
+    return (long long)a.row_samples * G + (a.O - a.Mb + 2);
+}
+
+template <int R, int U>
+DEV void stage_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
+                    Shared &sh, unsigned &mbar_parity, int tid) {
+    const int rows = kThreads + a.HR;
+    const long long G0 = tile * kThreads - a.HR;
+    const bool interior = a.use_tma && G0 >= a.tma_row0 && (G0 + rows) <= (a.tma_row0 + a.tma_rows);
+    if (interior) {
+        const uint32_t mbar = smem_u32(&sh.mbar);
+        if (tid == 0) {
+            fence_proxy_async();           // earlier generic-proxy accesses to the tile vs the async write
+            mbar_expect_tx(mbar, (uint32_t)(rows * a.row_pitch));
+            tma_load_2d(smem_u32(smem), tmap, 0, (int)(G0 - a.tma_row0), mbar);
+        }
+        int spins = 0;
+        while (!mbar_try_wait(mbar, mbar_parity)) {
+            if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+        }
+        mbar_parity ^= 1u;
+    } else {
+        const int cpr = a.row_samples >> 1;                 // 16-byte chunks per row
+        const int total = rows * cpr;
+        const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
+        for (int c = tid; c < total; c += kThreads) {
+            const int rho = c / cpr;
+            const int cc = c - rho * cpr;
+            const long long s = row_start_sample(a, G0 + rho) + 2 * cc;
+            float4 v;
+            if (al16 && s >= 0 && s + 1 < a.n_in) {
+                v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.in) + s));
+            } else {
+                const float2 x0 = load_x(a, s), x1 = load_x(a, s + 1);
+                v = make_float4(x0.x, x0.y, x1.x, x1.y);
+            }
+            *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v;
+        }
+        __syncthreads();
+    }
+    if (a.mix != MIX_NONE) {
+        // in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
+        const int cpr = a.row_samples >> 1;
+        const float2 w = make_float2(a.pre.wre, a.pre.wim);
+        for (int rho = tid; rho < rows; rho += kThreads) {
+            const long long s0 = row_start_sample(a, G0 + rho);
+            unsigned char *rp = smem + (size_t)rho * a.row_pitch;
+            float2 p = make_float2(1.f, 0.f);
+            for (int cc = 0; cc < cpr; ++cc) {
+                const unsigned long long k = a.pre.kbase + (unsigned long long)(s0 + 2 * cc) + 1ull;
+                if ((cc & 7) == 0) p = nco_unit(a.pre, k);
+                float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
+                const float2 y0 = mix_apply(a.mix, make_float2(v.x, v.y), scale2(p, nco_amp(a.pre, k)));
+                p = cmul_fma(p, w);
+                const float2 y1 = mix_apply(a.mix, make_float2(v.z, v.w), scale2(p, nco_amp(a.pre, k + 1ull)));
+                p = cmul_fma(p, w);
+                *reinterpret_cast<float4 *>(rp + cc * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// shared-memory address of call-relative sample s inside the staged tile
+DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, long long G0, long long s) {
+    const long long d = s - row_start_sample(a, G0);
+    const int rho = (int)(d / a.row_samples);
+    const int w = (int)(d - (long long)rho * a.row_samples);
+    return reinterpret_cast<const float2 *>(smem + (size_t)rho * a.row_pitch + (size_t)w * 8);
+}
+
+// polyphase FIR over the staged tile: thread `tid` produces outputs of blocks tid*R .. tid*R+R-1
+template <int R, int U>
+DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int tid, float2 (&z)[R * U]) {
+    float2 acc[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < R; ++i) acc[u][i] = make_float2(0.f, 0.f);
+
+    const int Mb = a.Mb, pitch = a.row_pitch, P_pad = a.P_pad, HR = a.HR;
+    const int blk_bytes = Mb * 8;
+    const unsigned char *row_own = smem + (size_t)tid * pitch;
+    const int npairs = Mb >> 1;
+    for (int q = 0; q < npairs; ++q) {
+        const int off_q = (Mb - 2 - 2 * q) * 8;
+        float4 w[R];
+#pragma unroll
+        for (int k = 0; k + 1 < R; ++k)
+            w[k] = *reinterpret_cast<const float4 *>(row_own + (k + 1) * blk_bytes + off_q);
+        const float2 *tp0 = a.taps2 + (size_t)q * P_pad;
+        const float2 *tp1 = a.taps2 + (size_t)(npairs + q) * P_pad;     // U == 2 only
+        const unsigned char *rb = row_own + pitch + off_q;
+        for (int rr = 0; rr < HR; ++rr, rb += pitch) {
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+                w[(kk + R - 1) % R] = *reinterpret_cast<const float4 *>(rb + kk * blk_bytes);
+                const int c = rr * R + kk;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float2 t = (u == 0) ? tp0[c] : tp1[c];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const float4 wv = w[(kk + i) % R];
+                        acc[u][i].x = fmaf(t.x, wv.x, acc[u][i].x);
+                        acc[u][i].y = fmaf(t.x, wv.y, acc[u][i].y);
+                        acc[u][i].x = fmaf(t.y, wv.z, acc[u][i].x);
+                        acc[u][i].y = fmaf(t.y, wv.w, acc[u][i].y);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int u = 0; u < U; ++u) z[i * U + u] = acc[u][i];
+}
+
+// one FIR output evaluated straight from the virtual stream (any shape).  exact != 0 reproduces
+// the reference's accumulation order and rounding (fir.rs:57-66 unfused, fir.rs:229-247 fused).
+DEV float2 fir_global_one(const ChainArgs &a, long long j) {
+    const long long n = (long long)a.M * j;
+    float re = 0.f, im = 0.f;
+    if (a.fir == FIR_DECIM) {
+        // g[k] = taps[k-1] (k >= 1), g[0] = taps[L-1]; reference order: k = 1 .. L-1, then 0
+        for (int k = 1; k < a.Lg; ++k) {
+            const float2 x = load_x_mixed(a, n - k);
+            const float t = __ldg(a.g + k);
+            re = re + x.x * t;
+            im = im + x.y * t;
+        }
+        const float2 x = load_x_mixed(a, n);
+        const float t = __ldg(a.g);
+        re = re + x.x * t;
+        im = im + x.y * t;
+    } else {
+        for (int k = 0; k < a.Lg; ++k) {
+            const float2 x = load_x_mixed(a, n - k);
+            const float t = __ldg(a.g + k);
+            re = fmaf(x.x, t, re);
+            im = fmaf(x.y, t, im);
+        }
+    }
+    return make_float2(re, im);
+}
+
+// warp-cooperative evaluation of one FIR output from the staged tile (discriminator halo)
+DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, long long G0, long long j, int lane) {
+    const long long n = (long long)a.M * j;
+    float re = 0.f, im = 0.f;
+    for (int k = lane; k < a.Lg; k += 32) {
+        const float2 x = *staged_sample(a, smem, G0, n - k);
+        const float t = __ldg(a.g + k);
+        re = fmaf(x.x, t, re);
+        im = fmaf(x.y, t, im);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    return make_float2(re, im);
+}
+
+// ----------------------------------------------------------------------------------------------
+// one tile
+// ----------------------------------------------------------------------------------------------
+template <int FRONT, int R, int U>
+DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
+                      Shared &sh, unsigned &mbar_parity) {
+    constexpr int NPT = R * U;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long j0 = tile * (long long)(kThreads * NPT);
+    const long long jt = j0 + (long long)tid * NPT;
+    const bool is_c32_in = a.demod != DEMOD_F32;
+    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    const bool post_osc = (a.demod == DEMOD_FM && a.translate) || a.demod == DEMOD_SSB || a.demod == DEMOD_USB;
+
+    float2 z[NPT];
+    float  u[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) { z[i] = make_float2(0.f, 0.f); u[i] = 0.f; }
+    float2 zhalo = make_float2(0.f, 0.f);           // item j0-1 (thread 0 only)
+
+    // ---------------- front: produce z[] (C32 items at the demod rate) or u[] (f32 items) --------
+    if (FRONT == FRONT_STAGED) {
+        stage_tile<R, U>(a, tmap, tile, smem, sh, mbar_parity, tid);
+        fir_staged<R, U>(a, smem, tid, z);
+        if (need_prev && j0 > 0 && wid == 0) {
+            const long long G0 = tile * kThreads - a.HR;
+            zhalo = fir_staged_one(a, smem, G0, j0 - 1, lane);
+        }
+    } else if (FRONT == FRONT_GLOBAL) {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i)
+            if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
+        if (need_prev && j0 > 0 && tid == 0) zhalo = fir_global_one(a, j0 - 1);
+    } else {
+        if (is_c32_in) {
+            const float2 *in = reinterpret_cast<const float2 *>(a.in);
+            const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 2 == 0);
+            if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+                for (int i = 0; i < NPT; i += 2) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
+                    z[i] = make_float2(v.x, v.y);
+                    z[i + 1] = make_float2(v.z, v.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NPT; ++i)
+                    if (jt + i < a.n_out) z[i] = __ldg(in + jt + i);
+            }
+            if (a.mix != MIX_NONE) {
+                const unsigned long long k0 = a.pre.kbase + (unsigned long long)jt + 1ull;
+                float2 p = nco_unit(a.pre, k0);
+                const float2 w = make_float2(a.pre.wre, a.pre.wim);
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {
+                    z[i] = mix_apply(a.mix, z[i], scale2(p, nco_amp(a.pre, k0 + i)));
+                    p = cmul_fma(p, w);
+                }
+            }
+            if (need_prev && j0 > 0 && tid == 0) zhalo = load_x_mixed(a, j0 - 1);
+        } else {
+            const float *in = reinterpret_cast<const float *>(a.in);
+            const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 4 == 0);
+            if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+                for (int i = 0; i < NPT; i += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
+                    u[i] = v.x; u[i + 1] = v.y; u[i + 2] = v.z; u[i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NPT; ++i)
+                    if (jt + i < a.n_out) u[i] = __ldg(in + jt + i);
+            }
+        }
+    }
+
+    // ---------------- demod-rate oscillator + front map ------------------------------------------
+    if (is_c32_in && a.demod != DEMOD_NONE) {
+        float2 p = make_float2(1.f, 0.f);
+        const float2 w = make_float2(a.post.wre, a.post.wim);
+        const unsigned long long kp0 = a.post.kbase + (unsigned long long)jt + 1ull;
+        if (post_osc) p = nco_unit(a.post, kp0);
+        if (a.demod == DEMOD_FM && a.translate) {
+            // z = in * conj(p)   (num-complex Mul, unfused; fm.rs:49)
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {
+                const float am = nco_amp(a.post, kp0 + i);
+                const float cr = p.x * am, ci = -(p.y * am);
+                z[i] = make_float2(z[i].x * cr - z[i].y * ci, z[i].x * ci + z[i].y * cr);
+                p = cmul_fma(p, w);
+            }
+            if (j0 > 0 && tid == 0) {
+                const float2 ph = nco_phasor(a.post, a.post.kbase + (unsigned long long)j0);
+                const float cr = ph.x, ci = -ph.y;
+                zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
+            }
+        }
+        if (need_prev) {
+            sh.zlast[tid] = z[NPT - 1];
+            __syncthreads();
+            float2 prev;
+            if (tid > 0) prev = sh.zlast[tid - 1];
+            else prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+            // carried discriminator state for the next call
+            if (a.n_out > 0 && jt <= a.n_out - 1 && a.n_out - 1 < jt + NPT) {
+                float2 last = z[0];
+#pragma unroll
+                for (int i = 1; i < NPT; ++i)
+                    if (jt + i == a.n_out - 1) last = z[i];
+                a.carry_out->prev = last;
+            }
+            if (a.demod == DEMOD_FM) {
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {             // fm.rs:50-56
+                    const float pr = z[i].x * prev.x + z[i].y * prev.y;
+                    const float pi = z[i].y * prev.x - z[i].x * prev.y;
+                    u[i] = atan2_approx(pi, pr) * a.k;
+                    prev = z[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {             // pm.rs:54-58 (z * prev.conj())
+                    const float cr = prev.x, ci = -prev.y;
+                    const float wre = z[i].x * cr - z[i].y * ci;
+                    const float wim = z[i].x * ci + z[i].y * cr;
+                    u[i] = a.k * atan2_approx(wim, wre);
+                    prev = z[i];
+                }
+            }
+        } else if (a.demod == DEMOD_AM) {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) u[i] = fmaf(z[i].x, z[i].x, z[i].y * z[i].y);          // am.rs:53
+        } else if (a.demod == DEMOD_AM_ABS) {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) u[i] = fmaf(a.k1, fabsf(z[i].x), a.k2 * fabsf(z[i].y)); // am.rs:86
+        } else if (a.demod == DEMOD_SSB || a.demod == DEMOD_USB) {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {                                                      // ssb.rs:36-37
+                const float2 pa = scale2(p, nco_amp(a.post, kp0 + i));
+                u[i] = fmaf(z[i].x, pa.x, z[i].y * pa.y);
+                p = cmul_fma(p, w);
+            }
+        } else if (a.demod == DEMOD_CW) {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) u[i] = sqrtf(z[i].x * z[i].x + z[i].y * z[i].y);        // cw.rs:37
+        }
+    }
+
+    // ---------------- recursive sections: serial in-thread, scanned across threads and tiles -----
+    if (a.demod != DEMOD_NONE) {
+        for (int s = 0; s < a.nsec; ++s) {
+            const SecParam P = a.sec[s];
+            const SecTables *T = a.tabs + s;
+            // pass 1: end state of this thread's chunk from a zero start state
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) (void)sec_step(P, u[i], e0, e1);
+            // warp-level inclusive scan with constant transition powers
+            float2 E = make_float2(e0, e1);
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                const int d = 1 << l;
+                const float ox = __shfl_up_sync(0xffffffffu, E.x, d);
+                const float oy = __shfl_up_sync(0xffffffffu, E.y, d);
+                if (lane >= d) E = add2(E, mv(T->lv[l], make_float2(ox, oy)));
+            }
+            float2 X = make_float2(__shfl_up_sync(0xffffffffu, E.x, 1), __shfl_up_sync(0xffffffffu, E.y, 1));
+            if (lane == 0) X = make_float2(0.f, 0.f);
+            if (lane == 31) sh.wtot[wid] = E;
+            __syncthreads();
+            if (wid == 0) {
+                // tile aggregate, published as soon as it exists; then the look-back
+                float2 S = make_float2(0.f, 0.f);
+                float2 spre[4];
+                const float4 wstep = T->warp[1];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    spre[w] = S;
+                    S = add2(mv(wstep, S), sh.wtot[w]);
+                }
+                if (lane == 0) publish(a, tile, s, S, false);
+                const float2 sin = lookback(a, T, tile, s, lane);
+                if (lane == 0) {
+                    publish(a, tile, s, add2(mv(T->tile, sin), S), true);
+                    sh.s_tile_in = sin;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) sh.spre[w] = spre[w];
+                }
+            }
+            __syncthreads();
+            // state at the start of this thread's chunk
+            const float2 sw = add2(sh.spre[wid], mv(T->warp[wid], sh.s_tile_in));
+            const float2 st = add2(X, mv(T->lane[lane], sw));
+            float s0 = st.x, s1 = st.y;
+            // pass 2: the reference recursion from the true start state
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {
+                if (jt + i < a.n_out) {
+                    const float y = sec_step(P, u[i], s0, s1);
+                    u[i] = post_apply(P, y);
+                    if (jt + i == a.n_out - 1) a.carry_out->sec[s] = make_float2(s0, s1);
+                }
+            }
+        }
+    }
+
+    // ---------------- store -------------------------------------------------------------------
+    if (a.demod == DEMOD_NONE) {
+        float2 *out = reinterpret_cast<float2 *>(a.out);
+        const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
+        if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+            for (int i = 0; i < NPT; i += 2)
+                *reinterpret_cast<float4 *>(out + jt + i) = make_float4(z[i].x, z[i].y, z[i + 1].x, z[i + 1].y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) out[jt + i] = z[i];
+        }
+    } else {
+        float *out = reinterpret_cast<float *>(a.out);
+        const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 4 == 0);
+        if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+            for (int i = 0; i < NPT; i += 4)
+                *reinterpret_cast<float4 *>(out + jt + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) out[jt + i] = u[i];
+        }
+    }
+
+    // ---------------- end-of-call duties (last tile) ------------------------------------------
+    if (tile == a.ntiles - 1) {
+        if (a.H > 0)
+            for (int k = tid; k < a.H; k += kThreads) a.hist_out[k] = load_x(a, a.n_in - a.H + k);
+        if (tid == 0) {
+            if (!need_prev || a.n_out == 0) a.carry_out->prev = a.carry_in->prev;
+            for (int s = 0; s < kMaxSections; ++s)
+                if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
+        }
+    }
+}
+
+template <int FRONT, int R, int U>
+__global__ void __launch_bounds__(kThreads)
+chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ Shared sh;
+    unsigned mbar_parity = 0;
+    if (FRONT == FRONT_STAGED) {
+        if (threadIdx.x == 0) {
+            mbar_init(smem_u32(&sh.mbar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    if (a.serial) {
+        for (long long t = 0; t < a.ntiles; ++t) {
+            process_tile<FRONT, R, U>(a, &tmap, t, smem, sh, mbar_parity);
+            __syncthreads();
+        }
+        return;
+    }
+    for (;;) {
+        __syncthreads();                       // everyone is done with sh.tile / the staged tile
+        if (threadIdx.x == 0) sh.tile = (long long)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
+        __syncthreads();
+        const long long tile = sh.tile;
+        if (tile >= a.ntiles) break;
+        process_tile<FRONT, R, U>(a, &tmap, tile, smem, sh, mbar_parity);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host-side launcher
+// ----------------------------------------------------------------------------------------------
+typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
+
+template <int FRONT, int R, int U>
+static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U>; }
+
+chain_kernel_t select_kernel(int front, int R, int U) {
+    if (front == FRONT_DIRECT) return kptr<FRONT_DIRECT, 8, 1>();
+    if (front == FRONT_GLOBAL) return kptr<FRONT_GLOBAL, 8, 1>();
+    if (U == 1) {
+        switch (R) {
+            case 8: return kptr<FRONT_STAGED, 8, 1>();
+            case 4: return kptr<FRONT_STAGED, 4, 1>();
+            case 2: return kptr<FRONT_STAGED, 2, 1>();
+            case 1: return kptr<FRONT_STAGED, 1, 1>();
+        }
+    } else if (U == 2) {
+        switch (R) {
+            case 8: return kptr<FRONT_STAGED, 8, 2>();
+            case 4: return kptr<FRONT_STAGED, 4, 2>();
+            case 2: return kptr<FRONT_STAGED, 2, 2>();
+            case 1: return kptr<FRONT_STAGED, 1, 2>();
+        }
+    }
+    return nullptr;
+}
+
+cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads, dyn_smem);
+}
+
+cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid,
+                                size_t dyn_smem, cudaStream_t stream) {
+    k<<<grid, kThreads, dyn_smem, stream>>>(args, tmap);
+    return cudaGetLastError();
+}
+
+}  // namespace orion

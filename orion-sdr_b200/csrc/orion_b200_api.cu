@@ -1,0 +1,1039 @@
+// orion_b200_api.cu -- the C ABI (include/orion_b200.h): block handles, the reference's
+// design-time math restated on the host, launch planning, and the host<->device plumbing.
+//
+// No CPU fallback lives here: every process() call ends in a launch of the sm_100a chain
+// kernel (chain_kernels.cu); without a usable CUDA device the constructors fail.
+#include "../../include/orion_b200.h"
+#include "chain_args.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace orion {
+typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
+chain_kernel_t select_kernel(int front, int R, int U);
+cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int *ctas_per_sm);
+cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid,
+                                size_t dyn_smem, cudaStream_t stream);
+}  // namespace orion
+
+using namespace orion;
+
+// ================================================================================================
+// design-time math (host, f32 + libm) -- the reference's constructors, quirks included
+// ================================================================================================
+namespace {
+
+const float kPi  = 3.14159265358979323846f;
+const float kTau = 6.28318530717958647692f;
+const float kEps = 1.1920929e-07f;
+
+inline float maxf_rs(float a, float b) { return (a > b || b != b) ? a : b; }   // f32::max
+
+size_t fir_lowpass_ntaps(float fs, float pass_hz, float trans_hz) {            // fir.rs:17-19
+    pass_hz = maxf_rs(pass_hz, 10.0f);
+    trans_hz = maxf_rs(trans_hz, pass_hz * 0.2f);
+    float c = ceilf(fs / trans_hz);
+    size_t n = (c > 0.0f) ? (size_t)c : 0;
+    if (n < 31) n = 31;
+    return n | 1;
+}
+
+void fir_lowpass_design(float fs, float pass_hz, float *taps, size_t ntaps) {  // fir.rs:20-44
+    pass_hz = maxf_rs(pass_hz, 10.0f);
+    const float fc = pass_hz / fs;
+    const long m0 = (long)ntaps / 2;
+    for (size_t n = 0; n < ntaps; ++n) {
+        const long m = (long)n - m0;
+        float sinc;
+        if (m == 0) sinc = 2.0f * fc;
+        else {
+            const float x = kPi * (float)m;
+            sinc = (2.0f * fc) * sinf(2.0f * kPi * fc * (float)m) / x;
+        }
+        const float w = 0.5f - 0.5f * cosf(2.0f * kPi * (float)n / ((float)ntaps - 1.0f));
+        taps[n] = sinc * w;
+    }
+    float s = 0.0f;
+    for (size_t n = 0; n < ntaps; ++n) s += taps[n];
+    for (size_t n = 0; n < ntaps; ++n) taps[n] /= s;
+}
+
+float kaiser_beta(float a_db) {                                                // fir.rs:74-82
+    if (a_db > 50.0f) return 0.1102f * (a_db - 8.7f);
+    if (a_db >= 21.0f) return 0.5842f * powf(a_db - 21.0f, 0.4f) + 0.07886f * (a_db - 21.0f);
+    return 0.0f;
+}
+float bessel_i0(float x) {                                                     // fir.rs:86-99
+    const float half = 0.5f * x;
+    float term = 1.0f, sum = 1.0f;
+    for (unsigned k = 1; k <= 40; ++k) {
+        term *= half / (float)k;
+        const float t = term * term;
+        sum += t;
+        if (t < 1e-12f * sum) break;
+    }
+    return sum;
+}
+size_t kaiser_len(size_t num_taps) { return (num_taps < 3 ? 3 : num_taps) | 1; }
+void kaiser_taps(size_t m, float cutoff_norm, float stopband_db, float *taps) { // fir.rs:113-141
+    const float mid = (float)(m / 2);
+    float fc = cutoff_norm;
+    if (fc < 1e-4f) fc = 1e-4f;
+    if (fc > 0.4999f) fc = 0.4999f;
+    const float beta = kaiser_beta(stopband_db);
+    const float i0b = bessel_i0(beta);
+    for (size_t n = 0; n < m; ++n) {
+        const float d = (float)n - mid;
+        const float ideal = (d == 0.0f) ? 2.0f * fc : sinf(kTau * fc * d) / (kPi * d);
+        const float r = d / mid;
+        const float w = bessel_i0(beta * sqrtf(maxf_rs(1.0f - r * r, 0.0f))) / i0b;
+        taps[n] = ideal * w;
+    }
+    float s = 0.0f;
+    for (size_t n = 0; n < m; ++n) s += taps[n];
+    if (fabsf(s) > kEps)
+        for (size_t n = 0; n < m; ++n) taps[n] /= s;
+}
+
+void lp_biquad_design(float fs, float fc, float c[5]) {                        // iir.rs:49-71
+    const float w0 = kTau * fc / fs;
+    const float sn = sinf(w0), cs = cosf(w0);
+    const float alpha = sn / (2.0f * sqrtf(0.5f));
+    const float b0 = (1.0f - cs) * 0.5f, b1 = 1.0f - cs, b2 = (1.0f - cs) * 0.5f;
+    const float a0 = 1.0f + alpha, a1 = -2.0f * cs, a2 = 1.0f - alpha;
+    const float norm = 1.0f / a0;
+    c[0] = b0 * norm; c[1] = b1 * norm; c[2] = b2 * norm; c[3] = a1 * norm; c[4] = a2 * norm;
+}
+float dc_pole(float fs, float cut_hz) {                                        // dc.rs:15-17
+    float r = 1.0f - 2.0f * kPi * (maxf_rs(cut_hz, 0.1f) / fs);
+    if (r < 0.0f) r = 0.0f;
+    if (r > 0.9999f) r = 0.9999f;
+    return r;
+}
+float cw_alpha(float fs, float env_bw_hz) {                                    // cw.rs:15-18
+    return expf(-kTau * maxf_rs(env_bw_hz, 1.0f) / fs);
+}
+
+// ---- 2x2 helpers in f64 for the scan tables -----------------------------------------------------
+struct M2 { double a, b, c, d; };
+M2 mul(const M2 &x, const M2 &y) {
+    return { x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d };
+}
+M2 mpow(M2 base, unsigned long long e) {
+    M2 r = { 1, 0, 0, 1 };
+    while (e) {
+        if (e & 1ull) r = mul(r, base);
+        base = mul(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+float4 f4(const M2 &m) { return make_float4((float)m.a, (float)m.b, (float)m.c, (float)m.d); }
+
+M2 section_matrix(const SecParam &p) {
+    if (p.type == SEC_BIQUAD) return { -(double)p.c[3], 1.0, -(double)p.c[4], 0.0 };   // s' = A s + B x
+    if (p.type == SEC_DC) return { 0.0, 0.0, -1.0, (double)p.c[0] };                   // (x1, y1)
+    return { (double)p.c[0], 0.0, 0.0, 0.0 };                                           // one-pole
+}
+void build_tables(const SecParam &p, int npt, SecTables *t) {
+    const M2 A = section_matrix(p);
+    const unsigned long long n = (unsigned long long)npt, T = n * kThreads;
+    for (int l = 0; l < 5; ++l) t->lv[l] = f4(mpow(A, n << l));
+    for (int k = 0; k < 32; ++k) t->lane[k] = f4(mpow(A, n * k));
+    for (int w = 0; w < 4; ++w) t->warp[w] = f4(mpow(A, 32ull * n * w));
+    for (int k = 0; k < 32; ++k) t->lb[k] = f4(mpow(A, T * k));
+    t->lb32 = f4(mpow(A, T * 32ull));
+    t->tile = f4(mpow(A, T));
+}
+
+// ---- oscillator ------------------------------------------------------------------------------
+struct Osc {
+    bool on = false;
+    unsigned long long step = 0, phase0 = 0, k0 = 0;
+    float wre = 1.f, wim = 0.f, amp_delta = 0.f;
+    void set(float freq_hz, float fs, unsigned long long k_now) {
+        // keep the phase reached so far (rotator.rs:35-39), then change the step
+        phase0 = phase0 + step * (k_now - k0);
+        k0 = k_now;
+        const float phi = kTau * freq_hz / fs;                 // rotator.rs:17
+        const float c = cosf(phi), s = sinf(phi);              // the reference's f32 step w
+        const double th = atan2((double)s, (double)c);
+        const double turns = th / 6.283185307179586476925286766559;
+        if (turns >= 0.5) step = 1ull << 63;
+        else step = (unsigned long long)(long long)llround(turns * 18446744073709551616.0);
+        amp_delta = (float)(0.5 * log((double)c * (double)c + (double)s * (double)s));
+        wre = (float)cos(th);
+        wim = (float)sin(th);
+        on = true;
+    }
+    void reset_phase() { phase0 = 0; k0 = 0; }
+    NcoParam param(unsigned long long kbase) const {
+        NcoParam p;
+        p.step = step; p.phase0 = phase0; p.k0 = k0; p.kbase = kbase; p.wre = wre; p.wim = wim;
+        p.amp_delta = amp_delta; p.pad = 0.f;
+        return p;
+    }
+};
+
+// ---- staged polyphase FIR plan -------------------------------------------------------------------
+struct FirPlan {
+    int front = FRONT_DIRECT;
+    int R = 8, U = 1, Mb = 0, O = 0, P = 0, P_pad = 0, HR = 0, row_samples = 0, row_pitch = 0, rows = 0;
+    int H = 0;
+    size_t dyn_smem = 0;
+    std::vector<float> g;          // generic causal taps
+    std::vector<float2> taps2;     // [u][q][c]
+};
+
+const size_t kMaxStagedSmem = 200 * 1024;
+
+void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl) {
+    const int L = (int)taps.size();
+    pl->g.assign(L, 0.f);
+    if (fir_kind == FIR_DECIM) {               // y[n] = taps[L-1] x[n] + sum_{t<L-1} taps[t] x[n-1-t]   (fir.rs:57-66)
+        pl->g[0] = taps[L - 1];
+        for (int k = 1; k < L; ++k) pl->g[k] = taps[k - 1];
+    } else {                                   // y[n] = sum_j taps[j] x[n-j]                           (fir.rs:229-247)
+        pl->g = taps;
+    }
+    const int Lg = L;
+    const int Mi = (int)M;
+    const int U = (Mi % 2 == 0) ? 1 : 2;
+    const long long Mb = (long long)Mi * U;
+    int O = Mi * (U - 1);
+    if (O & 1) O += 1;
+    int R = 0;
+    for (int r : { 8, 4, 2, 1 })
+        if (Mb * r <= kMaxRowSamples) { R = r; break; }
+    bool staged = R > 0 && M <= 4096;
+    if (staged) {
+        const int P = (int)((Lg + 1 + O + Mb - 1) / Mb);
+        const int P_pad = ((P + R - 1) / R) * R;
+        const int HR = P_pad / R;
+        const int row_samples = (int)(R * Mb);
+        const int pad = ((row_samples / 2) % 2 == 0) ? 16 : 0;
+        const int pitch = row_samples * 8 + pad;
+        const int rows = kThreads + HR;
+        const size_t table = (size_t)U * (size_t)(Mb / 2) * (size_t)P_pad;
+        const size_t smem = (size_t)rows * pitch;
+        if (table * 2 > (size_t)kMaxTapTable || rows > 256 || smem > kMaxStagedSmem) staged = false;
+        else {
+            pl->front = FRONT_STAGED;
+            pl->R = R; pl->U = U; pl->Mb = (int)Mb; pl->O = O; pl->P = P; pl->P_pad = P_pad; pl->HR = HR;
+            pl->row_samples = row_samples; pl->row_pitch = pitch; pl->rows = rows; pl->dyn_smem = smem;
+            pl->taps2.assign(table, make_float2(0.f, 0.f));
+            for (int u = 0; u < U; ++u)
+                for (int q = 0; q < (int)(Mb / 2); ++q)
+                    for (int c = 0; c < P_pad; ++c) {
+                        const long long p = P_pad - 1 - c;
+                        const long long t0 = Mb * p + (long long)Mi * u - O + 2 * q;   // pairs with sample Mb*b + O - 2q
+                        const long long t1 = t0 - 1;                                    // ... and the one after it
+                        float2 v;
+                        v.x = (t0 >= 0 && t0 < Lg) ? pl->g[t0] : 0.f;
+                        v.y = (t1 >= 0 && t1 < Lg) ? pl->g[t1] : 0.f;
+                        pl->taps2[((size_t)u * (Mb / 2) + q) * P_pad + c] = v;
+                    }
+        }
+    }
+    // history: enough for either front, whichever one runs (the option can flip between calls)
+    long long H = Lg;                                            // direct evaluation needs Lg - 1
+    if (staged) H = std::max<long long>(H, (long long)pl->row_samples * pl->HR + pl->Mb - 2 - pl->O);
+    if (H & 1) H += 1;
+    pl->H = (int)H;
+    if (!staged || force_global) {
+        pl->front = FRONT_GLOBAL;
+        pl->R = 8; pl->U = 1; pl->Mb = 0; pl->O = 0; pl->P = pl->P_pad = pl->HR = 0;
+        pl->row_samples = pl->row_pitch = pl->rows = 0; pl->dyn_smem = 0;
+        pl->taps2.clear();
+    }
+}
+
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_t get_encode_tiled() {
+    static encode_tiled_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_t)p;
+    }
+    return fn;
+}
+
+thread_local int t_device = 0;
+
+}  // namespace
+
+// ================================================================================================
+// the block handle
+// ================================================================================================
+struct orion_b200_block {
+    // ---- specification ----
+    int in_item = ORION_B200_ITEM_C32, out_item = ORION_B200_ITEM_C32;
+    int mix = MIX_NONE;
+    int fir = FIR_NONE;
+    std::vector<float> taps;
+    size_t M = 1;
+    int demod = DEMOD_NONE;
+    int translate = 0;
+    float k = 0.f, k1 = 0.f, k2 = 0.f;
+    float fs_demod = 0.f;
+    std::vector<SecParam> secs;
+    Osc pre, post;
+    int cw_gain_sec = -1;
+    // ---- plan ----
+    FirPlan plan;
+    bool plan_dirty = true;
+    chain_kernel_t kernel = nullptr;
+    int ctas_per_sm = 1, sm_count = 1;
+    // ---- options ----
+    int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0;
+    // ---- device ----
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float *d_g = nullptr;
+    SecTables *d_tabs = nullptr;
+    float2 *d_hist[2] = { nullptr, nullptr };
+    size_t hist_cap = 0;
+    CarryState *d_carry[2] = { nullptr, nullptr };
+    int pp = 0;
+    TileLink *d_links = nullptr;
+    size_t links_cap = 0;
+    unsigned long long *d_ticket = nullptr;
+    unsigned long long ticket_base = 0;
+    unsigned epoch = 0;
+    int *d_err = nullptr;
+    int *h_err = nullptr;                 // pinned
+    void *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    // ---- counters ----
+    unsigned long long k_pre = 0, k_post = 0;     // items consumed at the input rate / demod rate since reset
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(orion_b200_block *b, int status, const char *what, cudaError_t e = cudaSuccess) {
+    if (b) {
+        b->err = what;
+        if (e != cudaSuccess) { b->err += ": "; b->err += cudaGetErrorString(e); }
+    }
+    return status;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, #call, _e); } while (0)
+
+size_t in_item_bytes(const orion_b200_block *b) { return b->in_item == ORION_B200_ITEM_C32 ? 8 : 4; }
+size_t out_item_bytes(const orion_b200_block *b) { return b->out_item == ORION_B200_ITEM_C32 ? 8 : 4; }
+
+int npt_of(const orion_b200_block *b) { return b->plan.R * b->plan.U; }
+
+// (re)build everything derived from the specification and upload it
+int finalize_plan(orion_b200_block *b) {
+    CK(cudaSetDevice(b->device));
+    if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
+    else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 8; b->plan.U = 1; }
+    b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U);
+    if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
+    CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, &b->ctas_per_sm));
+    if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
+    // FIR taps + history
+    if (b->fir != FIR_NONE) {
+        if (b->d_g) { cudaFree(b->d_g); b->d_g = nullptr; }
+        CK(cudaMalloc(&b->d_g, b->plan.g.size() * sizeof(float)));
+        CK(cudaMemcpy(b->d_g, b->plan.g.data(), b->plan.g.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if ((size_t)b->plan.H > b->hist_cap) {
+            // growing the history keeps the most recent samples at the end
+            for (int i = 0; i < 2; ++i) {
+                float2 *nh = nullptr;
+                CK(cudaMalloc(&nh, (size_t)b->plan.H * sizeof(float2)));
+                CK(cudaMemset(nh, 0, (size_t)b->plan.H * sizeof(float2)));
+                if (b->d_hist[i]) {
+                    CK(cudaMemcpy(nh + (b->plan.H - b->hist_cap), b->d_hist[i], b->hist_cap * sizeof(float2),
+                                  cudaMemcpyDeviceToDevice));
+                    cudaFree(b->d_hist[i]);
+                }
+                b->d_hist[i] = nh;
+            }
+            b->hist_cap = (size_t)b->plan.H;
+        }
+    }
+    // scan tables
+    if (!b->secs.empty()) {
+        std::vector<SecTables> tabs(b->secs.size());
+        for (size_t s = 0; s < b->secs.size(); ++s) build_tables(b->secs[s], npt_of(b), &tabs[s]);
+        if (b->d_tabs) { cudaFree(b->d_tabs); b->d_tabs = nullptr; }
+        CK(cudaMalloc(&b->d_tabs, tabs.size() * sizeof(SecTables)));
+        CK(cudaMemcpy(b->d_tabs, tabs.data(), tabs.size() * sizeof(SecTables), cudaMemcpyHostToDevice));
+    }
+    b->plan_dirty = false;
+    return ORION_B200_OK;
+}
+
+int reset_state(orion_b200_block *b) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CarryState cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.prev = make_float2(1.0f, 0.0f);                         // fm.rs:29, pm.rs:29
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMemcpy(b->d_carry[i], &cs, sizeof(cs), cudaMemcpyHostToDevice));
+        if (b->d_hist[i]) CK(cudaMemset(b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
+    }
+    b->k_pre = b->k_post = 0;
+    b->pre.reset_phase();
+    b->post.reset_phase();
+    return ORION_B200_OK;
+}
+
+int new_block(orion_b200_block **out, orion_b200_block **pb) {
+    if (!out) return ORION_B200_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return ORION_B200_ERR_NO_DEVICE; }
+    orion_b200_block *b = new (std::nothrow) orion_b200_block();
+    if (!b) return ORION_B200_ERR_ALLOC;
+    b->device = t_device;
+    *pb = b;
+    return ORION_B200_OK;
+}
+
+int init_device_side(orion_b200_block *b) {
+    CK(cudaSetDevice(b->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, b->device));
+    b->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    b->stream = b->own_stream;
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
+    CK(cudaMalloc(&b->d_ticket, sizeof(unsigned long long)));
+    CK(cudaMemset(b->d_ticket, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_err, sizeof(int)));
+    CK(cudaMemset(b->d_err, 0, sizeof(int)));
+    CK(cudaMallocHost(&b->h_err, sizeof(int)));
+    *b->h_err = 0;
+    int st = finalize_plan(b);
+    if (st != ORION_B200_OK) return st;
+    return reset_state(b);
+}
+
+int finish_create(orion_b200_block *b, orion_b200_block **out) {
+    if (b->secs.size() > (size_t)kMaxSections) { delete b; return ORION_B200_ERR_UNSUPPORTED; }
+    b->in_item = (b->demod == DEMOD_F32) ? ORION_B200_ITEM_F32 : ORION_B200_ITEM_C32;
+    b->out_item = (b->demod == DEMOD_NONE) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
+    int st = init_device_side(b);
+    if (st != ORION_B200_OK) {
+        // keep the message reachable through a static buffer, then drop the half-built block
+        static thread_local std::string last;
+        last = b->err;
+        orion_b200_block_destroy(b);
+        return st;
+    }
+    *out = b;
+    return ORION_B200_OK;
+}
+
+SecParam sec_biquad(const float c[5]) {
+    SecParam p; memset(&p, 0, sizeof(p));
+    p.type = SEC_BIQUAD; p.post_op = OP_NONE;
+    for (int i = 0; i < 5; ++i) p.c[i] = c[i];
+    return p;
+}
+SecParam sec_dc(float r) {
+    SecParam p; memset(&p, 0, sizeof(p));
+    p.type = SEC_DC; p.c[0] = r;
+    return p;
+}
+void add_lr4(orion_b200_block *b, float fs, float fc) {
+    float c[5];
+    lp_biquad_design(fs, fc, c);
+    b->secs.push_back(sec_biquad(c));
+    b->secs.push_back(sec_biquad(c));
+}
+
+void length_rules(const orion_b200_block *b, size_t n_in, size_t out_cap, size_t *consume, size_t *produce) {
+    if (b->fir != FIR_NONE && b->M > 1) {              // decim.rs:45,66-75: all input read, ceil(n/m) capped
+        *consume = n_in;
+        const size_t n_out = (n_in + b->M - 1) / b->M;
+        *produce = std::min(n_out, out_cap);
+    } else {                                           // rate-1: n = min(len(in), len(out))
+        const size_t n = std::min(n_in, out_cap);
+        *consume = n;
+        *produce = n;
+    }
+}
+
+int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out) {
+    if (b->plan_dirty) { int st = finalize_plan(b); if (st) return st; }
+    if (n_in == 0) return ORION_B200_OK;
+    CK(cudaSetDevice(b->device));
+    const int npt = npt_of(b);
+    const long long tile_items = (long long)kThreads * npt;
+    long long ntiles = ((long long)n_out + tile_items - 1) / tile_items;
+    if (ntiles < 1) ntiles = 1;
+    if (ntiles > 0x7fffffffLL) return fail(b, ORION_B200_ERR_UNSUPPORTED, "call too long");
+    const int nsec = (int)b->secs.size();
+    if (nsec > 0 && (size_t)ntiles > b->links_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        if (b->d_links) cudaFree(b->d_links);
+        size_t cap = std::max<size_t>((size_t)ntiles, 4096);
+        cap += cap / 4;
+        CK(cudaMalloc(&b->d_links, cap * kMaxSections * sizeof(TileLink)));
+        CK(cudaMemset(b->d_links, 0, cap * kMaxSections * sizeof(TileLink)));
+        b->links_cap = cap;
+        b->epoch = 0;
+    }
+    b->epoch += 1;
+    if (b->epoch >= (1u << 30)) {                      // epoch wrap: clear the links once
+        CK(cudaMemsetAsync(b->d_links, 0, b->links_cap * kMaxSections * sizeof(TileLink), b->stream));
+        b->epoch = 1;
+    }
+
+    ChainArgs *ap = new (std::nothrow) ChainArgs();    // ~11 KB: keep it off the stack
+    if (!ap) return fail(b, ORION_B200_ERR_ALLOC, "ChainArgs");
+    ChainArgs &a = *ap;
+    memset(&a, 0, sizeof(a));
+    a.in = d_in; a.out = d_out;
+    a.n_in = (long long)n_in; a.n_out = (long long)n_out;
+    a.hist_in = b->d_hist[b->pp]; a.hist_out = b->d_hist[b->pp ^ 1];
+    a.H = (b->fir != FIR_NONE) ? b->plan.H : 0;
+    a.mix = b->mix;
+    a.pre = b->pre.param(b->k_pre);
+    a.fir = b->fir; a.M = (int)b->M; a.Lg = (int)b->plan.g.size(); a.g = b->d_g;
+    a.Mb = b->plan.Mb; a.O = b->plan.O; a.P_pad = b->plan.P_pad; a.HR = b->plan.HR;
+    a.row_samples = b->plan.row_samples; a.row_pitch = b->plan.row_pitch;
+    a.demod = b->demod; a.translate = b->translate; a.k = b->k; a.k1 = b->k1; a.k2 = b->k2;
+    a.post = b->post.param(b->k_post);
+    a.nsec = nsec;
+    for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
+    a.tabs = b->d_tabs;
+    a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
+    a.links = b->d_links; a.ticket = b->d_ticket; a.ticket_base = b->ticket_base;
+    a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err;
+    if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
+
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (b->plan.front == FRONT_STAGED && b->opt_use_tma && ((reinterpret_cast<uintptr_t>(d_in) & 15u) == 0)) {
+        encode_tiled_t enc = get_encode_tiled();
+        const long long rs = b->plan.row_samples;
+        const long long off = (long long)b->plan.O - b->plan.Mb + 2;        // start sample of global row 0
+        long long row0 = 0;
+        if (off < 0) row0 = (-off + rs - 1) / rs;
+        const long long start = rs * row0 + off;
+        const long long nrows = ((long long)n_in - start) / rs;
+        if (enc && nrows >= b->plan.rows) {
+            const cuuint64_t gdim[2] = { (cuuint64_t)(2 * rs), (cuuint64_t)nrows };
+            const cuuint64_t gstr[1] = { (cuuint64_t)(rs * 8) };
+            const cuuint32_t box[2] = { (cuuint32_t)(b->plan.row_pitch / 4), (cuuint32_t)b->plan.rows };
+            const cuuint32_t estr[2] = { 1, 1 };
+            void *base = (void *)(reinterpret_cast<const char *>(d_in) + start * 8);
+            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) { a.use_tma = 1; a.tma_row0 = row0; a.tma_rows = nrows; }
+        }
+    }
+
+    int grid = 1;
+    if (!b->opt_serial) {
+        const long long resident = (long long)b->sm_count * b->ctas_per_sm;
+        grid = (int)std::min<long long>(ntiles, resident);
+    }
+    cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.dyn_smem, b->stream);
+    delete ap;
+    if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "chain kernel launch", e);
+    b->launches += 1;
+    if (!b->opt_serial) b->ticket_base += (unsigned long long)ntiles + (unsigned long long)grid;
+    b->pp ^= 1;
+    b->k_pre += n_in;
+    b->k_post += n_out;
+    return ORION_B200_OK;
+}
+
+int check_device_error(orion_b200_block *b) {
+    CK(cudaMemcpyAsync(b->h_err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    if (*b->h_err != 0) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "device watchdog tripped (code %d): inter-tile link or TMA wait timed out", *b->h_err);
+        *b->h_err = 0;
+        cudaMemset(b->d_err, 0, sizeof(int));
+        return fail(b, ORION_B200_ERR_INTERNAL, msg);
+    }
+    return ORION_B200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int orion_b200_abi_version(void) { return ORION_B200_ABI_VERSION; }
+const char *orion_b200_build_info(void) {
+    return "orion_b200 sm_100a (compute_100a) -fmad=false; kernels: chain_kernel<front,R,U>; no CPU fallback";
+}
+int orion_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int orion_b200_set_device(int ordinal) {
+    int n = orion_b200_device_count();
+    if (ordinal < 0 || ordinal >= n) return ORION_B200_ERR_NO_DEVICE;
+    t_device = ordinal;
+    return ORION_B200_OK;
+}
+const char *orion_b200_status_string(int status) {
+    switch (status) {
+        case ORION_B200_OK: return "ok";
+        case ORION_B200_ERR_INVALID: return "invalid argument";
+        case ORION_B200_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case ORION_B200_ERR_CUDA: return "CUDA error";
+        case ORION_B200_ERR_ALLOC: return "allocation failed";
+        case ORION_B200_ERR_UNSUPPORTED: return "unsupported configuration";
+        case ORION_B200_ERR_INTERNAL: return "internal error";
+    }
+    return "unknown status";
+}
+int orion_b200_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return ORION_B200_ERR_INVALID;
+    *ptr = nullptr;
+    if (orion_b200_device_count() <= 0) return ORION_B200_ERR_NO_DEVICE;
+    if (cudaMallocHost(ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return ORION_B200_ERR_ALLOC; }
+    return ORION_B200_OK;
+}
+void orion_b200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// ---- design helpers [host-only] ------------------------------------------------------------------
+size_t orion_b200_fir_lowpass_design(float fs, float pass_hz, float trans_hz, float *taps, size_t cap) {
+    const size_t n = fir_lowpass_ntaps(fs, pass_hz, trans_hz);
+    if (taps && cap >= n) fir_lowpass_design(fs, pass_hz, taps, n);
+    return n;
+}
+size_t orion_b200_kaiser_lowpass_taps(size_t num_taps, float cutoff_norm, float stopband_db, float *taps, size_t cap) {
+    const size_t m = kaiser_len(num_taps);
+    if (taps && cap >= m) kaiser_taps(m, cutoff_norm, stopband_db, taps);
+    return m;
+}
+float orion_b200_kaiser_transition_norm(size_t num_taps, float stopband_db) {   // fir.rs:147-150
+    const float m = (float)kaiser_len(num_taps);
+    return (maxf_rs(stopband_db, 21.0f) - 8.0f) / (14.36f * m);
+}
+size_t orion_b200_kaiser_num_taps(float transition_norm, float stopband_db) {   // fir.rs:154-157
+    const float m = ceilf((maxf_rs(stopband_db, 21.0f) - 8.0f) / (14.36f * maxf_rs(transition_norm, 1e-4f)));
+    return ((size_t)maxf_rs(m, 3.0f)) | 1;
+}
+void orion_b200_lp_biquad_design(float fs, float fc, float coeffs[5]) { lp_biquad_design(fs, fc, coeffs); }
+float orion_b200_dc_pole(float fs, float cut_hz) { return dc_pole(fs, cut_hz); }
+float orion_b200_cw_alpha(float fs, float env_bw_hz) { return cw_alpha(fs, env_bw_hz); }
+
+// ---- constructors ------------------------------------------------------------------------------
+#define NEW_BLOCK() orion_b200_block *b = nullptr; { int _s = new_block(out, &b); if (_s) return _s; }
+
+int orion_b200_fir_decimator_create_taps(const float *taps, size_t ntaps, size_t m, orion_b200_block **out) {
+    if (!taps || ntaps == 0) return ORION_B200_ERR_INVALID;
+    NEW_BLOCK();
+    b->fir = FIR_DECIM;
+    b->taps.assign(taps, taps + ntaps);
+    b->M = m < 1 ? 1 : m;                                           // decim.rs:30
+    return finish_create(b, out);
+}
+int orion_b200_fir_decimator_create(float fs, size_t m, float cutoff_hz, float trans_hz, orion_b200_block **out) {
+    const size_t n = fir_lowpass_ntaps(fs, cutoff_hz, trans_hz);
+    std::vector<float> t(n);
+    fir_lowpass_design(fs, cutoff_hz, t.data(), n);
+    return orion_b200_fir_decimator_create_taps(t.data(), n, m, out);
+}
+int orion_b200_fir_lowpass_iq_create_taps(const float *taps, size_t ntaps, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->fir = FIR_IQ;
+    if (!taps || ntaps == 0) b->taps.assign(1, 1.0f);               // fir.rs:193-196: empty -> identity
+    else b->taps.assign(taps, taps + ntaps);
+    b->M = 1;
+    return finish_create(b, out);
+}
+int orion_b200_fir_lowpass_iq_create(size_t num_taps, float cutoff_norm, float stopband_db, orion_b200_block **out) {
+    const size_t m = kaiser_len(num_taps);
+    std::vector<float> t(m);
+    kaiser_taps(m, cutoff_norm, stopband_db, t.data());
+    return orion_b200_fir_lowpass_iq_create_taps(t.data(), m, out);
+}
+
+int orion_b200_rotator_create(float freq_hz, float fs, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->mix = MIX_ROTATE;
+    b->pre.set(freq_hz, fs, 0);
+    return finish_create(b, out);
+}
+int orion_b200_rotator_usb_create(float freq_hz, float fs, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->demod = DEMOD_USB;
+    b->post.set(freq_hz, fs, 0);
+    return finish_create(b, out);
+}
+int orion_b200_nco_mixer_create(float freq_hz, float fs, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->mix = MIX_NCO;
+    b->pre.set(freq_hz, fs, 0);
+    return finish_create(b, out);
+}
+int orion_b200_oscillator_set_freq(orion_b200_block *b, float freq_hz, float fs) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    if (b->pre.on) b->pre.set(freq_hz, fs, b->k_pre);
+    else if (b->post.on) b->post.set(freq_hz, fs, b->k_post);
+    else return fail(b, ORION_B200_ERR_INVALID, "block has no oscillator");
+    return ORION_B200_OK;
+}
+int orion_b200_oscillator_reset_phase(orion_b200_block *b) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    // rotator.rs:28-31: z = 1, ctr = 0 -> the call counter restarts as well
+    if (b->pre.on) { b->pre.reset_phase(); b->k_pre = 0; }
+    if (b->post.on) { b->post.reset_phase(); b->k_post = 0; }
+    return ORION_B200_OK;
+}
+
+int orion_b200_iir_cascade_create(const float *sos, size_t nsections, orion_b200_block **out) {
+    if (!sos || nsections == 0 || nsections > (size_t)kMaxSections) return ORION_B200_ERR_INVALID;
+    NEW_BLOCK();
+    b->demod = DEMOD_F32;
+    for (size_t s = 0; s < nsections; ++s) b->secs.push_back(sec_biquad(sos + 5 * s));
+    return finish_create(b, out);
+}
+int orion_b200_biquad_create(float b0, float b1, float b2, float a1, float a2, orion_b200_block **out) {
+    const float c[5] = { b0, b1, b2, a1, a2 };
+    return orion_b200_iir_cascade_create(c, 1, out);
+}
+int orion_b200_lp_cascade_create(float fs, float fc, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->demod = DEMOD_F32;
+    add_lr4(b, fs, fc);
+    return finish_create(b, out);
+}
+int orion_b200_lp_dc_cascade_create(float fs, float lp_fc, float dc_cut_hz, int map_sqrt, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->demod = DEMOD_F32;
+    add_lr4(b, fs, lp_fc);
+    if (map_sqrt) b->secs.back().post_op = OP_SQRT;                 // iir.rs:170-186 process_mapped(x, sqrt)
+    b->secs.push_back(sec_dc(dc_pole(fs, dc_cut_hz)));
+    return finish_create(b, out);
+}
+int orion_b200_dc_blocker_create(float fs, float cut_hz, orion_b200_block **out) {
+    NEW_BLOCK();
+    b->demod = DEMOD_F32;
+    b->secs.push_back(sec_dc(dc_pole(fs, cut_hz)));
+    return finish_create(b, out);
+}
+
+static void demod_setup(orion_b200_block *b, int demod, float fs, float p0, float p1, float audio_bw_hz) {
+    b->demod = demod;
+    b->fs_demod = fs;
+    switch (demod) {
+        case DEMOD_FM:                                              // fm.rs:22-32
+            b->k = 1.0f / maxf_rs(p0, 1.0f);
+            add_lr4(b, fs, audio_bw_hz * 0.9f);
+            break;
+        case DEMOD_PM:                                              // pm.rs:22-32
+            b->k = p0;
+            add_lr4(b, fs, audio_bw_hz * 0.9f);
+            break;
+        case DEMOD_AM:                                              // am.rs:24-30 (PowerSqrt)
+            add_lr4(b, fs, audio_bw_hz * 0.9f);
+            b->secs.back().post_op = OP_SQRT;
+            b->secs.push_back(sec_dc(dc_pole(fs, 2.0f)));
+            break;
+        case DEMOD_AM_ABS:                                          // am.rs:33-36
+            b->k1 = p0; b->k2 = p1;
+            add_lr4(b, fs, audio_bw_hz * 0.9f);
+            b->secs.push_back(sec_dc(dc_pole(fs, 2.0f)));
+            break;
+        case DEMOD_SSB:                                             // ssb.rs:15-20
+            b->post.set(p0, fs, 0);
+            add_lr4(b, fs, audio_bw_hz * 0.9f);
+            b->secs.push_back(sec_dc(dc_pole(fs, 2.0f)));
+            break;
+        case DEMOD_CW: {                                            // cw.rs:15-24
+            SecParam p; memset(&p, 0, sizeof(p));
+            const float a = cw_alpha(fs, p0);
+            p.type = SEC_ONEPOLE; p.c[0] = a; p.c[1] = 1.0f - a;
+            p.post_op = OP_SCALE; p.post_scale = (p1 == 0.0f) ? 1.0f : p1;
+            b->cw_gain_sec = (int)b->secs.size();
+            b->secs.push_back(p);
+            break;
+        }
+        case DEMOD_USB:
+            b->post.set(p0, fs, 0);
+            break;
+        default: break;
+    }
+}
+
+int orion_b200_fm_demod_create(float fs, float dev_hz, float audio_bw_hz, orion_b200_block **out) {
+    NEW_BLOCK();
+    demod_setup(b, DEMOD_FM, fs, dev_hz, 0.f, audio_bw_hz);
+    return finish_create(b, out);
+}
+int orion_b200_fm_demod_with_translate(orion_b200_block *b, float freq_hz) {
+    if (!b || b->demod != DEMOD_FM) return ORION_B200_ERR_INVALID;
+    b->translate = 1;
+    b->post = Osc();
+    b->post.set(freq_hz, b->fs_demod, 0);                           // fm.rs:35: a fresh Rotator
+    b->k_post = 0;
+    return ORION_B200_OK;
+}
+int orion_b200_pm_demod_create(float fs, float k, float audio_bw_hz, orion_b200_block **out) {
+    NEW_BLOCK();
+    demod_setup(b, DEMOD_PM, fs, k, 0.f, audio_bw_hz);
+    return finish_create(b, out);
+}
+int orion_b200_am_demod_create(float fs, float audio_bw_hz, orion_b200_block **out) {
+    NEW_BLOCK();
+    demod_setup(b, DEMOD_AM, fs, 0.f, 0.f, audio_bw_hz);
+    return finish_create(b, out);
+}
+int orion_b200_am_demod_with_abs_approx(orion_b200_block *b, float k1, float k2) {
+    if (!b || (b->demod != DEMOD_AM && b->demod != DEMOD_AM_ABS)) return ORION_B200_ERR_INVALID;
+    b->demod = DEMOD_AM_ABS;
+    b->k1 = k1; b->k2 = k2;
+    for (auto &s : b->secs) if (s.post_op == OP_SQRT) s.post_op = OP_NONE;
+    return ORION_B200_OK;
+}
+int orion_b200_ssb_demod_create(float fs, float bfo_hz, float audio_bw_hz, orion_b200_block **out) {
+    NEW_BLOCK();
+    demod_setup(b, DEMOD_SSB, fs, bfo_hz, 0.f, audio_bw_hz);
+    return finish_create(b, out);
+}
+int orion_b200_cw_demod_create(float sample_rate, float tone_hz, float env_bw_hz, orion_b200_block **out) {
+    (void)tone_hz;                                                  // cw.rs:16: unused by the reference too
+    NEW_BLOCK();
+    demod_setup(b, DEMOD_CW, sample_rate, env_bw_hz, 1.0f, 0.f);
+    return finish_create(b, out);
+}
+int orion_b200_cw_demod_set_gain(orion_b200_block *b, float gain) {
+    if (!b || b->demod != DEMOD_CW || b->cw_gain_sec < 0) return ORION_B200_ERR_INVALID;
+    b->secs[b->cw_gain_sec].post_scale = gain;
+    return ORION_B200_OK;
+}
+
+int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block **out) {
+    if (!spec || spec->struct_size != sizeof(orion_b200_chain_spec)) return ORION_B200_ERR_INVALID;
+    if (spec->fir != FIR_NONE && (!spec->taps || spec->ntaps == 0)) return ORION_B200_ERR_INVALID;
+    if (spec->demod < 0 || spec->demod > DEMOD_USB) return ORION_B200_ERR_INVALID;
+    NEW_BLOCK();
+    b->mix = spec->mix;
+    if (spec->mix != MIX_NONE) b->pre.set(spec->mix_freq_hz, spec->mix_fs, 0);
+    b->fir = spec->fir;
+    if (spec->fir != FIR_NONE) {
+        b->taps.assign(spec->taps, spec->taps + spec->ntaps);
+        b->M = spec->decim < 1 ? 1 : spec->decim;
+    }
+    demod_setup(b, spec->demod, spec->fs_demod, spec->p0, spec->p1, spec->audio_bw_hz);
+    if (spec->demod == DEMOD_FM && spec->translate) {
+        b->translate = 1;
+        b->post.set(spec->translate_hz, spec->fs_demod, 0);
+    }
+    if (spec->n_post) {
+        if (!spec->post_sos || spec->demod == DEMOD_NONE) { delete b; return ORION_B200_ERR_INVALID; }
+        for (size_t s = 0; s < spec->n_post; ++s) b->secs.push_back(sec_biquad(spec->post_sos + 5 * s));
+    }
+    return finish_create(b, out);
+}
+
+// ---- common operations ---------------------------------------------------------------------------
+void orion_b200_block_destroy(orion_b200_block *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_g); cudaFree(b->d_tabs);
+    cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
+    cudaFree(b->d_carry[0]); cudaFree(b->d_carry[1]);
+    cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err);
+    cudaFree(b->d_in); cudaFree(b->d_out);
+    if (b->h_err) cudaFreeHost(b->h_err);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    cudaGetLastError();
+    delete b;
+}
+int orion_b200_block_reset(orion_b200_block *b) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    return reset_state(b);
+}
+const char *orion_b200_block_last_error(const orion_b200_block *b) { return b ? b->err.c_str() : "null block"; }
+int orion_b200_block_in_item(const orion_b200_block *b) { return b ? b->in_item : 0; }
+int orion_b200_block_out_item(const orion_b200_block *b) { return b ? b->out_item : 0; }
+size_t orion_b200_block_decimation(const orion_b200_block *b) { return (b && b->fir != FIR_NONE) ? b->M : 1; }
+orion_b200_work_report orion_b200_block_plan(const orion_b200_block *b, size_t n_in, size_t out_cap) {
+    orion_b200_work_report wr = { 0, 0 };
+    if (b) length_rules(b, n_in, out_cap, &wr.in_read, &wr.out_written);
+    return wr;
+}
+
+int orion_b200_block_process_dev(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t out_cap,
+                                 size_t *in_read, size_t *out_written) {
+    if (in_read) *in_read = 0;
+    if (out_written) *out_written = 0;
+    if (!b || (n_in && !d_in) || (out_cap && !d_out)) return b ? fail(b, ORION_B200_ERR_INVALID, "null buffer") : ORION_B200_ERR_INVALID;
+    size_t consume, produce;
+    length_rules(b, n_in, out_cap, &consume, &produce);
+    const int st = launch(b, d_in, consume, d_out, produce);
+    if (st != ORION_B200_OK) return st;
+    if (in_read) *in_read = consume;
+    if (out_written) *out_written = produce;
+    return ORION_B200_OK;
+}
+
+int orion_b200_block_process(orion_b200_block *b, const void *in, size_t n_in, void *out, size_t out_cap,
+                             size_t *in_read, size_t *out_written) {
+    if (in_read) *in_read = 0;
+    if (out_written) *out_written = 0;
+    if (!b || (n_in && !in) || (out_cap && !out)) return b ? fail(b, ORION_B200_ERR_INVALID, "null buffer") : ORION_B200_ERR_INVALID;
+    size_t consume, produce;
+    length_rules(b, n_in, out_cap, &consume, &produce);
+    if (consume == 0) return ORION_B200_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t ib = consume * in_item_bytes(b), ob = produce * out_item_bytes(b);
+    if (ib > b->d_in_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_in); b->d_in = nullptr; b->d_in_cap = 0;
+        const size_t cap = ib + ib / 4 + 256;
+        CK(cudaMalloc(&b->d_in, cap));
+        b->d_in_cap = cap;
+    }
+    if (ob > b->d_out_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_out); b->d_out = nullptr; b->d_out_cap = 0;
+        const size_t cap = ob + ob / 4 + 256;
+        CK(cudaMalloc(&b->d_out, cap));
+        b->d_out_cap = cap;
+    }
+    CK(cudaMemcpyAsync(b->d_in, in, ib, cudaMemcpyHostToDevice, b->stream));
+    const int st = launch(b, b->d_in, consume, b->d_out, produce);
+    if (st != ORION_B200_OK) return st;
+    if (ob) CK(cudaMemcpyAsync(out, b->d_out, ob, cudaMemcpyDeviceToHost, b->stream));
+    const int es = check_device_error(b);                          // also synchronises the stream
+    if (es != ORION_B200_OK) return es;
+    if (in_read) *in_read = consume;
+    if (out_written) *out_written = produce;
+    return ORION_B200_OK;
+}
+
+int orion_b200_block_synchronize(orion_b200_block *b) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    CK(cudaSetDevice(b->device));
+    return check_device_error(b);
+}
+int orion_b200_block_set_stream(orion_b200_block *b, void *cuda_stream) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return ORION_B200_OK;
+}
+
+int orion_b200_fir_lowpass_iq_filter_aligned(orion_b200_block *b, orion_b200_c32 *io, size_t n) {
+    if (!b || b->fir != FIR_IQ || b->M != 1 || b->demod != DEMOD_NONE || b->mix != MIX_NONE)
+        return b ? fail(b, ORION_B200_ERR_INVALID, "filter_aligned needs a FirLowpassIq block") : ORION_B200_ERR_INVALID;
+    if (n && !io) return fail(b, ORION_B200_ERR_INVALID, "null buffer");
+    // fir.rs:260-276: reset, prime with the first d samples, then emit n outputs while feeding
+    // io[i+d] (zeros past the end)  ==  stream io ++ zeros(d) through the filter, drop d outputs.
+    int st = reset_state(b);
+    if (st != ORION_B200_OK || n == 0) return st;
+    const size_t d = (b->taps.size() - 1) / 2;                      // fir.rs:216-218
+    const size_t tot = n + d;
+    float2 *din = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&din, tot * sizeof(float2)));
+    if (cudaMalloc(&dout, tot * sizeof(float2)) != cudaSuccess) { cudaFree(din); return fail(b, ORION_B200_ERR_ALLOC, "filter_aligned"); }
+    cudaMemsetAsync(din, 0, tot * sizeof(float2), b->stream);
+    cudaMemcpyAsync(din, io, n * sizeof(float2), cudaMemcpyHostToDevice, b->stream);
+    st = launch(b, din, tot, dout, tot);
+    if (st == ORION_B200_OK) {
+        cudaMemcpyAsync(io, dout + d, n * sizeof(float2), cudaMemcpyDeviceToHost, b->stream);
+        st = check_device_error(b);
+    }
+    cudaStreamSynchronize(b->stream);
+    cudaFree(din); cudaFree(dout);
+    return st;
+}
+
+int orion_b200_block_set_option(orion_b200_block *b, int option, double value) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    const int v = value != 0.0;
+    switch (option) {
+        case ORION_B200_OPT_FIR_GLOBAL:
+            if (b->opt_force_global != v) { b->opt_force_global = v; b->plan_dirty = true; }
+            break;
+        case ORION_B200_OPT_USE_TMA: b->opt_use_tma = v; break;
+        case ORION_B200_OPT_SERIAL_TILES: b->opt_serial = v; break;
+        default: return fail(b, ORION_B200_ERR_INVALID, "unknown option");
+    }
+    if (b->plan_dirty) {
+        // the history length may change with the front; finalize now so errors surface here
+        CK(cudaSetDevice(b->device));
+        CK(cudaStreamSynchronize(b->stream));
+        return finalize_plan(b);
+    }
+    return ORION_B200_OK;
+}
+
+size_t orion_b200_block_get_state(orion_b200_block *b, float *state, size_t cap) {
+    const size_t n = 4 + 2 * kMaxSections;
+    if (!b || !state || cap < n) return n;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    CarryState cs;
+    if (cudaMemcpy(&cs, b->d_carry[b->pp], sizeof(cs), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    state[0] = cs.prev.x; state[1] = cs.prev.y;
+    state[2] = (float)(b->k_pre & 0xFFFFFFull); state[3] = (float)(b->k_post & 0xFFFFFFull);
+    for (int s = 0; s < kMaxSections; ++s) { state[4 + 2 * s] = cs.sec[s].x; state[5 + 2 * s] = cs.sec[s].y; }
+    return n;
+}
+
+uint64_t orion_b200_block_launch_count(const orion_b200_block *b) { return b ? b->launches : 0; }
+
+// plan introspection for the host-logic tests [host-only]: fills `info` (12 ints) and, when
+// `table` has room, the polyphase tap table as floats.  Returns the table length in floats.
+size_t orion_b200_debug_fir_plan(int fir_kind, const float *taps, size_t ntaps, size_t m, int info[12],
+                                 float *table, size_t cap, float *g, size_t gcap) {
+    if (!taps || !ntaps || !info) return 0;
+    FirPlan pl;
+    std::vector<float> t(taps, taps + ntaps);
+    plan_fir(fir_kind, t, m < 1 ? 1 : m, false, &pl);
+    info[0] = pl.front; info[1] = pl.R; info[2] = pl.U; info[3] = pl.Mb; info[4] = pl.O; info[5] = pl.P;
+    info[6] = pl.P_pad; info[7] = pl.HR; info[8] = pl.row_samples; info[9] = pl.row_pitch; info[10] = pl.rows;
+    info[11] = pl.H;
+    const size_t nf = pl.taps2.size() * 2;
+    if (table && cap >= nf && nf) memcpy(table, pl.taps2.data(), nf * sizeof(float));
+    if (g && gcap >= pl.g.size()) memcpy(g, pl.g.data(), pl.g.size() * sizeof(float));
+    return nf;
+}
+// scan tables for one section [host-only]; `tables` receives sizeof(SecTables)/4 floats
+size_t orion_b200_debug_scan_tables(int type, const float c[5], int npt, float *tables, size_t cap) {
+    const size_t nf = sizeof(SecTables) / sizeof(float);
+    if (!tables || cap < nf) return nf;
+    SecParam p; memset(&p, 0, sizeof(p));
+    p.type = type;
+    for (int i = 0; i < 5; ++i) p.c[i] = c[i];
+    SecTables t;
+    build_tables(p, npt, &t);
+    memcpy(tables, &t, sizeof(t));
+    return nf;
+}
+
+}  // extern "C"

@@ -1,0 +1,527 @@
+"""orion_b200 -- ctypes binding of liborion_b200.so (include/orion_b200.h).
+
+Host-side mirror of the reference's block interface for the sample-stream front end:
+every class below corresponds to one reference `impl Block` (src/core.rs:12-22) and keeps
+its constructor arguments and its `process(input, output) -> WorkReport` contract.  All
+arithmetic happens in the sm_100a kernels behind the C ABI; there is no CPU fallback --
+constructing a block without a CUDA device raises `OrionB200Error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import namedtuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))           # .../orion-sdr_b200
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "liborion_b200.so")
+
+WorkReport = namedtuple("WorkReport", ["in_read", "out_written"])   # src/core.rs:7-10
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED, ERR_INTERNAL = range(7)
+ITEM_F32, ITEM_C32 = 1, 2
+MIX_NONE, MIX_ROTATE, MIX_NCO = 0, 1, 2
+FIR_NONE, FIR_DECIM, FIR_IQ = 0, 1, 2
+DEMOD_NONE, DEMOD_FM, DEMOD_PM, DEMOD_AM, DEMOD_AM_ABS, DEMOD_SSB, DEMOD_CW, DEMOD_USB = range(8)
+OPT_FIR_GLOBAL, OPT_USE_TMA, OPT_SERIAL_TILES = 1, 2, 3
+
+
+class OrionB200Error(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__(f"orion_b200 status {status}: {msg}")
+
+
+class _WR(C.Structure):
+    _fields_ = [("in_read", C.c_size_t), ("out_written", C.c_size_t)]
+
+
+class ChainSpec(C.Structure):
+    """orion_b200_chain_spec (include/orion_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("mix", C.c_int32), ("mix_freq_hz", C.c_float), ("mix_fs", C.c_float),
+        ("fir", C.c_int32), ("taps", C.POINTER(C.c_float)), ("ntaps", C.c_size_t), ("decim", C.c_size_t),
+        ("demod", C.c_int32), ("fs_demod", C.c_float), ("p0", C.c_float), ("p1", C.c_float),
+        ("audio_bw_hz", C.c_float), ("translate", C.c_int32), ("translate_hz", C.c_float),
+        ("post_sos", C.POINTER(C.c_float)), ("n_post", C.c_size_t),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    f, sz, vp, i, d = C.c_float, C.c_size_t, C.c_void_p, C.c_int, C.c_double
+    pp = C.POINTER(vp)
+    psz = C.POINTER(sz)
+
+    def sig(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig("orion_b200_abi_version", i)
+    sig("orion_b200_build_info", C.c_char_p)
+    sig("orion_b200_device_count", i)
+    sig("orion_b200_set_device", i, i)
+    sig("orion_b200_status_string", C.c_char_p, i)
+    sig("orion_b200_host_alloc", i, pp, sz)
+    sig("orion_b200_host_free", None, vp)
+    sig("orion_b200_fir_lowpass_design", sz, f, f, f, vp, sz)
+    sig("orion_b200_kaiser_lowpass_taps", sz, sz, f, f, vp, sz)
+    sig("orion_b200_kaiser_transition_norm", f, sz, f)
+    sig("orion_b200_kaiser_num_taps", sz, f, f)
+    sig("orion_b200_lp_biquad_design", None, f, f, vp)
+    sig("orion_b200_dc_pole", f, f, f)
+    sig("orion_b200_cw_alpha", f, f, f)
+    sig("orion_b200_fir_decimator_create", i, f, sz, f, f, pp)
+    sig("orion_b200_fir_decimator_create_taps", i, vp, sz, sz, pp)
+    sig("orion_b200_fir_lowpass_iq_create", i, sz, f, f, pp)
+    sig("orion_b200_fir_lowpass_iq_create_taps", i, vp, sz, pp)
+    sig("orion_b200_fir_lowpass_iq_filter_aligned", i, vp, vp, sz)
+    sig("orion_b200_rotator_create", i, f, f, pp)
+    sig("orion_b200_rotator_usb_create", i, f, f, pp)
+    sig("orion_b200_nco_mixer_create", i, f, f, pp)
+    sig("orion_b200_oscillator_set_freq", i, vp, f, f)
+    sig("orion_b200_oscillator_reset_phase", i, vp)
+    sig("orion_b200_biquad_create", i, f, f, f, f, f, pp)
+    sig("orion_b200_lp_cascade_create", i, f, f, pp)
+    sig("orion_b200_lp_dc_cascade_create", i, f, f, f, i, pp)
+    sig("orion_b200_dc_blocker_create", i, f, f, pp)
+    sig("orion_b200_iir_cascade_create", i, vp, sz, pp)
+    sig("orion_b200_fm_demod_create", i, f, f, f, pp)
+    sig("orion_b200_fm_demod_with_translate", i, vp, f)
+    sig("orion_b200_pm_demod_create", i, f, f, f, pp)
+    sig("orion_b200_am_demod_create", i, f, f, pp)
+    sig("orion_b200_am_demod_with_abs_approx", i, vp, f, f)
+    sig("orion_b200_ssb_demod_create", i, f, f, f, pp)
+    sig("orion_b200_cw_demod_create", i, f, f, f, pp)
+    sig("orion_b200_cw_demod_set_gain", i, vp, f)
+    sig("orion_b200_chain_create", i, C.POINTER(ChainSpec), pp)
+    sig("orion_b200_block_destroy", None, vp)
+    sig("orion_b200_block_reset", i, vp)
+    sig("orion_b200_block_last_error", C.c_char_p, vp)
+    sig("orion_b200_block_in_item", i, vp)
+    sig("orion_b200_block_out_item", i, vp)
+    sig("orion_b200_block_decimation", sz, vp)
+    sig("orion_b200_block_plan", _WR, vp, sz, sz)
+    sig("orion_b200_block_process", i, vp, vp, sz, vp, sz, psz, psz)
+    sig("orion_b200_block_process_dev", i, vp, vp, sz, vp, sz, psz, psz)
+    sig("orion_b200_block_synchronize", i, vp)
+    sig("orion_b200_block_set_stream", i, vp, vp)
+    sig("orion_b200_block_set_option", i, vp, i, d)
+    sig("orion_b200_block_get_state", sz, vp, vp, sz)
+    sig("orion_b200_block_launch_count", C.c_uint64, vp)
+    sig("orion_b200_debug_fir_plan", sz, i, vp, sz, sz, vp, vp, sz, vp, sz)
+    sig("orion_b200_debug_scan_tables", sz, i, vp, i, vp, sz)
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "orion_b200_abi_version", "orion_b200_build_info", "orion_b200_device_count", "orion_b200_set_device",
+    "orion_b200_status_string", "orion_b200_host_alloc", "orion_b200_host_free",
+    "orion_b200_fir_lowpass_design", "orion_b200_kaiser_lowpass_taps", "orion_b200_kaiser_transition_norm",
+    "orion_b200_kaiser_num_taps", "orion_b200_lp_biquad_design", "orion_b200_dc_pole", "orion_b200_cw_alpha",
+    "orion_b200_fir_decimator_create", "orion_b200_fir_decimator_create_taps", "orion_b200_fir_lowpass_iq_create",
+    "orion_b200_fir_lowpass_iq_create_taps", "orion_b200_fir_lowpass_iq_filter_aligned",
+    "orion_b200_rotator_create", "orion_b200_rotator_usb_create", "orion_b200_nco_mixer_create",
+    "orion_b200_oscillator_set_freq", "orion_b200_oscillator_reset_phase", "orion_b200_biquad_create",
+    "orion_b200_lp_cascade_create", "orion_b200_lp_dc_cascade_create", "orion_b200_dc_blocker_create",
+    "orion_b200_iir_cascade_create", "orion_b200_fm_demod_create", "orion_b200_fm_demod_with_translate",
+    "orion_b200_pm_demod_create", "orion_b200_am_demod_create", "orion_b200_am_demod_with_abs_approx",
+    "orion_b200_ssb_demod_create", "orion_b200_cw_demod_create", "orion_b200_cw_demod_set_gain",
+    "orion_b200_chain_create", "orion_b200_block_destroy", "orion_b200_block_reset",
+    "orion_b200_block_last_error", "orion_b200_block_in_item", "orion_b200_block_out_item",
+    "orion_b200_block_decimation", "orion_b200_block_plan", "orion_b200_block_process",
+    "orion_b200_block_process_dev", "orion_b200_block_synchronize", "orion_b200_block_set_stream",
+    "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
+    "orion_b200_debug_fir_plan", "orion_b200_debug_scan_tables",
+]
+
+
+def _check(status, handle=None):
+    if status != OK:
+        L = lib()
+        msg = L.orion_b200_status_string(status).decode()
+        if handle:
+            extra = L.orion_b200_block_last_error(handle)
+            if extra:
+                msg += " -- " + extra.decode()
+        raise OrionB200Error(status, msg)
+
+
+def device_count() -> int:
+    return lib().orion_b200_device_count()
+
+
+def set_device(ordinal: int) -> None:
+    _check(lib().orion_b200_set_device(int(ordinal)))
+
+
+# ---- design helpers (host-only; reference design math, quirks included) ---------------------------
+def fir_lowpass_design(fs, pass_hz, trans_hz) -> np.ndarray:          # src/dsp/fir.rs:16-44
+    L = lib()
+    n = L.orion_b200_fir_lowpass_design(fs, pass_hz, trans_hz, None, 0)
+    t = np.zeros(n, np.float32)
+    L.orion_b200_fir_lowpass_design(fs, pass_hz, trans_hz, t.ctypes.data, n)
+    return t
+
+
+def kaiser_lowpass_taps(num_taps, cutoff_norm, stopband_db) -> np.ndarray:   # src/dsp/fir.rs:113-141
+    L = lib()
+    n = L.orion_b200_kaiser_lowpass_taps(num_taps, cutoff_norm, stopband_db, None, 0)
+    t = np.zeros(n, np.float32)
+    L.orion_b200_kaiser_lowpass_taps(num_taps, cutoff_norm, stopband_db, t.ctypes.data, n)
+    return t
+
+
+def kaiser_transition_norm(num_taps, stopband_db) -> float:
+    return float(lib().orion_b200_kaiser_transition_norm(num_taps, stopband_db))
+
+
+def kaiser_num_taps(transition_norm, stopband_db) -> int:
+    return int(lib().orion_b200_kaiser_num_taps(transition_norm, stopband_db))
+
+
+def lp_biquad_design(fs, fc) -> np.ndarray:                            # src/dsp/iir.rs:49-71
+    c = np.zeros(5, np.float32)
+    lib().orion_b200_lp_biquad_design(fs, fc, c.ctypes.data)
+    return c
+
+
+def dc_pole(fs, cut_hz) -> float:
+    return float(lib().orion_b200_dc_pole(fs, cut_hz))
+
+
+def cw_alpha(fs, env_bw_hz) -> float:
+    return float(lib().orion_b200_cw_alpha(fs, env_bw_hz))
+
+
+def debug_fir_plan(fir_kind, taps, m):
+    """Host-side launch plan of the staged FIR (tests only)."""
+    L = lib()
+    taps = np.ascontiguousarray(taps, np.float32)
+    info = (C.c_int * 12)()
+    g = np.zeros(len(taps), np.float32)
+    nf = L.orion_b200_debug_fir_plan(fir_kind, taps.ctypes.data, len(taps), m, info, None, 0, g.ctypes.data, len(g))
+    table = np.zeros(max(nf, 1), np.float32)
+    L.orion_b200_debug_fir_plan(fir_kind, taps.ctypes.data, len(taps), m, info, table.ctypes.data, nf,
+                                g.ctypes.data, len(g))
+    keys = ["front", "R", "U", "Mb", "O", "P", "P_pad", "HR", "row_samples", "row_pitch", "rows", "H"]
+    plan = dict(zip(keys, list(info)))
+    plan["table"] = table[:nf].reshape(-1, 2)
+    plan["g"] = g
+    return plan
+
+
+def debug_scan_tables(sec_type, coeffs, npt):
+    L = lib()
+    c = np.zeros(5, np.float32)
+    c[:len(coeffs)] = coeffs
+    nf = L.orion_b200_debug_scan_tables(sec_type, c.ctypes.data, npt, None, 0)
+    t = np.zeros(nf, np.float32)
+    L.orion_b200_debug_scan_tables(sec_type, c.ctypes.data, npt, t.ctypes.data, nf)
+    m = t.reshape(-1, 4)
+    return {"lv": m[0:5], "lane": m[5:37], "warp": m[37:41], "lb": m[41:73], "lb32": m[73], "tile": m[74]}
+
+
+_DT = {ITEM_F32: np.float32, ITEM_C32: np.complex64}
+
+
+class Block:
+    """One reference `Block` instance living on the GPU (src/core.rs:12-22)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        L = lib()
+        self.in_dtype = _DT[L.orion_b200_block_in_item(self._h)]
+        self.out_dtype = _DT[L.orion_b200_block_out_item(self._h)]
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orion_b200_block_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Block::process ---------------------------------------------------------------------------
+    def process(self, inp: np.ndarray, out: np.ndarray) -> WorkReport:
+        """`fn process(&mut self, input: &[In], output: &mut [Out]) -> WorkReport` with host slices."""
+        if inp.dtype != self.in_dtype or out.dtype != self.out_dtype:
+            raise TypeError(f"expected {self.in_dtype.__name__} -> {self.out_dtype.__name__}")
+        if inp.ndim != 1 or out.ndim != 1 or not inp.flags.c_contiguous or not out.flags.c_contiguous:
+            raise ValueError("input and output must be 1-D contiguous arrays")
+        ir, ow = C.c_size_t(0), C.c_size_t(0)
+        st = lib().orion_b200_block_process(self._h, inp.ctypes.data if inp.size else None, inp.size,
+                                            out.ctypes.data if out.size else None, out.size,
+                                            C.byref(ir), C.byref(ow))
+        _check(st, self._h)
+        return WorkReport(ir.value, ow.value)
+
+    process_into = process                                            # src/core.rs:19-21
+
+    def plan(self, n_in: int, out_cap: int) -> WorkReport:
+        wr = lib().orion_b200_block_plan(self._h, n_in, out_cap)
+        return WorkReport(wr.in_read, wr.out_written)
+
+    def run(self, inp: np.ndarray) -> np.ndarray:
+        """Convenience: size the output like a careful caller would and return the written part."""
+        inp = np.ascontiguousarray(inp, self.in_dtype)
+        cap = self.plan(inp.size, 1 << 62).out_written
+        out = np.zeros(cap, self.out_dtype)
+        wr = self.process(inp, out)
+        return out[:wr.out_written]
+
+    def process_dev(self, d_in: int, n_in: int, d_out: int, out_cap: int) -> WorkReport:
+        """Device-pointer variant: enqueues on the block's stream, does not synchronise."""
+        ir, ow = C.c_size_t(0), C.c_size_t(0)
+        st = lib().orion_b200_block_process_dev(self._h, C.c_void_p(d_in), n_in, C.c_void_p(d_out), out_cap,
+                                                C.byref(ir), C.byref(ow))
+        _check(st, self._h)
+        return WorkReport(ir.value, ow.value)
+
+    def synchronize(self):
+        _check(lib().orion_b200_block_synchronize(self._h), self._h)
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib().orion_b200_block_set_stream(self._h, C.c_void_p(cuda_stream)), self._h)
+
+    def reset(self):
+        _check(lib().orion_b200_block_reset(self._h), self._h)
+
+    def set_option(self, option: int, value: float):
+        _check(lib().orion_b200_block_set_option(self._h, option, float(value)), self._h)
+
+    def state(self) -> np.ndarray:
+        n = lib().orion_b200_block_get_state(self._h, None, 0)
+        s = np.zeros(n, np.float32)
+        lib().orion_b200_block_get_state(self._h, s.ctypes.data, n)
+        return s
+
+    @property
+    def decimation(self) -> int:
+        return int(lib().orion_b200_block_decimation(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().orion_b200_block_launch_count(self._h))
+
+
+def _mk(fn_name, *args) -> int:
+    h = C.c_void_p(0)
+    st = getattr(lib(), fn_name)(*args, C.byref(h))
+    _check(st)
+    return h.value
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+# ---- src/dsp --------------------------------------------------------------------------------------
+class FirDecimator(Block):                                            # src/dsp/decim.rs:24-37
+    def __init__(self, fs, m, cutoff_hz, trans_hz):
+        super().__init__(_mk("orion_b200_fir_decimator_create", fs, int(m), cutoff_hz, trans_hz))
+
+    @classmethod
+    def from_taps(cls, taps, m):
+        t = _f32(taps)
+        self = cls.__new__(cls)
+        Block.__init__(self, _mk("orion_b200_fir_decimator_create_taps", t.ctypes.data, t.size, int(m)))
+        return self
+
+
+class FirLowpassIq(Block):                                            # src/dsp/fir.rs:177-297
+    def __init__(self, num_taps, cutoff_norm, stopband_db):
+        super().__init__(_mk("orion_b200_fir_lowpass_iq_create", int(num_taps), cutoff_norm, stopband_db))
+        self._ntaps = int(lib().orion_b200_kaiser_lowpass_taps(int(num_taps), cutoff_norm, stopband_db, None, 0))
+
+    design = classmethod(lambda cls, num_taps, cutoff_norm, stopband_db: cls(num_taps, cutoff_norm, stopband_db))
+
+    @classmethod
+    def from_taps(cls, taps):
+        t = _f32(taps)
+        self = cls.__new__(cls)
+        Block.__init__(self, _mk("orion_b200_fir_lowpass_iq_create_taps", t.ctypes.data if t.size else None, t.size))
+        self._ntaps = max(int(t.size), 1)
+        return self
+
+    def group_delay(self) -> int:                                     # src/dsp/fir.rs:216-218
+        return (self._ntaps - 1) // 2
+
+    def filter_aligned(self, io: np.ndarray) -> None:                 # src/dsp/fir.rs:260-276 (in place)
+        if io.dtype != np.complex64 or io.ndim != 1 or not io.flags.c_contiguous:
+            raise TypeError("filter_aligned needs a contiguous complex64 vector")
+        _check(lib().orion_b200_fir_lowpass_iq_filter_aligned(self._h, io.ctypes.data if io.size else None, io.size),
+               self._h)
+
+
+class Rotator(Block):                                                 # src/dsp/rotator.rs (rotate_block)
+    def __init__(self, freq_hz, fs):
+        super().__init__(_mk("orion_b200_rotator_create", freq_hz, fs))
+
+    def set_freq(self, freq_hz, fs):
+        _check(lib().orion_b200_oscillator_set_freq(self._h, freq_hz, fs), self._h)
+
+    def reset_phase(self):
+        _check(lib().orion_b200_oscillator_reset_phase(self._h), self._h)
+
+    rotate_block = Block.process
+
+
+class RotatorUsb(Block):                                              # Rotator::mix_usb_block, rotator.rs:88-94
+    def __init__(self, freq_hz, fs):
+        super().__init__(_mk("orion_b200_rotator_usb_create", freq_hz, fs))
+
+    def set_freq(self, freq_hz, fs):
+        _check(lib().orion_b200_oscillator_set_freq(self._h, freq_hz, fs), self._h)
+
+    mix_usb_block = Block.process
+
+
+class NcoMixer(Block):                                                # src/dsp/nco.rs (mix_with_nco per sample)
+    def __init__(self, freq_hz, fs):
+        super().__init__(_mk("orion_b200_nco_mixer_create", freq_hz, fs))
+        self._fs = fs
+
+    def set_freq(self, freq_hz):
+        _check(lib().orion_b200_oscillator_set_freq(self._h, freq_hz, self._fs), self._h)
+
+
+class Biquad(Block):                                                  # src/dsp/iir.rs:5-41
+    def __init__(self, b0, b1, b2, a1, a2):
+        super().__init__(_mk("orion_b200_biquad_create", b0, b1, b2, a1, a2))
+
+
+class LpCascade(Block):                                               # src/dsp/iir.rs:44-84
+    def __init__(self, fs, fc):
+        super().__init__(_mk("orion_b200_lp_cascade_create", fs, fc))
+
+    design = classmethod(lambda cls, fs, fc: cls(fs, fc))
+
+
+class LpDcCascade(Block):                                             # src/dsp/iir.rs:90-187
+    def __init__(self, fs, lp_fc, dc_cut_hz, map_sqrt=False):
+        super().__init__(_mk("orion_b200_lp_dc_cascade_create", fs, lp_fc, dc_cut_hz, int(bool(map_sqrt))))
+
+    design = classmethod(lambda cls, fs, lp_fc, dc_cut_hz: cls(fs, lp_fc, dc_cut_hz))
+
+
+class DcBlocker(Block):                                               # src/dsp/dc.rs:8-59
+    def __init__(self, fs, cut_hz):
+        super().__init__(_mk("orion_b200_dc_blocker_create", fs, cut_hz))
+
+
+class IirCascade(Block):                                              # N x Biquad::process
+    def __init__(self, sos):
+        s = _f32(sos).reshape(-1, 5)
+        super().__init__(_mk("orion_b200_iir_cascade_create", s.ctypes.data, s.shape[0]))
+
+
+# ---- src/demodulate -------------------------------------------------------------------------------
+class FmQuadratureDemod(Block):                                       # src/demodulate/fm.rs:11-78
+    def __init__(self, fs, dev_hz, audio_bw_hz):
+        super().__init__(_mk("orion_b200_fm_demod_create", fs, dev_hz, audio_bw_hz))
+
+    def with_translate(self, freq_hz):
+        _check(lib().orion_b200_fm_demod_with_translate(self._h, freq_hz), self._h)
+        return self
+
+
+class PmQuadratureDemod(Block):                                       # src/demodulate/pm.rs:12-67
+    def __init__(self, fs, k, audio_bw_hz):
+        super().__init__(_mk("orion_b200_pm_demod_create", fs, k, audio_bw_hz))
+
+
+class AmEnvelopeDemod(Block):                                         # src/demodulate/am.rs:10-130
+    def __init__(self, fs, audio_bw_hz):
+        super().__init__(_mk("orion_b200_am_demod_create", fs, audio_bw_hz))
+
+    def with_abs_approx(self, k1, k2):
+        _check(lib().orion_b200_am_demod_with_abs_approx(self._h, k1, k2), self._h)
+        return self
+
+
+class SsbProductDemod(Block):                                         # src/demodulate/ssb.rs:9-72
+    def __init__(self, fs, bfo_hz, audio_bw_hz):
+        super().__init__(_mk("orion_b200_ssb_demod_create", fs, bfo_hz, audio_bw_hz))
+
+
+class CwEnvelopeDemod(Block):                                         # src/demodulate/cw.rs:8-47
+    def __init__(self, sample_rate, tone_hz, env_bw_hz):
+        super().__init__(_mk("orion_b200_cw_demod_create", sample_rate, tone_hz, env_bw_hz))
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_cw_demod_set_gain(self._h, g), self._h)
+
+
+# ---- fused chain ----------------------------------------------------------------------------------
+class Chain(Block):
+    """[mixer] -> [FIR, decimate] -> [demod] -> [post biquads] in one kernel (orion_b200_chain_create)."""
+
+    def __init__(self, *, mix=MIX_NONE, mix_freq_hz=0.0, mix_fs=1.0, fir=FIR_NONE, taps=None, decim=1,
+                 demod=DEMOD_NONE, fs_demod=1.0, p0=0.0, p1=0.0, audio_bw_hz=0.0, translate_hz=None,
+                 post_sos=None):
+        sp = ChainSpec()
+        sp.struct_size = C.sizeof(ChainSpec)
+        sp.mix, sp.mix_freq_hz, sp.mix_fs = mix, mix_freq_hz, mix_fs
+        sp.fir = fir
+        self._taps = _f32(taps) if taps is not None else np.zeros(0, np.float32)
+        sp.taps = self._taps.ctypes.data_as(C.POINTER(C.c_float)) if self._taps.size else None
+        sp.ntaps, sp.decim = self._taps.size, int(decim)
+        sp.demod, sp.fs_demod, sp.p0, sp.p1, sp.audio_bw_hz = demod, fs_demod, p0, p1, audio_bw_hz
+        sp.translate = int(translate_hz is not None)
+        sp.translate_hz = float(translate_hz or 0.0)
+        self._sos = _f32(post_sos).reshape(-1, 5) if post_sos is not None else np.zeros((0, 5), np.float32)
+        sp.post_sos = self._sos.ctypes.data_as(C.POINTER(C.c_float)) if self._sos.size else None
+        sp.n_post = self._sos.shape[0]
+        h = C.c_void_p(0)
+        _check(lib().orion_b200_chain_create(C.byref(sp), C.byref(h)))
+        super().__init__(h.value)
+
+
+# ---- src/core.rs chain wrappers --------------------------------------------------------------------
+class _ChainWrapper:
+    """IqToIqChain / IqToAudioChain / AudioToIqChain (src/core.rs:25-109): one block, a grow-only
+    scratch, and `process` returns `input.len()` items whatever the block reported."""
+
+    def __init__(self, block: Block):
+        self.block = block
+        self._out = np.zeros(0, block.out_dtype)
+
+    def process(self, inp) -> np.ndarray:
+        return self.process_ref(np.ascontiguousarray(inp, self.block.in_dtype))
+
+    def process_ref(self, inp: np.ndarray) -> np.ndarray:
+        n = inp.size
+        if self._out.size < n:                                        # src/core.rs:99-101
+            grown = np.zeros(n, self.block.out_dtype)
+            grown[:self._out.size] = self._out
+            self._out = grown
+        self.block.process_into(inp, self._out[:n])
+        return self._out[:n].copy()                                   # src/core.rs:104 (`to_vec`)
+
+    def process_into(self, inp: np.ndarray, out: np.ndarray) -> WorkReport:
+        return self.block.process_into(inp, out)
+
+
+IqToIqChain = _ChainWrapper
+IqToAudioChain = _ChainWrapper
+AudioToIqChain = _ChainWrapper

@@ -1,0 +1,89 @@
+"""Synthetic IQ generators shared by the parity tests, smoke() and bench.py.
+Signals are built in f64 and cast to complex64; every generator is seeded."""
+import numpy as np
+
+
+def awgn(n, sigma, seed):
+    r = np.random.default_rng(seed)
+    return sigma * (r.standard_normal(n) + 1j * r.standard_normal(n))
+
+
+def fm_iq(n, fs, f_c=100e3, dev=25e3, tones=((1e3, 0.5), (3.7e3, 0.25)), amp=0.5, sigma=1e-3, seed=0x0510):
+    """C1: carrier offset f_c, two-tone message, peak deviation `dev`, plus AWGN."""
+    t = np.arange(n) / fs
+    msg_int = np.zeros(n)
+    for f, a in tones:                       # integral of a*cos(2 pi f t)
+        msg_int += a * np.sin(2 * np.pi * f * t) / (2 * np.pi * f)
+    ph = 2 * np.pi * f_c * t + 2 * np.pi * dev * msg_int
+    return (amp * np.exp(1j * ph) + awgn(n, sigma, seed)).astype(np.complex64)
+
+
+def am_iq(n, fs, carrier=0.8, m=0.5, tones=(400.0, 1e3), sigma=1e-3, seed=0x0512, f_off=0.0):
+    t = np.arange(n) / fs
+    msg = sum(np.cos(2 * np.pi * f * t) for f in tones) / len(tones)
+    env = carrier * (1.0 + m * msg)
+    return (env * np.exp(2j * np.pi * f_off * t) + awgn(n, sigma, seed)).astype(np.complex64)
+
+
+def ssb_iq(n, fs, f_bfo=250e3, tones=(300.0, 700.0, 1200.0, 1900.0, 2500.0), a=0.15, sigma=1e-3, seed=0x0511):
+    t = np.arange(n) / fs
+    x = sum(a * np.exp(2j * np.pi * (f_bfo + f) * t) for f in tones)
+    return (x + awgn(n, sigma, seed)).astype(np.complex64)
+
+
+def pm_iq(n, fs, k=0.8, tone=1e3, amp=0.5, sigma=1e-3, seed=0x0515):
+    t = np.arange(n) / fs
+    return (amp * np.exp(1j * k * np.sin(2 * np.pi * tone * t)) + awgn(n, sigma, seed)).astype(np.complex64)
+
+
+def cw_iq(n, fs, tone=700.0, wpm_period=0.12, amp=0.6, sigma=1e-3, seed=0x0516):
+    t = np.arange(n) / fs
+    key = ((t / wpm_period) % 1.0) < 0.5
+    return (amp * key * np.exp(2j * np.pi * tone * t) + awgn(n, sigma, seed)).astype(np.complex64)
+
+
+def noise_c64(n, scale=0.5, seed=1):
+    r = np.random.default_rng(seed)
+    return (scale * (r.standard_normal(n) + 1j * r.standard_normal(n))).astype(np.complex64)
+
+
+def noise_f32(n, scale=0.5, seed=2):
+    return (scale * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+
+
+def parity(got, ref):
+    """(max abs error / full scale, SNR in dB) with full scale := max|ref|."""
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0, np.inf
+    fsv = float(np.max(np.abs(ref)))
+    d = got.astype(np.complex128) - ref.astype(np.complex128)
+    e = float(np.max(np.abs(d)))
+    p_ref = float(np.sum(np.abs(ref.astype(np.complex128)) ** 2))
+    p_err = float(np.sum(np.abs(d) ** 2))
+    snr = np.inf if p_err == 0.0 else 10.0 * np.log10(max(p_ref, 1e-300) / p_err)
+    return (e / fsv if fsv > 0 else e), snr
+
+
+TOL = 1e-4       # max abs error, fraction of full scale (BASELINE.json north_star)
+SNR_DB = 90.0    # demodulated-output SNR against the reference
+
+
+def assert_parity(got, ref, tol=TOL, snr_db=SNR_DB, what=""):
+    e, snr = parity(got, ref)
+    assert e <= tol, f"{what}: max abs error {e:.3e} of full scale > {tol:.1e} (snr {snr:.1f} dB)"
+    assert snr >= snr_db, f"{what}: SNR {snr:.1f} dB < {snr_db} dB (max err {e:.3e})"
+    return e, snr
+
+
+def bit_equal(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    fa = a.view(np.float32)
+    fb = b.view(np.float32)
+    nan = np.isnan(fa)
+    return bool(np.array_equal(nan, np.isnan(fb)) and np.array_equal(fa.view(np.uint32)[~nan], fb.view(np.uint32)[~nan]))

@@ -1,0 +1,337 @@
+"""GPU parity tests: every block of the C ABI (through the ctypes binding, i.e. through
+liborion_b200.so) against the CPU oracle on identical seeded input.
+
+Bar (BASELINE.json north_star): WorkReport, output count and decimation phase bit-exact;
+values within max|gpu-ref| <= 1e-4 * max|ref| and SNR >= 90 dB.  With
+ORION_B200_OPT_FIR_GLOBAL the FIR follows the reference's accumulation order and the result
+must be bit-identical."""
+import numpy as np
+import pytest
+
+import oracle
+import orion_b200 as ob
+from signals import (am_iq, assert_parity, bit_equal, cw_iq, fm_iq, noise_c64, noise_f32, pm_iq, ssb_iq)
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pair(gpu, ref, x, out_dtype, cap=None, ratio=1):
+    """One process() call on both sides with equally sized outputs."""
+    n_cap = cap if cap is not None else -(-x.size // ratio)
+    og = np.zeros(n_cap, out_dtype)
+    orf = np.zeros(n_cap, out_dtype)
+    wg = gpu.process(x, og)
+    wr = ref.process(x, orf)
+    assert tuple(wg) == tuple(wr), (wg, wr)
+    return og[:wg.out_written], orf[:wr.out_written]
+
+
+def stream_pair(gpu, ref, x, out_dtype, chunks, ratio=1):
+    """Feed the same ragged chunk sequence to both sides (decimation phase restarts per call)."""
+    og, orf, pos = [], [], 0
+    for c in chunks:
+        a, b = run_pair(gpu, ref, x[pos:pos + c], out_dtype, ratio=ratio)
+        og.append(a)
+        orf.append(b)
+        pos += c
+    return np.concatenate(og), np.concatenate(orf)
+
+
+# ---- FIR decimator ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("fs,m,cut,trans,n", [(96e3, 4, 10e3, 2400.0, 4096), (2.4e6, 8, 100e3, 38400.0, 200_003),
+                                              (48e3, 2, 5e3, 1500.0, 30_001), (1e6, 16, 20e3, 30e3, 70_000),
+                                              (1e6, 5, 50e3, 25e3, 41_234), (100e6, 32, 450e3, 97800.0, 150_000)])
+def test_fir_decimator(fs, m, cut, trans, n):
+    x = noise_c64(n, seed=n)
+    g, r = ob.FirDecimator(fs, m, cut, trans), oracle.FirDecimator(fs, m, cut, trans)
+    a, b = run_pair(g, r, x, np.complex64, ratio=m)
+    assert a.size == -(-n // m)
+    assert_parity(a, b, what="staged")
+    g2 = ob.FirDecimator(fs, m, cut, trans)
+    g2.set_option(ob.OPT_FIR_GLOBAL, 1)
+    a2, _ = run_pair(g2, oracle.FirDecimator(fs, m, cut, trans), x, np.complex64, ratio=m)
+    assert bit_equal(a2, b), "reference-order FIR must be bit-identical"
+
+
+def test_fir_decimator_ragged_chunks_and_short_output():
+    fs, m = 2.4e6, 8
+    x = noise_c64(60_000, seed=7)
+    chunks = [1, 7, 8, 9, 1000, 4097, 13, 20_000, 0, 5, 34_860]
+    assert sum(chunks) == x.size
+    g, r = ob.FirDecimator(fs, m, 100e3, 38400.0), oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    a, b = stream_pair(g, r, x, np.complex64, chunks, ratio=m)
+    assert_parity(a, b, what="chunked")
+    # output shorter than ceil(n/m): everything is consumed, the output is truncated (decim.rs:66-75)
+    g, r = ob.FirDecimator(fs, m, 100e3, 38400.0), oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    a, b = run_pair(g, r, x[:10_000], np.complex64, cap=100)
+    assert a.size == 100
+    assert_parity(a, b)
+    a, b = run_pair(g, r, x[10_000:30_000], np.complex64, ratio=m)   # state must have advanced over all input
+    assert_parity(a, b, what="after truncated call")
+
+
+def test_fir_decimator_tma_and_serial_agree():
+    fs, m, n = 2.4e6, 8, 300_000
+    x = noise_c64(n, seed=11)
+    outs = []
+    for tma, serial in [(1, 0), (0, 0), (1, 1)]:
+        g = ob.FirDecimator(fs, m, 100e3, 38400.0)
+        g.set_option(ob.OPT_USE_TMA, tma)
+        g.set_option(ob.OPT_SERIAL_TILES, serial)
+        outs.append(g.run(x))
+    assert bit_equal(outs[0], outs[1]) and bit_equal(outs[0], outs[2])
+
+
+# ---- FirLowpassIq ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ntaps,fc,a,n", [(81, 0.1, 60.0, 50_001), (201, 0.01, 60.0, 120_000), (5, 0.3, 30.0, 999)])
+def test_fir_lowpass_iq(ntaps, fc, a, n):
+    x = noise_c64(n, seed=ntaps)
+    g, r = ob.FirLowpassIq(ntaps, fc, a), oracle.FirLowpassIq(ntaps, fc, a)
+    ya, yb = stream_pair(g, r, x, np.complex64, [n // 3, 1, n - n // 3 - 1])
+    assert_parity(ya, yb)
+    g2 = ob.FirLowpassIq(ntaps, fc, a)
+    g2.set_option(ob.OPT_FIR_GLOBAL, 1)
+    assert bit_equal(g2.run(x), oracle.FirLowpassIq(ntaps, fc, a).run(x))
+    # filter_aligned == streamed output advanced by the group delay (fir.rs:260-276)
+    io_g, io_r = x[:20_000].copy(), x[:20_000].copy()
+    ob.FirLowpassIq(ntaps, fc, a).filter_aligned(io_g)
+    oracle.FirLowpassIq(ntaps, fc, a).filter_aligned(io_r)
+    assert_parity(io_g, io_r, what="filter_aligned")
+
+
+def test_fir_identity_and_from_taps():
+    x = noise_c64(5000, seed=3)
+    g = ob.FirLowpassIq.from_taps([])                                   # fir.rs:193-196
+    assert bit_equal(g.run(x), x)
+    taps = np.random.default_rng(5).standard_normal(47).astype(np.float32)
+    a = ob.FirDecimator.from_taps(taps, 6).run(x)
+    b = oracle.FirDecimator(taps=taps, m=6).run(x)
+    assert_parity(a, b)
+
+
+# ---- oscillators -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f,fs,n", [(100e3, 2.4e6, 16_384), (1.5e3, 48e3, 200_000), (-250e3, 1.2e6, 65_536)])
+def test_rotator_nco_usb(f, fs, n):
+    x = noise_c64(n, seed=int(abs(f)))
+    a, b = stream_pair(ob.Rotator(f, fs), oracle.Rotator(f, fs), x, np.complex64, [n // 2 + 3, n - n // 2 - 3])
+    assert_parity(a, b, what="rotate_block")
+    a = ob.NcoMixer(f, fs).run(x)
+    b = oracle.Nco(f, fs).mix(x)
+    assert_parity(a, b, what="mix_with_nco")
+    a = ob.RotatorUsb(f, fs).run(x)
+    b = oracle.Rotator(f, fs).mix_usb_block(x)
+    assert_parity(a, b, what="mix_usb_block")
+
+
+def test_rotator_set_freq_keeps_phase():
+    x = noise_c64(8192, seed=21)
+    g, r = ob.Rotator(1.5e3, 48e3), oracle.Rotator(1.5e3, 48e3)
+    a1, b1 = run_pair(g, r, x[:4000], np.complex64)
+    g.set_freq(-3.1e3, 48e3)
+    r.set_freq(-3.1e3, 48e3)
+    a2, b2 = run_pair(g, r, x[4000:], np.complex64)
+    assert_parity(np.concatenate([a1, a2]), np.concatenate([b1, b2]))
+    g.reset_phase()
+    r.reset_phase()
+    a3, b3 = run_pair(g, r, x[:1000], np.complex64)
+    assert_parity(a3, b3)
+
+
+# ---- recursive sections -------------------------------------------------------------------------------
+def test_iir_blocks():
+    n = 400_000
+    x = noise_f32(n, seed=31)
+    chunks = [1, 5, 100_000, 7, 299_987]
+    c = oracle.lp_biquad_coeffs(48e3, 3e3)
+    pairs = [
+        (ob.Biquad(*c), oracle.Biquad(*c)),
+        (ob.LpCascade(48e3, 4.5e3), oracle.LpCascade(48e3, 4.5e3)),
+        (ob.LpDcCascade(48e3, 4.5e3, 2.0), oracle.LpDcCascade(48e3, 4.5e3, 2.0)),
+        (ob.DcBlocker(48e3, 2.0), oracle.DcBlocker(48e3, 2.0)),
+        (ob.DcBlocker(1e6, 0.05), oracle.DcBlocker(1e6, 0.05)),          # pole clamped at 0.9999
+    ]
+    for g, r in pairs:
+        a, b = stream_pair(g, r, x, np.float32, chunks)
+        assert_parity(a, b, what=type(g).__name__)
+    # process_mapped(x, sqrt) on a positive input (iir.rs:170-186)
+    xp = np.abs(x) + 0.5
+    a, b = stream_pair(ob.LpDcCascade(48e3, 4.5e3, 2.0, True), oracle.LpDcCascade(48e3, 4.5e3, 2.0, True), xp,
+                       np.float32, chunks)
+    assert_parity(a, b, what="LpDcCascade mapped")
+    # N-section cascade == LpCascade twice
+    sos = np.stack([c, c, c, c])
+    a = ob.IirCascade(sos).run(x)
+    r1, r2 = oracle.LpCascade(48e3, 3e3), oracle.LpCascade(48e3, 3e3)
+    assert_parity(a, r2.run(r1.run(x)), what="4-section cascade")
+
+
+def test_sqrt_of_negative_latches_nan_like_the_reference():
+    # am.rs:55 / iir.rs:180: LR4 of |z|^2 can ring below zero; sqrt -> NaN; the DC blocker keeps it forever
+    x = np.zeros(6000, np.complex64)
+    x[:3000] = 1.0
+    a = ob.AmEnvelopeDemod(48e3, 5e3).run(x)
+    b = oracle.AmEnvelopeDemod(48e3, 5e3).run(x)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    if np.isnan(b).any():
+        first = int(np.argmax(np.isnan(b)))
+        assert np.isnan(a[first:]).all()
+        assert_parity(a[:first], b[:first])
+
+
+# ---- demodulators -------------------------------------------------------------------------------------
+def _demod_cases():
+    n = 300_000
+    return [
+        ("fm", lambda m: m.FmQuadratureDemod(48e3, 2.5e3, 5e3), lambda: fm_iq(n, 48e3, f_c=0.0, dev=2.5e3)),
+        ("fm_translate", lambda m: m.FmQuadratureDemod(300e3, 25e3, 15e3).with_translate(100e3), lambda: fm_iq(n, 300e3)),
+        ("pm", lambda m: m.PmQuadratureDemod(48e3, 1.25, 5e3), lambda: pm_iq(n, 48e3)),
+        ("am", lambda m: m.AmEnvelopeDemod(48e3, 5e3), lambda: am_iq(n, 48e3)),
+        ("am_abs", lambda m: m.AmEnvelopeDemod(48e3, 5e3).with_abs_approx(0.9482, 0.3920), lambda: am_iq(n, 48e3, f_off=50.0)),
+        ("ssb", lambda m: m.SsbProductDemod(48e3, 1.5e3, 2.8e3), lambda: ssb_iq(n, 48e3, f_bfo=1.5e3)),
+        ("cw", lambda m: m.CwEnvelopeDemod(48e3, 700.0, 50.0), lambda: cw_iq(n, 48e3)),
+    ]
+
+
+@pytest.mark.parametrize("case", _demod_cases(), ids=lambda c: c[0])
+def test_demodulators(case):
+    name, make, gen = case
+    x = gen()
+    g, r = make(ob), make(oracle)
+    n = x.size
+    a, b = stream_pair(g, r, x, np.float32, [4096, 1, 100_003, n - 4096 - 1 - 100_003])
+    assert_parity(a, b, what=name)
+    # state persists across calls and equals the oracle's
+    sg, sr = g.state(), r.state()
+    if name in ("fm", "fm_translate", "pm"):
+        assert np.allclose(sg[0:2], sr[15:17], rtol=0, atol=1e-4 * max(1.0, np.max(np.abs(sr[15:17]))))
+
+
+def test_cw_set_gain():
+    x = cw_iq(20_000, 48e3)
+    g, r = ob.CwEnvelopeDemod(48e3, 700.0, 50.0), oracle.CwEnvelopeDemod(48e3, 700.0, 50.0)
+    g.set_gain(2.5)
+    r.set_gain(2.5)
+    a, b = run_pair(g, r, x, np.float32)
+    assert_parity(a, b)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 8, 9, 1023, 1024, 1025])
+def test_tiny_and_empty_inputs(n):
+    x = fm_iq(max(n, 1), 48e3, f_c=0.0, dev=2.5e3)[:n]
+    a, b = run_pair(ob.FmQuadratureDemod(48e3, 2.5e3, 5e3), oracle.FmQuadratureDemod(48e3, 2.5e3, 5e3), x, np.float32)
+    assert a.size == n
+    assert_parity(a, b)
+    xd = noise_c64(n, seed=n + 1)
+    a, b = run_pair(ob.FirDecimator(96e3, 4, 10e3, 2400.0), oracle.FirDecimator(96e3, 4, 10e3, 2400.0), xd,
+                    np.complex64, ratio=4)
+    assert a.size == -(-n // 4)
+    assert_parity(a, b)
+
+
+def test_rate_one_length_rule():
+    # n = min(len(in), len(out)) (fm.rs:46,73-76)
+    x = fm_iq(5000, 48e3, f_c=0.0, dev=2.5e3)
+    g, r = ob.FmQuadratureDemod(48e3, 2.5e3, 5e3), oracle.FmQuadratureDemod(48e3, 2.5e3, 5e3)
+    a, b = run_pair(g, r, x, np.float32, cap=3000)
+    assert a.size == 3000
+    assert_parity(a, b)
+    a, b = run_pair(g, r, x[3000:], np.float32, cap=9000)
+    assert a.size == 2000
+    assert_parity(a, b)
+
+
+# ---- the fused chain (north-star path) -----------------------------------------------------------------
+def _c1_pair(fs=2.4e6, m=8):
+    taps = ob.fir_lowpass_design(fs, 100e3, 38400.0)
+    g = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_FM, fs_demod=fs / m, p0=25e3,
+                 audio_bw_hz=15e3, translate_hz=100e3)
+    dec = oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
+    return g, dec, fm, taps
+
+
+def _ref_chain(dec, fm, x, m):
+    mid = np.zeros(-(-x.size // m), np.complex64)
+    wr = dec.process(x, mid)
+    out = np.zeros(wr.out_written, np.float32)
+    fm.process(mid[:wr.out_written], out)
+    return out
+
+
+def test_chain_c1_fir_decim_nco_fm():
+    fs, m, n = 2.4e6, 8, 1_200_000                       # 0.5 s of the C1 stream
+    x = fm_iq(n, fs)
+    g, dec, fm, taps = _c1_pair(fs, m)
+    assert taps.size == 63
+    ref = _ref_chain(dec, fm, x, m)
+    out = np.zeros(ref.size, np.float32)
+    wr = g.process(x, out)
+    assert tuple(wr) == (n, ref.size)
+    e, snr = assert_parity(out, ref, what="C1 chain")
+    print(f"C1 chain parity: max err {e:.2e} of full scale, SNR {snr:.1f} dB")
+    # start-up transient included; streaming in ragged chunks gives the oracle's chunked result
+    g, dec, fm, _ = _c1_pair(fs, m)
+    outs, refs, pos = [], [], 0
+    for c in [8 * 1000, 8 * 37 + 3, 500_001, n - 8 * 1000 - (8 * 37 + 3) - 500_001]:
+        xc = x[pos:pos + c]
+        pos += c
+        refs.append(_ref_chain(dec, fm, xc, m))
+        o = np.zeros(refs[-1].size, np.float32)
+        g.process(xc, o)
+        outs.append(o)
+    assert_parity(np.concatenate(outs), np.concatenate(refs), what="C1 chain chunked")
+
+
+def test_chain_c1_reference_order_fir_variant():
+    fs, m, n = 2.4e6, 8, 160_000
+    x = fm_iq(n, fs)
+    g, dec, fm, _ = _c1_pair(fs, m)
+    g.set_option(ob.OPT_FIR_GLOBAL, 1)
+    ref = _ref_chain(dec, fm, x, m)
+    out = g.run(x)
+    assert_parity(out, ref, tol=2e-6, snr_db=120.0, what="C1 with bit-faithful FIR")
+
+
+def test_chain_c2_mix_fir_decim_ssb():
+    # Rotator(-250k) -> FirLowpassIq(201, 0.01, 60) -> keep every 25th -> SsbProductDemod(48k, 0, 2800)
+    fs, m, n = 1.2e6, 25, 2 ** 17
+    x = ssb_iq(n, fs)
+    taps = ob.kaiser_lowpass_taps(201, 0.01, 60.0)
+    g = ob.Chain(mix=ob.MIX_ROTATE, mix_freq_hz=-250e3, mix_fs=fs, fir=ob.FIR_IQ, taps=taps, decim=m,
+                 demod=ob.DEMOD_SSB, fs_demod=fs / m, p0=0.0, audio_bw_hz=2800.0)
+    rot, fir = oracle.Rotator(-250e3, fs), oracle.FirLowpassIq(201, 0.01, 60.0)
+    ssb = oracle.SsbProductDemod(fs / m, 0.0, 2800.0)
+    y = fir.run(rot.rotate_block(x))[::m]
+    ref = ssb.run(np.ascontiguousarray(y))
+    out = g.run(x)
+    assert out.size == ref.size == -(-n // m)
+    assert_parity(out, ref, what="C2 chain")
+
+
+def test_chain_c3_fir_decim_am_four_sections():
+    fs, m, n = 384e3, 8, 1_000_000
+    x = am_iq(n, fs)
+    taps = ob.fir_lowpass_design(fs, 10e3, 6144.0)
+    extra = np.stack([oracle.lp_biquad_coeffs(48e3, 3e3)] * 2)
+    g = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_AM, fs_demod=48e3, audio_bw_hz=5e3,
+                 post_sos=extra)
+    dec, am, lp = oracle.FirDecimator(fs, m, 10e3, 6144.0), oracle.AmEnvelopeDemod(48e3, 5e3), oracle.LpCascade(48e3, 3e3)
+    ref = lp.run(am.run(dec.run(x)))
+    out = g.run(x)
+    assert_parity(out, ref, what="C3 chain")
+
+
+# ---- src/core.rs chain wrappers ------------------------------------------------------------------------
+def test_chain_wrappers_return_input_len_items():
+    x = cw_iq(4096, 48e3)
+    a = ob.IqToAudioChain(ob.CwEnvelopeDemod(48e3, 700.0, 50.0)).process(x)
+    b = oracle.IqToAudioChain(oracle.CwEnvelopeDemod(48e3, 700.0, 50.0)).process(x)
+    assert a.size == b.size == x.size
+    assert_parity(a, b)
+    # a decimating block behind IqToIqChain: input.len() items come back, tail stale (core.rs:70-77)
+    xd = noise_c64(4096, seed=9)
+    a = ob.IqToIqChain(ob.FirDecimator(96e3, 4, 10e3, 2400.0)).process(xd)
+    b = oracle.IqToIqChain(oracle.FirDecimator(96e3, 4, 10e3, 2400.0)).process(xd)
+    assert a.size == b.size == 4096
+    assert_parity(a[:1024], b[:1024])
+    assert not a[1024:].any() and not b[1024:].any()

@@ -1,0 +1,234 @@
+"""CPU-only tests of the host logic behind the C ABI: the library loads and exports every
+symbol of include/orion_b200.h, the restated design math equals the oracle bit for bit, and
+the launch plan (polyphase tap table, staged-tile geometry, scan tables) is emulated in numpy
+with exactly the index arithmetic the kernels use and checked against the direct definitions."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import orion_b200 as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KTHREADS = 128
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "orion_b200.h")).read()
+    declared = set(re.findall(r"\b(orion_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = C.CDLL(ob.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"missing exports: {missing}"
+    assert declared == set(ob.EXPORTED_SYMBOLS)
+    assert ob.lib().orion_b200_abi_version() == 1
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if ob.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(ob.OrionB200Error) as e:
+        ob.FmQuadratureDemod(48e3, 2.5e3, 5e3)
+    assert e.value.status == ob.ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("fs,p,t", [(2.4e6, 100e3, 38400.0), (96e3, 10e3, 2400.0), (100e6, 450e3, 97800.0),
+                                    (384e3, 10e3, 6144.0), (48e3, 5.0, 0.5)])
+def test_fir_design_matches_oracle(fs, p, t):
+    a, b = ob.fir_lowpass_design(fs, p, t), oracle.fir_lowpass_taps(fs, p, t)
+    assert a.size == b.size and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,fc,a", [(81, 0.1, 60.0), (201, 0.01, 60.0), (1023, 1 / 64, 80.0), (4, 0.3, 30.0), (31, 0.25, 10.0)])
+def test_kaiser_design_matches_oracle(n, fc, a):
+    x, y = ob.kaiser_lowpass_taps(n, fc, a), oracle.kaiser_lowpass_taps(n, fc, a)
+    assert x.size == y.size and np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    assert ob.kaiser_num_taps(0.01, a) == oracle.kaiser_num_taps(0.01, a)
+    assert np.float32(ob.kaiser_transition_norm(n, a)) == np.float32(oracle.kaiser_transition_norm(n, a))
+
+
+def test_scalar_design_helpers_match_oracle():
+    for fs, fc in [(48e3, 4.5e3), (300e3, 13.5e3), (64e3, 2.7e3)]:
+        assert np.array_equal(ob.lp_biquad_design(fs, fc).view(np.uint32),
+                              np.asarray(oracle.lp_biquad_coeffs(fs, fc), np.float32).view(np.uint32))
+        assert np.float32(ob.dc_pole(fs, 2.0)) == np.float32(oracle.dc_pole(fs, 2.0))
+        assert np.float32(ob.cw_alpha(fs, 50.0)) == np.float32(oracle.cw_alpha(fs, 50.0))
+
+
+# --------------------------------------------------------------------------------------------------
+# staged polyphase FIR: numpy emulation of fir_staged()/stage_tile() indexing
+# --------------------------------------------------------------------------------------------------
+def _emulate_staged(plan, M, x_virtual, H, n_out):
+    """x_virtual[s + H] = sample s of the virtual stream (history first).  Returns y[0:n_out]."""
+    R, U, Mb, O, P_pad, HR = (plan[k] for k in ("R", "U", "Mb", "O", "P_pad", "HR"))
+    rs, rows = plan["row_samples"], plan["rows"]
+    tab = plan["table"][:, 0].astype(np.float64), plan["table"][:, 1].astype(np.float64)
+    NPT = R * U
+    ntiles = -(-n_out // (KTHREADS * NPT))
+    y = np.zeros(ntiles * KTHREADS * NPT, np.complex128)
+
+    def sample(s):
+        i = s + H
+        ok = (i >= 0) & (i < x_virtual.size)
+        return np.where(ok, x_virtual[np.clip(i, 0, x_virtual.size - 1)], 0)
+
+    for t in range(ntiles):
+        G0 = t * KTHREADS - HR
+        row_start = rs * (G0 + np.arange(rows)) + (O - Mb + 2)                 # row_start_sample()
+        smem = sample(row_start[:, None] + np.arange(rs)[None, :])             # [rows, rs]
+        tid = np.arange(KTHREADS)
+        acc = np.zeros((U, R, KTHREADS), np.complex128)
+        for q in range(Mb // 2):
+            off = Mb - 2 - 2 * q
+            w = [None] * R
+            for k in range(R - 1):
+                w[k] = (smem[tid, (k + 1) * Mb + off], smem[tid, (k + 1) * Mb + off + 1])
+            for rr in range(HR):
+                for kk in range(R):
+                    col = kk * Mb + off
+                    w[(kk + R - 1) % R] = (smem[tid + 1 + rr, col], smem[tid + 1 + rr, col + 1])
+                    c = rr * R + kk
+                    for u in range(U):
+                        ti = (u * (Mb // 2) + q) * P_pad + c
+                        for i in range(R):
+                            w0, w1 = w[(kk + i) % R]
+                            acc[u, i] += tab[0][ti] * w0 + tab[1][ti] * w1
+        for i in range(R):
+            for u in range(U):
+                j = t * KTHREADS * NPT + tid * NPT + i * U + u
+                y[j] = acc[u, i]
+    return y[:n_out]
+
+
+def _direct(g, M, x_virtual, H, n_out):
+    y = np.zeros(n_out, np.complex128)
+    for j in range(n_out):
+        for t in range(len(g)):
+            s = M * j - t + H
+            if 0 <= s < x_virtual.size:
+                y[j] += float(g[t]) * x_virtual[s]
+    return y
+
+
+@pytest.mark.parametrize("kind,L,M", [
+    (ob.FIR_DECIM, 63, 8), (ob.FIR_DECIM, 31, 4), (ob.FIR_DECIM, 41, 2), (ob.FIR_DECIM, 33, 16),
+    (ob.FIR_DECIM, 65, 32), (ob.FIR_IQ, 81, 1), (ob.FIR_IQ, 51, 25), (ob.FIR_IQ, 21, 3), (ob.FIR_DECIM, 31, 5),
+    (ob.FIR_IQ, 1, 1), (ob.FIR_DECIM, 47, 12), (ob.FIR_DECIM, 95, 48),
+])
+def test_staged_fir_plan_reproduces_direct_fir(kind, L, M, rng):
+    taps = rng.standard_normal(L).astype(np.float32)
+    plan = ob.debug_fir_plan(kind, taps, M)
+    assert plan["front"] == 1, plan
+    g = plan["g"]
+    if kind == ob.FIR_DECIM:                      # fir.rs:57-66 pairing
+        assert g[0] == taps[-1] and np.array_equal(g[1:], taps[:-1])
+    else:
+        assert np.array_equal(g, taps)
+    R, U, Mb = plan["R"], plan["U"], plan["Mb"]
+    assert Mb == M * U and Mb % 2 == 0 and plan["P_pad"] % R == 0 and plan["HR"] * R == plan["P_pad"]
+    assert plan["row_pitch"] % 16 == 0 and (plan["row_pitch"] // 16) % 2 == 1      # conflict-free lane stride
+    assert plan["rows"] == KTHREADS + plan["HR"] <= 256
+    H = plan["H"]
+    assert H % 2 == 0 and H >= L
+    # the first staged sample of tile 0 must lie inside the history
+    assert plan["row_samples"] * (-plan["HR"]) + plan["O"] - Mb + 2 >= -H
+    NPT = R * U
+    n_out = KTHREADS * NPT + 37                   # one full tile + a ragged one
+    n_in = M * n_out
+    xv = (rng.standard_normal(H + n_in) + 1j * rng.standard_normal(H + n_in))
+    want = _direct(g, M, xv, H, n_out)
+    got = _emulate_staged(plan, M, xv, H, n_out)
+    assert np.max(np.abs(got - want)) < 1e-9 * max(1.0, np.max(np.abs(want)))
+
+
+def test_large_shapes_fall_back_to_global_front(rng):
+    plan = ob.debug_fir_plan(ob.FIR_DECIM, rng.standard_normal(513).astype(np.float32), 128)
+    assert plan["front"] == 2 and plan["H"] >= 513
+
+
+# --------------------------------------------------------------------------------------------------
+# scan tables: emulate pass 1 / warp scan / block combine / look-back in f64
+# --------------------------------------------------------------------------------------------------
+def _step(sec_type, c, x, s):
+    if sec_type == 1:
+        y = x * c[0] + s[0]
+        return y, np.array([x * c[1] + s[1] - c[3] * y, x * c[2] - c[4] * y])
+    if sec_type == 2:
+        y = x - s[0] + c[0] * s[1]
+        return y, np.array([x, y])
+    y = c[0] * s[0] + c[1] * x
+    return y, np.array([y, 0.0])
+
+
+def _mat(m):
+    return np.array([[m[0], m[1]], [m[2], m[3]]], np.float64)
+
+
+@pytest.mark.parametrize("sec_type,coef", [
+    (1, None), (2, [0.99973822]), (3, [0.98, 0.02]), (2, [0.9999]),
+])
+@pytest.mark.parametrize("npt", [8, 16, 2])
+def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
+    if coef is None:
+        coef = list(ob.lp_biquad_design(48e3, 4.5e3).astype(np.float64))
+    c = np.zeros(5)
+    c[:len(coef)] = np.asarray(coef, np.float32).astype(np.float64)
+    T = ob.debug_scan_tables(sec_type, c, npt)
+    ntiles, tile_items = 3, KTHREADS * npt
+    x = rng.standard_normal(ntiles * tile_items)
+    s_carry = rng.standard_normal(2) * (0.1 if sec_type != 2 else 1.0)
+    if sec_type == 3:
+        s_carry[1] = 0.0
+    # sequential truth
+    s = s_carry.copy()
+    want = np.zeros_like(x)
+    for n in range(x.size):
+        want[n], s = _step(sec_type, c, x[n], s)
+    # chunked: per-thread zero-state end states, warp scan, block combine, look-back with aggregates only
+    got = np.zeros_like(x)
+    aggs = []
+    tile_in = None
+    for t in range(ntiles):
+        xs = x[t * tile_items:(t + 1) * tile_items].reshape(KTHREADS, npt)
+        e = np.zeros((KTHREADS, 2))
+        for th in range(KTHREADS):
+            st = np.zeros(2)
+            for i in range(npt):
+                _, st = _step(sec_type, c, xs[th, i], st)
+            e[th] = st
+        E = e.copy()
+        for w in range(4):                                   # Kogge-Stone inside each warp
+            for l in range(5):
+                d = 1 << l
+                prev = E[w * 32:(w + 1) * 32].copy()
+                for lane in range(d, 32):
+                    E[w * 32 + lane] = prev[lane] + _mat(T["lv"][l]) @ prev[lane - d]
+        X = np.zeros_like(E)
+        for w in range(4):
+            X[w * 32 + 1:(w + 1) * 32] = E[w * 32:(w + 1) * 32 - 1]
+        S = np.zeros(2)
+        spre = []
+        for w in range(4):
+            spre.append(S.copy())
+            S = _mat(T["warp"][1]) @ S + E[w * 32 + 31]
+        aggs.append(S.copy())
+        # look-back over aggregates down to the carried state (virtual tile -1)
+        sin = np.zeros(2)
+        for k in range(t + 1):
+            pay = aggs[t - 1 - k] if t - 1 - k >= 0 else s_carry
+            sin = sin + _mat(T["lb"][k]) @ pay
+        incl = _mat(T["tile"]) @ sin + S
+        if tile_in is not None:
+            assert np.allclose(sin, tile_in, rtol=1e-5, atol=1e-6)
+        tile_in = incl
+        for th in range(KTHREADS):
+            w, lane = divmod(th, 32)
+            sw = spre[w] + _mat(T["warp"][w]) @ sin
+            st = X[th] + _mat(T["lane"][lane]) @ sw
+            for i in range(npt):
+                got[t * tile_items + th * npt + i], st = _step(sec_type, c, xs[th, i], st)
+    scale = max(1.0, np.max(np.abs(want)))
+    assert np.max(np.abs(got - want)) < 2e-5 * scale

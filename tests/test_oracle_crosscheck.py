@@ -15,15 +15,13 @@ def bits(a):
 
 
 def same(a, b):
-    a = np.asarray(a); b = np.asarray(b)
-    assert a.shape == b.shape
-    # NaN payloads may differ; compare NaN positions + bits elsewhere
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype
     fa = a.view(np.float32) if a.dtype == np.complex64 else a
     fb = b.view(np.float32) if b.dtype == np.complex64 else b
-    nan = np.isnan(fa)
+    nan = np.isnan(fa)                       # NaN payloads may differ: compare positions
     assert np.array_equal(nan, np.isnan(fb))
-    assert np.array_equal(bits(a)[~nan.ravel()] if a.dtype != np.complex64 else bits(a)[~nan],
-                          bits(b)[~nan.ravel()] if b.dtype != np.complex64 else bits(b)[~nan])
+    assert np.array_equal(fa.view(np.uint32)[~nan], fb.view(np.uint32)[~nan])
 
 
 def iq(n, seed, scale=0.5):
