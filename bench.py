@@ -94,6 +94,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the chain kernel, from the committed
+    ncu --set full capture (profiles/); None until one exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "chain_kernel_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def make_chain(ob):
     taps = ob.fir_lowpass_design(FS, 100e3, 38400.0)
     assert taps.size == 63
@@ -179,17 +189,28 @@ def main():
     n_out = -(-n // M)
 
     x_host = torch.from_numpy(c1_signal(n)).pin_memory()
-    x_dev = x_host.to("cuda", non_blocking=True)
+    # NBUF distinct device copies of the stream, used round-robin: 4 x 192 MB between two uses of
+    # the same buffer, so no step can be served from the 126 MB L2
+    NBUF = 4
+    x_devs = [x_host.to("cuda", non_blocking=True) for _ in range(NBUF)]
+    x_dev = x_devs[0]
     y_dev = torch.empty(n_out, dtype=torch.float32, device="cuda")
     y_host = torch.empty(n_out, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
     chain = make_chain(ob)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "the block's own stream" to the C ABI, and
+    # torch.cuda.Event only times work on the stream it is recorded on
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
     chain.set_stream(stream.cuda_stream)
 
+    counter = [0]
+
     def step_dev():
-        chain.process_dev(x_dev.data_ptr(), n, y_dev.data_ptr(), n_out)
+        xb = x_devs[counter[0] % NBUF]
+        counter[0] += 1
+        chain.process_dev(xb.data_ptr(), n, y_dev.data_ptr(), n_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -198,13 +219,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") + per-launch kernel time for the roofline ----------
-    for _ in range(W):
-        step_dev()
-    chain.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    for _ in range(W):
+        step_dev()
+    chain.synchronize()
+    # keep the GPU under the same load for ~2 s before the timed steps so that nvidia-smi (100 ms
+    # period) sees the clocks the timed region runs at; these passes are untimed warm-up
+    t_end = time.perf_counter() + 2.0
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step_dev()
+        chain.synchronize()
     barrier()
     l0 = chain.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -227,6 +254,36 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / K
     value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- full-size correctness: the last timed pass against the oracle on the head of the stream,
+    #      and one-shot vs two-call streaming over the whole stream (size-independent property) ----
+    check = None
+    if rank == 0:
+        import oracle
+        from signals import parity
+        nchk = 1_200_000
+        dec = oracle.FirDecimator(FS, M, 100e3, 38400.0)
+        fm = oracle.FmQuadratureDemod(FS / M, 25e3, 15e3).with_translate(100e3)
+        ref = fm.run(dec.run(x_host.numpy()[:nchk]))
+        c2 = make_chain(ob)
+        c2.set_stream(stream.cuda_stream)
+        y2 = torch.empty(n_out, dtype=torch.float32, device="cuda")
+        c2.process_dev(x_dev.data_ptr(), n, y2.data_ptr(), n_out)
+        c2.synchronize()
+        full = y2.cpu().numpy()
+        e_head, snr_head = parity(full[:ref.size], ref)
+        c3 = make_chain(ob)
+        c3.set_stream(stream.cuda_stream)
+        y3 = torch.empty(n_out, dtype=torch.float32, device="cuda")
+        cut = (n // 3) // M * M
+        c3.process_dev(x_dev.data_ptr(), cut, y3.data_ptr(), cut // M)
+        c3.process_dev(x_dev.data_ptr() + cut * 8, n - cut, y3.data_ptr() + (cut // M) * 4, n_out - cut // M)
+        c3.synchronize()
+        e_split, snr_split = parity(y3.cpu().numpy(), full)
+        check = {"head_vs_oracle": {"samples": nchk, "max_err_fs": e_head, "snr_db": snr_head},
+                 "one_shot_vs_two_calls_full_stream": {"max_err_fs": e_split, "snr_db": snr_split},
+                 "pass": bool(e_head <= 1e-4 and snr_head >= 90.0 and e_split <= 1e-4 and snr_split >= 90.0)}
+        del c2, c3, y2, y3
 
     # ---- end to end through the host-pointer C ABI (H2D + kernel + D2H inside the timed region) ---
     Ke = max(3, min(K, 6))
@@ -256,12 +313,12 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "samples_per_step_per_gpu": n, "parallelism": f"{world} independent streams (replicas)",
                        "l2": "input 192 MB per step > 126 MB L2 (no flush needed)", "tolerance": "max abs err <= 1e-4 of full scale, SNR >= 90 dB vs oracle"},
-            "clocks": clocks,
+            "clocks": clocks, "parity_check": check,
             "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n_out * 4),
                     "steps": Ke, "api": "orion_b200_block_process (host pointers, pinned)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n},
         }

@@ -26,23 +26,30 @@ enum : int { FRONT_DIRECT = 0,   // no FIR: items are read straight from global 
 
 // One first/second-order recursive section.  Coefficients are the reference's f32 values;
 // the per-sample arithmetic in sec_step() follows the reference op for op.
+constexpr int kMaxNpt = 16;         // items per thread (R * U)
+
 struct SecParam {
     int   type;        // SEC_*
     int   post_op;     // OP_* applied to the section's output before the next section
     float c[5];        // BIQUAD: b0,b1,b2,a1,a2 | DC: r | ONEPOLE: a, (1-a)
     float post_scale;  // OP_SCALE factor
+    // launch-plan data (filled by the host for the plan's items-per-thread n; parameter bank):
+    float2 imp[kMaxNpt];   // state impulse responses A^(n-1-i) B: zero-state end state = sum_i imp[i]*x[i]
+    float4 lv[5];          // A^(n*2^l), l = 0..4   (warp-level Kogge-Stone scan)
 };
 
 // 2x2 state-transition powers used by the chunked parallel scan (row-major a00,a01,a10,a11),
 // computed on the host in f64 from the f32 coefficients and rounded once.  n = items per
 // thread, T = kThreads * n = items per tile.
 struct SecTables {
-    float4 lv[5];     // A^(n*2^l), l = 0..4        (warp-level Kogge-Stone scan)
+    float4 lv[5];     // A^(n*2^l), l = 0..4        (copy of SecParam::lv, for the host-logic tests)
     float4 lane[32];  // A^(n*lane)                  (carry into a lane's chunk)
     float4 warp[4];   // A^(32*n*w), w = 0..3        (carry into a warp); warp[1] = one-warp step
     float4 lb[32];    // A^(T*k), k = 0..31          (inter-tile look-back)
     float4 lb32;      // A^(32*T)
     float4 tile;      // A^T
+    int    depth;     // predecessor tiles with a non-zero weight: A^(T*k) == 0 in f32 for k >= depth
+    int    pad[3];
 };
 
 // Oscillator (Rotator / Nco).  Phase is a 64-bit fraction of a turn:
@@ -67,11 +74,9 @@ struct CarryState {              // streaming state carried between process() ca
     float2 pad;
 };
 
-struct TileLink {                // one per (tile, section): decoupled look-back record
-    float2 agg;                  // end state of this tile from a zero start state
-    float2 incl;                 // true end state
-    unsigned int status;         // (epoch << 2) | {0 none, 1 agg valid, 2 agg+incl valid}
-    unsigned int pad[3];
+struct TileLink {                // one per (tile, section): decoupled look-back records, each
+    uint4 agg;                   //   {state.x, state.y, epoch tag, 0} written/read as ONE 128-bit access:
+    uint4 incl;                  //   agg = end state from a zero start state, incl = true end state
 };
 
 struct ChainArgs {

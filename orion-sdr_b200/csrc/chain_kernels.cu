@@ -176,27 +176,59 @@ struct __align__(16) Shared {
 // ----------------------------------------------------------------------------------------------
 // inter-tile decoupled look-back for one section (warp 0, all lanes).  Returns the section state
 // at the start of `tile`.
+//
+// A link record is 16 bytes {state.x, state.y, epoch tag, 0} written and read with single 128-bit
+// accesses, so payload and flag can never be observed apart (no fences, one L2 round trip per
+// window of 32 predecessors).  T->depth is the number of predecessor tiles whose transition power
+// A^(T*k) is still non-zero in f32: tiles further back contribute exactly nothing, so for fast
+// decaying sections (the LR4 biquads) the look-back reads one aggregate and never waits for an
+// inclusive value; slow poles (the DC blocker) fall through to the classic chained form.
 // ----------------------------------------------------------------------------------------------
+DEV uint4 ld_relaxed_b128(const void *p) {
+    uint4 v;
+    asm volatile(
+        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
+        "ld.relaxed.gpu.global.b128 t, [%4];\n\t"
+        "mov.b128 {lo, hi}, t;\n\t"
+        "mov.b64 {%0, %1}, lo;\n\t"
+        "mov.b64 {%2, %3}, hi;\n\t}"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_relaxed_b128(void *p, uint4 v) {
+    asm volatile(
+        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
+        "mov.b64 lo, {%1, %2};\n\t"
+        "mov.b64 hi, {%3, %4};\n\t"
+        "mov.b128 t, {lo, hi};\n\t"
+        "st.relaxed.gpu.global.b128 [%0], t;\n\t}"
+        ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int s, int lane) {
     float2 acc = make_float2(0.f, 0.f);
     float4 M = make_float4(1.f, 0.f, 0.f, 1.f);     // A^(T * 32 * window)
     long long base = tile - 1;
+    int dist0 = 0;                                   // predecessor distance of lane 0 in this window
     const float4 lbk = T->lb[lane];
+    const int depth = T->depth;
     for (;;) {
         const long long idx = base - lane;
+        const bool beyond = (dist0 + lane) >= depth;      // weight is exactly zero from here on
         const TileLink *lk = a.links + (idx >= 0 ? idx : 0) * kMaxSections + s;
-        unsigned st = 0;
+        uint4 ra = make_uint4(0, 0, 0, 0), ri = make_uint4(0, 0, 0, 0);
         int first_incl = 32;
         int spins = 0;
         for (;;) {
             bool ready, incl;
-            if (idx >= 0) {
-                st = ld_acquire_u32(&lk->status);
-                ready = (st >> 2) == a.epoch && (st & 3u) != 0u;
-                incl = ready && (st & 3u) == 2u;
-            } else {                       // virtual tile -1 = state carried in from the last call
+            if (beyond || idx < 0) {       // virtual terminators: zero weight / the state carried in
                 ready = true;
                 incl = true;
+            } else {
+                ra = ld_relaxed_b128(&lk->agg);
+                ri = ld_relaxed_b128(&lk->incl);
+                incl = ri.z == a.epoch;
+                ready = incl || ra.z == a.epoch;
             }
             const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
             const unsigned ready_mask = __ballot_sync(0xffffffffu, ready);
@@ -207,13 +239,14 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
                 if (lane == 0) atomicExch(a.err_flag, 1);
                 return acc;
             }
-            __nanosleep(20);
+            __nanosleep(32);
         }
         float2 term = make_float2(0.f, 0.f);
-        if (lane <= first_incl) {
+        if (lane <= first_incl && !beyond) {
             float2 pay;
             if (idx < 0) pay = (idx == -1) ? a.carry_in->sec[s] : make_float2(0.f, 0.f);
-            else pay = (lane == first_incl) ? ld_cg_f2(&lk->incl) : ld_cg_f2(&lk->agg);
+            else if (lane == first_incl) pay = make_float2(__uint_as_float(ri.x), __uint_as_float(ri.y));
+            else pay = make_float2(__uint_as_float(ra.x), __uint_as_float(ra.y));
             term = mv(M, mv(lbk, pay));
         }
 #pragma unroll
@@ -225,15 +258,60 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
         if (first_incl < 32) break;
         M = mm(M, T->lb32);
         base -= 32;
+        dist0 += 32;
     }
     return acc;
 }
 
 DEV void publish(const ChainArgs &a, long long tile, int s, float2 v, bool inclusive) {
     TileLink *lk = a.links + tile * kMaxSections + s;
-    if (inclusive) __stcg(&lk->incl, v); else __stcg(&lk->agg, v);
-    __threadfence();
-    st_release_u32(&lk->status, (a.epoch << 2) | (inclusive ? 2u : 1u));
+    const uint4 rec = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), a.epoch, 0u);
+    st_relaxed_b128(inclusive ? (void *)&lk->incl : (void *)&lk->agg, rec);
+}
+
+// ----------------------------------------------------------------------------------------------
+// recursive sections: per-thread passes, specialised per section type (no per-item branches)
+// ----------------------------------------------------------------------------------------------
+template <int TYPE>
+DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
+    float y;
+    if (TYPE == SEC_BIQUAD) {                 // iir.rs:34-40
+        y = fmaf(x, P.c[0], s0);
+        s0 = fmaf(x, P.c[1], s1) - P.c[3] * y;
+        s1 = x * P.c[2] - P.c[4] * y;
+    } else if (TYPE == SEC_DC) {              // iir.rs:160-163 / dc.rs:49-52: y = x - x1 + r*y1
+        y = (x - s0) + P.c[0] * s1;
+        s0 = x;
+        s1 = y;
+    } else {                                  // cw.rs:38: y = a*y + (1-a)*x
+        y = P.c[0] * s0 + P.c[1] * x;
+        s0 = y;
+    }
+    return y;
+}
+
+// pass 2: the reference recursion from the true start state; writes the carried state when this
+// thread owns the last item of the call
+template <int TYPE, int NPT>
+DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT], float s0, float s1,
+                   long long jt, bool full) {
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const float y = sec_step_t<TYPE>(P, u[i], s0, s1);
+            u[i] = (P.post_op == OP_NONE) ? y : post_apply(P, y);
+        }
+        if (jt + NPT == a.n_out) a.carry_out->sec[s] = make_float2(s0, s1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            if (jt + i < a.n_out) {
+                const float y = sec_step_t<TYPE>(P, u[i], s0, s1);
+                u[i] = post_apply(P, y);
+                if (jt + i == a.n_out - 1) a.carry_out->sec[s] = make_float2(s0, s1);
+            }
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -307,9 +385,9 @@ DEV void stage_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile,
 
 // shared-memory address of call-relative sample s inside the staged tile
 DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, long long G0, long long s) {
-    const long long d = s - row_start_sample(a, G0);
-    const int rho = (int)(d / a.row_samples);
-    const int w = (int)(d - (long long)rho * a.row_samples);
+    const int d = (int)(s - row_start_sample(a, G0));           // tile-local: fits 32 bits
+    const int rho = d / a.row_samples;
+    const int w = d - rho * a.row_samples;
     return reinterpret_cast<const float2 *>(smem + (size_t)rho * a.row_pitch + (size_t)w * 8);
 }
 
@@ -558,22 +636,27 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
 
     // ---------------- recursive sections: serial in-thread, scanned across threads and tiles -----
     if (a.demod != DEMOD_NONE) {
+        const bool full = jt + NPT <= a.n_out;
         for (int s = 0; s < a.nsec; ++s) {
-            const SecParam P = a.sec[s];
+            const SecParam &P = a.sec[s];
             const SecTables *T = a.tabs + s;
-            // pass 1: end state of this thread's chunk from a zero start state
-            float e0 = 0.f, e1 = 0.f;
+            // pass 1: end state of this thread's chunk from a zero start state, as the dot product
+            // with the section's state impulse responses  e = sum_i A^(NPT-1-i) B u[i]
+            float2 E = make_float2(0.f, 0.f);
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < NPT; ++i)
-                if (jt + i < a.n_out) (void)sec_step(P, u[i], e0, e1);
+                for (int i = 0; i < NPT; ++i) {
+                    E.x = fmaf(P.imp[i].x, u[i], E.x);
+                    E.y = fmaf(P.imp[i].y, u[i], E.y);
+                }
+            }
             // warp-level inclusive scan with constant transition powers
-            float2 E = make_float2(e0, e1);
 #pragma unroll
             for (int l = 0; l < 5; ++l) {
                 const int d = 1 << l;
                 const float ox = __shfl_up_sync(0xffffffffu, E.x, d);
                 const float oy = __shfl_up_sync(0xffffffffu, E.y, d);
-                if (lane >= d) E = add2(E, mv(T->lv[l], make_float2(ox, oy)));
+                if (lane >= d) E = add2(E, mv(P.lv[l], make_float2(ox, oy)));
             }
             float2 X = make_float2(__shfl_up_sync(0xffffffffu, E.x, 1), __shfl_up_sync(0xffffffffu, E.y, 1));
             if (lane == 0) X = make_float2(0.f, 0.f);
@@ -602,16 +685,9 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
             // state at the start of this thread's chunk
             const float2 sw = add2(sh.spre[wid], mv(T->warp[wid], sh.s_tile_in));
             const float2 st = add2(X, mv(T->lane[lane], sw));
-            float s0 = st.x, s1 = st.y;
-            // pass 2: the reference recursion from the true start state
-#pragma unroll
-            for (int i = 0; i < NPT; ++i) {
-                if (jt + i < a.n_out) {
-                    const float y = sec_step(P, u[i], s0, s1);
-                    u[i] = post_apply(P, y);
-                    if (jt + i == a.n_out - 1) a.carry_out->sec[s] = make_float2(s0, s1);
-                }
-            }
+            if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st.x, st.y, jt, full);
+            else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st.x, st.y, jt, full);
+            else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st.x, st.y, jt, full);
         }
     }
 

@@ -145,15 +145,52 @@ M2 section_matrix(const SecParam &p) {
     if (p.type == SEC_DC) return { 0.0, 0.0, -1.0, (double)p.c[0] };                   // (x1, y1)
     return { (double)p.c[0], 0.0, 0.0, 0.0 };                                           // one-pole
 }
-void build_tables(const SecParam &p, int npt, SecTables *t) {
+void section_input_vector(const SecParam &p, double B[2]) {
+    if (p.type == SEC_BIQUAD) {            // s' = A s + B x with y = b0 x + s0 substituted
+        B[0] = (double)p.c[1] - (double)p.c[3] * (double)p.c[0];
+        B[1] = (double)p.c[2] - (double)p.c[4] * (double)p.c[0];
+    } else if (p.type == SEC_DC) { B[0] = 1.0; B[1] = 1.0; }
+    else { B[0] = (double)p.c[1]; B[1] = 0.0; }
+}
+bool is_zero_f32(const M2 &m) {
+    const double t = 1e-30;                // far below anything an f32 state sum can resolve
+    return std::fabs(m.a) < t && std::fabs(m.b) < t && std::fabs(m.c) < t && std::fabs(m.d) < t;
+}
+// fills the launch-plan part of the section parameters (parameter bank) and the global tables
+void build_tables(SecParam &p, int npt, SecTables *t) {
     const M2 A = section_matrix(p);
+    double B[2];
+    section_input_vector(p, B);
+    for (int i = 0; i < kMaxNpt; ++i) p.imp[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < npt; ++i) {
+        const M2 Ak = mpow(A, (unsigned long long)(npt - 1 - i));
+        p.imp[i] = make_float2((float)(Ak.a * B[0] + Ak.b * B[1]), (float)(Ak.c * B[0] + Ak.d * B[1]));
+    }
     const unsigned long long n = (unsigned long long)npt, T = n * kThreads;
-    for (int l = 0; l < 5; ++l) t->lv[l] = f4(mpow(A, n << l));
+    for (int l = 0; l < 5; ++l) { t->lv[l] = f4(mpow(A, n << l)); p.lv[l] = t->lv[l]; }
     for (int k = 0; k < 32; ++k) t->lane[k] = f4(mpow(A, n * k));
     for (int w = 0; w < 4; ++w) t->warp[w] = f4(mpow(A, 32ull * n * w));
     for (int k = 0; k < 32; ++k) t->lb[k] = f4(mpow(A, T * k));
     t->lb32 = f4(mpow(A, T * 32ull));
     t->tile = f4(mpow(A, T));
+    // look-back depth: first k with A^(T*k) == 0; geometric search then bisection (monotone decay
+    // of the norm is not exact for complex poles, so verify a margin of 4 further powers)
+    int depth = 1 << 20;
+    {
+        int lo = 0, hi = 1;
+        while (hi < (1 << 20) && !is_zero_f32(mpow(A, T * (unsigned long long)hi))) hi <<= 1;
+        if (hi < (1 << 20)) {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) / 2;
+                if (is_zero_f32(mpow(A, T * (unsigned long long)mid))) hi = mid; else lo = mid;
+            }
+            bool ok = true;
+            for (int e = 1; e <= 4; ++e) ok = ok && is_zero_f32(mpow(A, T * (unsigned long long)(hi + e)));
+            if (ok) depth = hi;
+        }
+    }
+    t->depth = depth;
+    t->pad[0] = t->pad[1] = t->pad[2] = 0;
 }
 
 // ---- oscillator ------------------------------------------------------------------------------
@@ -376,7 +413,7 @@ int finalize_plan(orion_b200_block *b) {
     // scan tables
     if (!b->secs.empty()) {
         std::vector<SecTables> tabs(b->secs.size());
-        for (size_t s = 0; s < b->secs.size(); ++s) build_tables(b->secs[s], npt_of(b), &tabs[s]);
+        for (size_t s = 0; s < b->secs.size(); ++s) build_tables(b->secs[s], npt_of(b), &tabs[s]);   // also fills secs[s].imp/.lv
         if (b->d_tabs) { cudaFree(b->d_tabs); b->d_tabs = nullptr; }
         CK(cudaMalloc(&b->d_tabs, tabs.size() * sizeof(SecTables)));
         CK(cudaMemcpy(b->d_tabs, tabs.data(), tabs.size() * sizeof(SecTables), cudaMemcpyHostToDevice));
@@ -1033,6 +1070,7 @@ size_t orion_b200_debug_scan_tables(int type, const float c[5], int npt, float *
     SecTables t;
     build_tables(p, npt, &t);
     memcpy(tables, &t, sizeof(t));
+    if (cap >= nf + 2 * kMaxNpt) memcpy(tables + nf, p.imp, sizeof(p.imp));
     return nf;
 }
 

@@ -199,7 +199,10 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
             for i in range(npt):
                 _, st = _step(sec_type, c, xs[th, i], st)
             e[th] = st
-        E = e.copy()
+        # the kernel gets the same end states from the impulse-response dot product
+        e_dot = xs @ T["imp"].astype(np.float64)
+        assert np.allclose(e_dot, e, rtol=1e-5, atol=1e-6 * max(1.0, np.max(np.abs(e))))
+        E = e_dot.copy()
         for w in range(4):                                   # Kogge-Stone inside each warp
             for l in range(5):
                 d = 1 << l
@@ -217,7 +220,7 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
         aggs.append(S.copy())
         # look-back over aggregates down to the carried state (virtual tile -1)
         sin = np.zeros(2)
-        for k in range(t + 1):
+        for k in range(min(t + 1, T["depth"])):              # predecessors past `depth` weigh nothing
             pay = aggs[t - 1 - k] if t - 1 - k >= 0 else s_carry
             sin = sin + _mat(T["lb"][k]) @ pay
         incl = _mat(T["tile"]) @ sin + S
@@ -232,3 +235,9 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
                 got[t * tile_items + th * npt + i], st = _step(sec_type, c, xs[th, i], st)
     scale = max(1.0, np.max(np.abs(want)))
     assert np.max(np.abs(got - want)) < 2e-5 * scale
+    # look-back depth: A^(T*depth) vanishes, A^(T*(depth-1)) does not (fast poles: depth 1)
+    if sec_type == 1:
+        assert T["depth"] == 1
+    if sec_type == 2:
+        r = float(np.float32(coef[0]))
+        assert T["depth"] > 1 and r ** (KTHREADS * npt * T["depth"]) < 1e-30 <= r ** (KTHREADS * npt * (T["depth"] - 1))
