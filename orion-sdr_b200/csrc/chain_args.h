@@ -9,10 +9,10 @@
 
 namespace orion {
 
-constexpr int kThreads     = 128;   // threads per CTA (4 warps); one tile = kThreads * NPT outputs
+constexpr int kThreads     = 32;    // threads per CTA: one warp; one tile = 32 * NPT outputs
 constexpr int kMaxSections = 8;     // recursive sections per chain (LR4 = 2, LpDc = 3, + post sections)
 constexpr int kMaxTapTable = 2560;  // float capacity of the polyphase tap table held in the parameter bank
-constexpr int kMaxRowSamples = 96;  // R * Mb limit of the shared-memory staged FIR (row <= 768 B + pad)
+constexpr int kMaxRowSamples = 128; // R * Mb limit of the shared-memory staged FIR (row <= 1024 B + pad)
 
 enum : int { SEC_BIQUAD = 1, SEC_DC = 2, SEC_ONEPOLE = 3 };
 enum : int { OP_NONE = 0, OP_SQRT = 1, OP_SCALE = 2 };
@@ -40,11 +40,10 @@ struct SecParam {
 
 // 2x2 state-transition powers used by the chunked parallel scan (row-major a00,a01,a10,a11),
 // computed on the host in f64 from the f32 coefficients and rounded once.  n = items per
-// thread, T = kThreads * n = items per tile.
+// lane, T = 32 * n = items per (warp) tile.
 struct SecTables {
     float4 lv[5];     // A^(n*2^l), l = 0..4        (copy of SecParam::lv, for the host-logic tests)
     float4 lane[32];  // A^(n*lane)                  (carry into a lane's chunk)
-    float4 warp[4];   // A^(32*n*w), w = 0..3        (carry into a warp); warp[1] = one-warp step
     float4 lb[32];    // A^(T*k), k = 0..31          (inter-tile look-back)
     float4 lb32;      // A^(32*T)
     float4 tile;      // A^T

@@ -3,17 +3,19 @@
 //   [input-rate mixer] -> [FIR, keep every M-th] -> [demod-rate oscillator] -> [demod front map]
 //   -> [recursive sections]                                       one launch, one pass over HBM.
 //
-// Work decomposition (DESIGN.md "kernel"): the output stream is cut into tiles of
-// kThreads*NPT items; a CTA takes tiles in ticket order (persistent, dynamic), every thread owns
-// NPT = R*U CONSECUTIVE output items, so that
+// Work decomposition (DESIGN.md "kernel"): the output stream is cut into WARP TILES of
+// 32*NPT items.  A CTA is one warp (up to 12 resident per SM for the C1 shape); it takes tiles in
+// ticket order (persistent, dynamic), and every lane owns NPT = R*U CONSECUTIVE output items, so
 //   * the polyphase FIR slides an R-deep register window over the staged input (each staged
-//     sample is read once per thread and reused R times),
-//   * the discriminator needs one neighbour value per thread,
-//   * every recursive section is a per-thread serial recursion (the reference's exact
-//     arithmetic) stitched together by a block-level state-space scan and an inter-tile
-//     decoupled look-back.
-// Input staging: one cp.async.bulk.tensor (TMA) per interior tile into a padded row layout;
-// edge tiles (FIR history / ragged tail) use a cooperative loader into the same layout.
+//     sample is read once per lane and reused R times),
+//   * the discriminator needs one neighbour value per lane (a shuffle),
+//   * every recursive section is a per-lane serial recursion (the reference's exact arithmetic)
+//     stitched together by a warp-level state-space scan and an inter-tile decoupled look-back.
+// There is no block-level barrier anywhere: a warp that waits (TMA, look-back) stalls alone.
+// Input staging: one cp.async.bulk.tensor (TMA) per interior tile into a padded row layout,
+// issued for the NEXT tile as soon as the FIR of the current one has consumed the buffer, so the
+// load overlaps the demodulator / section / store phase; edge tiles (FIR history, ragged tail)
+// use a cooperative loader into the same layout.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (FMA only where written).
 #include "chain_args.h"
@@ -25,6 +27,7 @@
 namespace orion {
 
 #define DEV __device__ __forceinline__
+#define FULLMASK 0xffffffffu
 
 // ----------------------------------------------------------------------------------------------
 // small helpers
@@ -37,18 +40,15 @@ DEV float4 mm(const float4 a, const float4 b) {              // a * b
                        fmaf(a.z, b.x, a.w * b.z), fmaf(a.z, b.y, a.w * b.w));
 }
 DEV float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DEV float2 scale2(float2 z, float a) { return make_float2(z.x * a, z.y * a); }
+DEV float2 shfl_up2(float2 v, int d) {
+    return make_float2(__shfl_up_sync(FULLMASK, v.x, d), __shfl_up_sync(FULLMASK, v.y, d));
+}
+DEV float2 shfl2(float2 v, int src) {
+    return make_float2(__shfl_sync(FULLMASK, v.x, src), __shfl_sync(FULLMASK, v.y, src));
+}
 
 DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-DEV unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-DEV void st_release_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-DEV float2 ld_cg_f2(const float2 *p) { return __ldcg(p); }
 
 // mbarrier / TMA (PTX ISA: mbarrier, cp.async.bulk.tensor)
 DEV void mbar_init(uint32_t mbar, uint32_t count) {
@@ -74,32 +74,48 @@ DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint3
 }
 DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 128-bit single-copy-atomic global accesses for the look-back records
+DEV uint4 ld_relaxed_b128(const void *p) {
+    uint4 v;
+    asm volatile(
+        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
+        "ld.relaxed.gpu.global.b128 t, [%4];\n\t"
+        "mov.b128 {lo, hi}, t;\n\t"
+        "mov.b64 {%0, %1}, lo;\n\t"
+        "mov.b64 {%2, %3}, hi;\n\t}"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_relaxed_b128(void *p, uint4 v) {
+    asm volatile(
+        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
+        "mov.b64 lo, {%1, %2};\n\t"
+        "mov.b64 hi, {%3, %4};\n\t"
+        "mov.b128 t, {lo, hi};\n\t"
+        "st.relaxed.gpu.global.b128 [%0], t;\n\t}"
+        ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // oscillator: closed-form phase from the absolute call counter (NcoParam in chain_args.h)
 // ----------------------------------------------------------------------------------------------
 DEV float2 nco_unit(const NcoParam &p, unsigned long long k) {
     const unsigned long long ph = p.phase0 + p.step * (k - p.k0);
-    // top 32 bits as a signed fraction of pi in [-1, 1); the low word refines it to ~2^-40 turn
+    // top 32 bits as a signed fraction of pi in [-1, 1); the float conversion keeps 24 of them,
+    // the dropped bits come back as a first-order rotation
     const int hi = (int)(unsigned)(ph >> 32);
-    const float xh = (float)hi;                                   // rounded to 24 bits
-    const long long rem = ((long long)ph >> 8) - ((long long)xh << 24);   // exact remainder, 2^-56 turn units
-    const float x = xh * 4.656612873077393e-10f;                  // * 2^-31  (units of pi)
+    const float xh = (float)hi;
+    const long long rem = ((long long)ph >> 8) - ((long long)xh << 24);   // exact, 2^-56 turn units
     float s, c;
-    sincospif(x, &s, &c);
-    // first-order correction for the bits the float conversion dropped: d = rem * 2^-55 * pi
-    const float d = (float)rem * (3.14159265358979f * 2.7755575615628914e-17f);
+    __sincosf(xh * (4.656612873077393e-10f * 3.14159265358979323846f), &s, &c);   // MUFU: |err| <= 2^-21.4 on [-pi, pi]
+    const float d = (float)rem * (3.14159265358979f * 2.7755575615628914e-17f);   // rem * 2^-55 * pi
     return make_float2(fmaf(-s, d, c), fmaf(c, d, s));
 }
 // |z_k| of the reference recurrence: |w_f32|^(k mod 1024), renormalised to 1 every 1024 steps
 DEV float nco_amp(const NcoParam &p, unsigned long long k) {
     return fmaf((float)(unsigned)(k & 1023ull), p.amp_delta, 1.0f);
 }
-DEV float2 nco_phasor(const NcoParam &p, unsigned long long k) {
-    const float2 u = nco_unit(p, k);
-    const float a = nco_amp(p, k);
-    return make_float2(u.x * a, u.y * a);
-}
-DEV float2 scale2(float2 z, float a) { return make_float2(z.x * a, z.y * a); }
+DEV float2 nco_phasor(const NcoParam &p, unsigned long long k) { return scale2(nco_unit(p, k), nco_amp(p, k)); }
 DEV float2 cmul_fma(float2 z, float2 w) {   // phasor advance, reference form (rotator.rs:46-47)
     return make_float2(fmaf(z.x, w.x, -(z.y * w.y)), fmaf(z.y, w.x, z.x * w.y));
 }
@@ -125,23 +141,6 @@ DEV float atan2_approx(float y, float x) {
     return phi * sgn;
 }
 
-// one recursive-section step, reference arithmetic (iir.rs:34-40, iir.rs:160-163, cw.rs:38-39)
-DEV float sec_step(const SecParam &P, float x, float &s0, float &s1) {
-    float y;
-    if (P.type == SEC_BIQUAD) {
-        y = fmaf(x, P.c[0], s0);
-        s0 = fmaf(x, P.c[1], s1) - P.c[3] * y;
-        s1 = x * P.c[2] - P.c[4] * y;
-    } else if (P.type == SEC_DC) {            // y = x - x1 + r*y1 ; s0 = x1, s1 = y1
-        y = (x - s0) + P.c[0] * s1;
-        s0 = x;
-        s1 = y;
-    } else {                                  // y = a*y + (1-a)*x ; s0 = y
-        y = P.c[0] * s0 + P.c[1] * x;
-        s0 = y;
-    }
-    return y;
-}
 DEV float post_apply(const SecParam &P, float y) {
     if (P.post_op == OP_SQRT) return sqrtf(y);
     if (P.post_op == OP_SCALE) return y * P.post_scale;
@@ -163,55 +162,24 @@ DEV float2 load_x_mixed(const ChainArgs &a, long long s) {
     return x;
 }
 
-struct __align__(16) Shared {
-    unsigned long long mbar;
-    long long tile;
-    float2 zlast[kThreads];
-    float2 wtot[4];
-    float2 spre[4];
-    float2 s_tile_in;
-    float2 zhalo;
-};
-
 // ----------------------------------------------------------------------------------------------
-// inter-tile decoupled look-back for one section (warp 0, all lanes).  Returns the section state
-// at the start of `tile`.
+// inter-tile decoupled look-back for one section (the whole warp).  Returns the section state at
+// the start of `tile`.
 //
 // A link record is 16 bytes {state.x, state.y, epoch tag, 0} written and read with single 128-bit
 // accesses, so payload and flag can never be observed apart (no fences, one L2 round trip per
 // window of 32 predecessors).  T->depth is the number of predecessor tiles whose transition power
 // A^(T*k) is still non-zero in f32: tiles further back contribute exactly nothing, so for fast
-// decaying sections (the LR4 biquads) the look-back reads one aggregate and never waits for an
+// decaying sections (the LR4 biquads) the look-back reads a few aggregates and never waits for an
 // inclusive value; slow poles (the DC blocker) fall through to the classic chained form.
 // ----------------------------------------------------------------------------------------------
-DEV uint4 ld_relaxed_b128(const void *p) {
-    uint4 v;
-    asm volatile(
-        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
-        "ld.relaxed.gpu.global.b128 t, [%4];\n\t"
-        "mov.b128 {lo, hi}, t;\n\t"
-        "mov.b64 {%0, %1}, lo;\n\t"
-        "mov.b64 {%2, %3}, hi;\n\t}"
-        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-DEV void st_relaxed_b128(void *p, uint4 v) {
-    asm volatile(
-        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
-        "mov.b64 lo, {%1, %2};\n\t"
-        "mov.b64 hi, {%3, %4};\n\t"
-        "mov.b128 t, {lo, hi};\n\t"
-        "st.relaxed.gpu.global.b128 [%0], t;\n\t}"
-        ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int s, int lane) {
     float2 acc = make_float2(0.f, 0.f);
     float4 M = make_float4(1.f, 0.f, 0.f, 1.f);     // A^(T * 32 * window)
     long long base = tile - 1;
     int dist0 = 0;                                   // predecessor distance of lane 0 in this window
-    const float4 lbk = T->lb[lane];
-    const int depth = T->depth;
+    const float4 lbk = __ldg(&T->lb[lane]);
+    const int depth = __ldg(&T->depth);
     for (;;) {
         const long long idx = base - lane;
         const bool beyond = (dist0 + lane) >= depth;      // weight is exactly zero from here on
@@ -230,10 +198,10 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
                 incl = ri.z == a.epoch;
                 ready = incl || ra.z == a.epoch;
             }
-            const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
-            const unsigned ready_mask = __ballot_sync(0xffffffffu, ready);
+            const unsigned incl_mask = __ballot_sync(FULLMASK, incl);
+            const unsigned ready_mask = __ballot_sync(FULLMASK, ready);
             first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-            const unsigned need = (first_incl >= 31) ? 0xffffffffu : ((2u << first_incl) - 1u);
+            const unsigned need = (first_incl >= 31) ? FULLMASK : ((2u << first_incl) - 1u);
             if ((ready_mask & need) == need) break;
             if (++spins > (1 << 21)) {     // watchdog: never hang the device
                 if (lane == 0) atomicExch(a.err_flag, 1);
@@ -251,12 +219,12 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
-            term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
+            term.x += __shfl_xor_sync(FULLMASK, term.x, o);
+            term.y += __shfl_xor_sync(FULLMASK, term.y, o);
         }
         acc = add2(acc, term);
         if (first_incl < 32) break;
-        M = mm(M, T->lb32);
+        M = mm(M, __ldg(&T->lb32));
         base -= 32;
         dist0 += 32;
     }
@@ -270,7 +238,7 @@ DEV void publish(const ChainArgs &a, long long tile, int s, float2 v, bool inclu
 }
 
 // ----------------------------------------------------------------------------------------------
-// recursive sections: per-thread passes, specialised per section type (no per-item branches)
+// recursive sections: per-lane passes, specialised per section type (no per-item branches)
 // ----------------------------------------------------------------------------------------------
 template <int TYPE>
 DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
@@ -291,7 +259,7 @@ DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
 }
 
 // pass 2: the reference recursion from the true start state; writes the carried state when this
-// thread owns the last item of the call
+// lane owns the last item of the call
 template <int TYPE, int NPT>
 DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT], float s0, float s1,
                    long long jt, bool full) {
@@ -317,35 +285,44 @@ DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT]
 // ----------------------------------------------------------------------------------------------
 // staged-tile geometry (FRONT_STAGED)
 //   global row G covers samples [row_samples*G + O - Mb + 2, +row_samples)   (call-relative)
-//   tile t stages rows G0 .. G0+rows-1 with G0 = t*kThreads - HR, rows = kThreads + HR
+//   tile t stages rows G0 .. G0+rows-1 with G0 = t*32 - HR, rows = 32 + HR; lane l reads rows
+//   l .. l+HR.  row_pitch is an odd multiple of 16 bytes, so the 8 lanes of a quarter-warp hit 8
+//   different 16-byte bank groups on every LDS.128.
 // ----------------------------------------------------------------------------------------------
 DEV long long row_start_sample(const ChainArgs &a, long long G) {
     return (long long)a.row_samples * G + (a.O - a.Mb + 2);
 }
+DEV bool tile_is_interior(const ChainArgs &a, long long tile) {
+    const long long G0 = tile * kThreads - a.HR;
+    return a.use_tma && G0 >= a.tma_row0 && (G0 + kThreads + a.HR) <= (a.tma_row0 + a.tma_rows);
+}
 
-template <int R, int U>
-DEV void stage_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
-                    Shared &sh, unsigned &mbar_parity, int tid) {
+// start the TMA load of an interior tile (one elected lane); edge tiles are loaded in stage_wait
+DEV void stage_issue(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
+                     uint32_t mbar, int lane) {
+    if (tile_is_interior(a, tile) && lane == 0) {
+        const long long G0 = tile * kThreads - a.HR;
+        fence_proxy_async();               // earlier generic-proxy accesses to the buffer vs the async write
+        mbar_expect_tx(mbar, (uint32_t)((kThreads + a.HR) * a.row_pitch));
+        tma_load_2d(smem_u32(smem), tmap, 0, (int)(G0 - a.tma_row0), mbar);
+    }
+}
+
+DEV void stage_wait(const ChainArgs &a, long long tile, unsigned char *smem, uint32_t mbar, unsigned &parity,
+                    int lane) {
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
-    const bool interior = a.use_tma && G0 >= a.tma_row0 && (G0 + rows) <= (a.tma_row0 + a.tma_rows);
-    if (interior) {
-        const uint32_t mbar = smem_u32(&sh.mbar);
-        if (tid == 0) {
-            fence_proxy_async();           // earlier generic-proxy accesses to the tile vs the async write
-            mbar_expect_tx(mbar, (uint32_t)(rows * a.row_pitch));
-            tma_load_2d(smem_u32(smem), tmap, 0, (int)(G0 - a.tma_row0), mbar);
-        }
+    if (tile_is_interior(a, tile)) {
         int spins = 0;
-        while (!mbar_try_wait(mbar, mbar_parity)) {
+        while (!mbar_try_wait(mbar, parity)) {
             if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
         }
-        mbar_parity ^= 1u;
+        parity ^= 1u;
     } else {
         const int cpr = a.row_samples >> 1;                 // 16-byte chunks per row
         const int total = rows * cpr;
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
-        for (int c = tid; c < total; c += kThreads) {
+        for (int c = lane; c < total; c += kThreads) {
             const int rho = c / cpr;
             const int cc = c - rho * cpr;
             const long long s = row_start_sample(a, G0 + rho) + 2 * cc;
@@ -358,13 +335,13 @@ DEV void stage_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile,
             }
             *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v;
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (a.mix != MIX_NONE) {
         // in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
         const int cpr = a.row_samples >> 1;
         const float2 w = make_float2(a.pre.wre, a.pre.wim);
-        for (int rho = tid; rho < rows; rho += kThreads) {
+        for (int rho = lane; rho < rows; rho += kThreads) {
             const long long s0 = row_start_sample(a, G0 + rho);
             unsigned char *rp = smem + (size_t)rho * a.row_pitch;
             float2 p = make_float2(1.f, 0.f);
@@ -379,7 +356,7 @@ DEV void stage_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile,
                 *reinterpret_cast<float4 *>(rp + cc * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -391,9 +368,11 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
     return reinterpret_cast<const float2 *>(smem + (size_t)rho * a.row_pitch + (size_t)w * 8);
 }
 
-// polyphase FIR over the staged tile: thread `tid` produces outputs of blocks tid*R .. tid*R+R-1
+// polyphase FIR over the staged tile: lane l produces the outputs of blocks l*R .. l*R+R-1.
+// Per tap step: one LDS.128 (two adjacent samples), one tap pair from the parameter bank,
+// 4*R*U FMAs on an R-deep sliding register window.
 template <int R, int U>
-DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int tid, float2 (&z)[R * U]) {
+DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int lane, float2 (&z)[R * U]) {
     float2 acc[U][R];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -402,7 +381,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int tid, floa
 
     const int Mb = a.Mb, pitch = a.row_pitch, P_pad = a.P_pad, HR = a.HR;
     const int blk_bytes = Mb * 8;
-    const unsigned char *row_own = smem + (size_t)tid * pitch;
+    const unsigned char *row_own = smem + (size_t)lane * pitch;
     const int npairs = Mb >> 1;
     for (int q = 0; q < npairs; ++q) {
         const int off_q = (Mb - 2 - 2 * q) * 8;
@@ -439,8 +418,8 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int tid, floa
         for (int u = 0; u < U; ++u) z[i * U + u] = acc[u][i];
 }
 
-// one FIR output evaluated straight from the virtual stream (any shape).  exact != 0 reproduces
-// the reference's accumulation order and rounding (fir.rs:57-66 unfused, fir.rs:229-247 fused).
+// one FIR output evaluated straight from the virtual stream (any shape), in the reference's
+// accumulation order and rounding (fir.rs:57-66 unfused; fir.rs:229-247 fused)
 DEV float2 fir_global_one(const ChainArgs &a, long long j) {
     const long long n = (long long)a.M * j;
     float re = 0.f, im = 0.f;
@@ -479,88 +458,23 @@ DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, long lo
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
+        re += __shfl_xor_sync(FULLMASK, re, o);
+        im += __shfl_xor_sync(FULLMASK, im, o);
     }
     return make_float2(re, im);
 }
 
 // ----------------------------------------------------------------------------------------------
-// one tile
+// everything after the front: demod-rate oscillator, front map, recursive sections, store
 // ----------------------------------------------------------------------------------------------
-template <int FRONT, int R, int U>
-DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
-                      Shared &sh, unsigned &mbar_parity) {
-    constexpr int NPT = R * U;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+template <int NPT>
+DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo) {
     const long long j0 = tile * (long long)(kThreads * NPT);
-    const long long jt = j0 + (long long)tid * NPT;
+    const long long jt = j0 + (long long)lane * NPT;
     const bool is_c32_in = a.demod != DEMOD_F32;
     const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
     const bool post_osc = (a.demod == DEMOD_FM && a.translate) || a.demod == DEMOD_SSB || a.demod == DEMOD_USB;
-
-    float2 z[NPT];
-    float  u[NPT];
-#pragma unroll
-    for (int i = 0; i < NPT; ++i) { z[i] = make_float2(0.f, 0.f); u[i] = 0.f; }
-    float2 zhalo = make_float2(0.f, 0.f);           // item j0-1 (thread 0 only)
-
-    // ---------------- front: produce z[] (C32 items at the demod rate) or u[] (f32 items) --------
-    if (FRONT == FRONT_STAGED) {
-        stage_tile<R, U>(a, tmap, tile, smem, sh, mbar_parity, tid);
-        fir_staged<R, U>(a, smem, tid, z);
-        if (need_prev && j0 > 0 && wid == 0) {
-            const long long G0 = tile * kThreads - a.HR;
-            zhalo = fir_staged_one(a, smem, G0, j0 - 1, lane);
-        }
-    } else if (FRONT == FRONT_GLOBAL) {
-#pragma unroll
-        for (int i = 0; i < NPT; ++i)
-            if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
-        if (need_prev && j0 > 0 && tid == 0) zhalo = fir_global_one(a, j0 - 1);
-    } else {
-        if (is_c32_in) {
-            const float2 *in = reinterpret_cast<const float2 *>(a.in);
-            const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 2 == 0);
-            if (al16 && jt + NPT <= a.n_out) {
-#pragma unroll
-                for (int i = 0; i < NPT; i += 2) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
-                    z[i] = make_float2(v.x, v.y);
-                    z[i + 1] = make_float2(v.z, v.w);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NPT; ++i)
-                    if (jt + i < a.n_out) z[i] = __ldg(in + jt + i);
-            }
-            if (a.mix != MIX_NONE) {
-                const unsigned long long k0 = a.pre.kbase + (unsigned long long)jt + 1ull;
-                float2 p = nco_unit(a.pre, k0);
-                const float2 w = make_float2(a.pre.wre, a.pre.wim);
-#pragma unroll
-                for (int i = 0; i < NPT; ++i) {
-                    z[i] = mix_apply(a.mix, z[i], scale2(p, nco_amp(a.pre, k0 + i)));
-                    p = cmul_fma(p, w);
-                }
-            }
-            if (need_prev && j0 > 0 && tid == 0) zhalo = load_x_mixed(a, j0 - 1);
-        } else {
-            const float *in = reinterpret_cast<const float *>(a.in);
-            const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 4 == 0);
-            if (al16 && jt + NPT <= a.n_out) {
-#pragma unroll
-                for (int i = 0; i < NPT; i += 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
-                    u[i] = v.x; u[i + 1] = v.y; u[i + 2] = v.z; u[i + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NPT; ++i)
-                    if (jt + i < a.n_out) u[i] = __ldg(in + jt + i);
-            }
-        }
-    }
+    const bool full = jt + NPT <= a.n_out;
 
     // ---------------- demod-rate oscillator + front map ------------------------------------------
     if (is_c32_in && a.demod != DEMOD_NONE) {
@@ -577,18 +491,15 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
                 z[i] = make_float2(z[i].x * cr - z[i].y * ci, z[i].x * ci + z[i].y * cr);
                 p = cmul_fma(p, w);
             }
-            if (j0 > 0 && tid == 0) {
+            if (j0 > 0 && lane == 0) {
                 const float2 ph = nco_phasor(a.post, a.post.kbase + (unsigned long long)j0);
                 const float cr = ph.x, ci = -ph.y;
                 zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
             }
         }
         if (need_prev) {
-            sh.zlast[tid] = z[NPT - 1];
-            __syncthreads();
-            float2 prev;
-            if (tid > 0) prev = sh.zlast[tid - 1];
-            else prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+            float2 prev = shfl_up2(z[NPT - 1], 1);
+            if (lane == 0) prev = (j0 > 0) ? zhalo : a.carry_in->prev;
             // carried discriminator state for the next call
             if (a.n_out > 0 && jt <= a.n_out - 1 && a.n_out - 1 < jt + NPT) {
                 float2 last = z[0];
@@ -634,13 +545,12 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
         }
     }
 
-    // ---------------- recursive sections: serial in-thread, scanned across threads and tiles -----
+    // ---------------- recursive sections: serial in-lane, scanned across lanes and tiles ---------
     if (a.demod != DEMOD_NONE) {
-        const bool full = jt + NPT <= a.n_out;
         for (int s = 0; s < a.nsec; ++s) {
             const SecParam &P = a.sec[s];
             const SecTables *T = a.tabs + s;
-            // pass 1: end state of this thread's chunk from a zero start state, as the dot product
+            // pass 1: end state of this lane's chunk from a zero start state, as the dot product
             // with the section's state impulse responses  e = sum_i A^(NPT-1-i) B u[i]
             float2 E = make_float2(0.f, 0.f);
             if (full) {
@@ -654,37 +564,18 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
 #pragma unroll
             for (int l = 0; l < 5; ++l) {
                 const int d = 1 << l;
-                const float ox = __shfl_up_sync(0xffffffffu, E.x, d);
-                const float oy = __shfl_up_sync(0xffffffffu, E.y, d);
-                if (lane >= d) E = add2(E, mv(P.lv[l], make_float2(ox, oy)));
+                const float2 o = shfl_up2(E, d);
+                if (lane >= d) E = add2(E, mv(P.lv[l], o));
             }
-            float2 X = make_float2(__shfl_up_sync(0xffffffffu, E.x, 1), __shfl_up_sync(0xffffffffu, E.y, 1));
+            float2 X = shfl_up2(E, 1);
             if (lane == 0) X = make_float2(0.f, 0.f);
-            if (lane == 31) sh.wtot[wid] = E;
-            __syncthreads();
-            if (wid == 0) {
-                // tile aggregate, published as soon as it exists; then the look-back
-                float2 S = make_float2(0.f, 0.f);
-                float2 spre[4];
-                const float4 wstep = T->warp[1];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    spre[w] = S;
-                    S = add2(mv(wstep, S), sh.wtot[w]);
-                }
-                if (lane == 0) publish(a, tile, s, S, false);
-                const float2 sin = lookback(a, T, tile, s, lane);
-                if (lane == 0) {
-                    publish(a, tile, s, add2(mv(T->tile, sin), S), true);
-                    sh.s_tile_in = sin;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) sh.spre[w] = spre[w];
-                }
-            }
-            __syncthreads();
-            // state at the start of this thread's chunk
-            const float2 sw = add2(sh.spre[wid], mv(T->warp[wid], sh.s_tile_in));
-            const float2 st = add2(X, mv(T->lane[lane], sw));
+            const float2 agg = shfl2(E, 31);
+            // the tile aggregate is published as soon as it exists; then the look-back
+            if (lane == 0) publish(a, tile, s, agg, false);
+            const float2 sin = lookback(a, T, tile, s, lane);
+            if (lane == 0) publish(a, tile, s, add2(mv(__ldg(&T->tile), sin), agg), true);
+            // state at the start of this lane's chunk
+            const float2 st = add2(X, mv(__ldg(&T->lane[lane]), sin));
             if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st.x, st.y, jt, full);
             else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st.x, st.y, jt, full);
             else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st.x, st.y, jt, full);
@@ -695,7 +586,7 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
     if (a.demod == DEMOD_NONE) {
         float2 *out = reinterpret_cast<float2 *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
-        if (al16 && jt + NPT <= a.n_out) {
+        if (al16 && full) {
 #pragma unroll
             for (int i = 0; i < NPT; i += 2)
                 *reinterpret_cast<float4 *>(out + jt + i) = make_float4(z[i].x, z[i].y, z[i + 1].x, z[i + 1].y);
@@ -707,7 +598,7 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
     } else {
         float *out = reinterpret_cast<float *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 4 == 0);
-        if (al16 && jt + NPT <= a.n_out) {
+        if (al16 && full) {
 #pragma unroll
             for (int i = 0; i < NPT; i += 4)
                 *reinterpret_cast<float4 *>(out + jt + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
@@ -721,8 +612,8 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
     // ---------------- end-of-call duties (last tile) ------------------------------------------
     if (tile == a.ntiles - 1) {
         if (a.H > 0)
-            for (int k = tid; k < a.H; k += kThreads) a.hist_out[k] = load_x(a, a.n_in - a.H + k);
-        if (tid == 0) {
+            for (int k = lane; k < a.H; k += kThreads) a.hist_out[k] = load_x(a, a.n_in - a.H + k);
+        if (lane == 0) {
             if (!need_prev || a.n_out == 0) a.carry_out->prev = a.carry_in->prev;
             for (int s = 0; s < kMaxSections; ++s)
                 if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
@@ -730,33 +621,112 @@ DEV void process_tile(const ChainArgs &a, const CUtensorMap *tmap, long long til
     }
 }
 
+// direct front: items straight from global memory (rate-1 blocks)
+template <int NPT>
+DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 &zhalo) {
+    const long long j0 = tile * (long long)(kThreads * NPT);
+    const long long jt = j0 + (long long)lane * NPT;
+    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    if (a.demod != DEMOD_F32) {
+        const float2 *in = reinterpret_cast<const float2 *>(a.in);
+        const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 2 == 0);
+        if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+            for (int i = 0; i < NPT; i += 2) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
+                z[i] = make_float2(v.x, v.y);
+                z[i + 1] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) z[i] = __ldg(in + jt + i);
+        }
+        if (a.mix != MIX_NONE) {
+            const unsigned long long k0 = a.pre.kbase + (unsigned long long)jt + 1ull;
+            float2 p = nco_unit(a.pre, k0);
+            const float2 w = make_float2(a.pre.wre, a.pre.wim);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {
+                z[i] = mix_apply(a.mix, z[i], scale2(p, nco_amp(a.pre, k0 + i)));
+                p = cmul_fma(p, w);
+            }
+        }
+        if (need_prev && j0 > 0 && lane == 0) zhalo = load_x_mixed(a, j0 - 1);
+    } else {
+        const float *in = reinterpret_cast<const float *>(a.in);
+        const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 4 == 0);
+        if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+            for (int i = 0; i < NPT; i += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
+                u[i] = v.x; u[i + 1] = v.y; u[i + 2] = v.z; u[i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) u[i] = __ldg(in + jt + i);
+        }
+    }
+}
+
 template <int FRONT, int R, int U>
 __global__ void __launch_bounds__(kThreads)
 chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int NPT = R * U;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ Shared sh;
-    unsigned mbar_parity = 0;
+    __shared__ __align__(8) unsigned long long mbar_storage;
+    const int lane = threadIdx.x;
+    const uint32_t mbar = smem_u32(&mbar_storage);
+    unsigned parity = 0;
     if (FRONT == FRONT_STAGED) {
-        if (threadIdx.x == 0) {
-            mbar_init(smem_u32(&sh.mbar), 1);
+        if (lane == 0) {
+            mbar_init(mbar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
+        __syncwarp();
     }
-    if (a.serial) {
-        for (long long t = 0; t < a.ntiles; ++t) {
-            process_tile<FRONT, R, U>(a, &tmap, t, smem, sh, mbar_parity);
-            __syncthreads();
+    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+
+    long long serial_next = 0;
+    auto take_ticket = [&]() -> long long {
+        if (a.serial) return serial_next++;
+        long long t = 0;
+        if (lane == 0) t = (long long)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
+        return __shfl_sync(FULLMASK, t, 0);
+    };
+
+    long long tile = take_ticket();
+    if (FRONT == FRONT_STAGED && tile < a.ntiles) stage_issue(a, &tmap, tile, smem, mbar, lane);
+    while (tile < a.ntiles) {
+        float2 z[NPT];
+        float  u[NPT];
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) { z[i] = make_float2(0.f, 0.f); u[i] = 0.f; }
+        float2 zhalo = make_float2(0.f, 0.f);           // item j0-1 (lane 0 only)
+        const long long j0 = tile * (long long)(kThreads * NPT);
+        long long next;
+
+        if (FRONT == FRONT_STAGED) {
+            stage_wait(a, tile, smem, mbar, parity, lane);
+            fir_staged<R, U>(a, smem, lane, z);
+            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, smem, tile * kThreads - a.HR, j0 - 1, lane);
+            __syncwarp();                               // every lane is done with the staged buffer:
+            next = take_ticket();                       // prefetch the next tile behind the rest of this one
+            if (next < a.ntiles) stage_issue(a, &tmap, next, smem, mbar, lane);
+        } else if (FRONT == FRONT_GLOBAL) {
+            const long long jt = j0 + (long long)lane * NPT;
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+                if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
+            if (need_prev && j0 > 0 && lane == 0) zhalo = fir_global_one(a, j0 - 1);
+            next = take_ticket();
+        } else {
+            front_direct<NPT>(a, tile, lane, z, u, zhalo);
+            next = take_ticket();
         }
-        return;
-    }
-    for (;;) {
-        __syncthreads();                       // everyone is done with sh.tile / the staged tile
-        if (threadIdx.x == 0) sh.tile = (long long)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
-        __syncthreads();
-        const long long tile = sh.tile;
-        if (tile >= a.ntiles) break;
-        process_tile<FRONT, R, U>(a, &tmap, tile, smem, sh, mbar_parity);
+        finish_tile<NPT>(a, tile, lane, z, u, zhalo);
+        tile = next;
     }
 }
 
@@ -769,7 +739,7 @@ template <int FRONT, int R, int U>
 static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U>; }
 
 chain_kernel_t select_kernel(int front, int R, int U) {
-    if (front == FRONT_DIRECT) return kptr<FRONT_DIRECT, 8, 1>();
+    if (front == FRONT_DIRECT) return kptr<FRONT_DIRECT, 16, 1>();
     if (front == FRONT_GLOBAL) return kptr<FRONT_GLOBAL, 8, 1>();
     if (U == 1) {
         switch (R) {
@@ -791,6 +761,8 @@ chain_kernel_t select_kernel(int front, int R, int U) {
 
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int *ctas_per_sm) {
     cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads, dyn_smem);
 }

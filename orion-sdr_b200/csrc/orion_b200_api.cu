@@ -169,7 +169,6 @@ void build_tables(SecParam &p, int npt, SecTables *t) {
     const unsigned long long n = (unsigned long long)npt, T = n * kThreads;
     for (int l = 0; l < 5; ++l) { t->lv[l] = f4(mpow(A, n << l)); p.lv[l] = t->lv[l]; }
     for (int k = 0; k < 32; ++k) t->lane[k] = f4(mpow(A, n * k));
-    for (int w = 0; w < 4; ++w) t->warp[w] = f4(mpow(A, 32ull * n * w));
     for (int k = 0; k < 32; ++k) t->lb[k] = f4(mpow(A, T * k));
     t->lb32 = f4(mpow(A, T * 32ull));
     t->tile = f4(mpow(A, T));
@@ -232,7 +231,7 @@ struct FirPlan {
     std::vector<float2> taps2;     // [u][q][c]
 };
 
-const size_t kMaxStagedSmem = 200 * 1024;
+const size_t kMaxStagedSmem = 100 * 1024;
 
 void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl) {
     const int L = (int)taps.size();
@@ -384,7 +383,7 @@ int npt_of(const orion_b200_block *b) { return b->plan.R * b->plan.U; }
 int finalize_plan(orion_b200_block *b) {
     CK(cudaSetDevice(b->device));
     if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
-    else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 8; b->plan.U = 1; }
+    else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
     CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, &b->ctas_per_sm));
@@ -575,12 +574,14 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         const long long start = rs * row0 + off;
         const long long nrows = ((long long)n_in - start) / rs;
         if (enc && nrows >= b->plan.rows) {
-            const cuuint64_t gdim[2] = { (cuuint64_t)(2 * rs), (cuuint64_t)nrows };
+            // 8-byte elements (one complex sample each); the box is 2 elements wider than the tensor
+            // row, so the TMA zero-fills the 16-byte pad that keeps the rows bank-conflict free
+            const cuuint64_t gdim[2] = { (cuuint64_t)rs, (cuuint64_t)nrows };
             const cuuint64_t gstr[1] = { (cuuint64_t)(rs * 8) };
-            const cuuint32_t box[2] = { (cuuint32_t)(b->plan.row_pitch / 4), (cuuint32_t)b->plan.rows };
+            const cuuint32_t box[2] = { (cuuint32_t)(b->plan.row_pitch / 8), (cuuint32_t)b->plan.rows };
             const cuuint32_t estr[2] = { 1, 1 };
             void *base = (void *)(reinterpret_cast<const char *>(d_in) + start * 8);
-            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr,
+            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r == CUDA_SUCCESS) { a.use_tma = 1; a.tma_row0 = row0; a.tma_rows = nrows; }

@@ -234,8 +234,8 @@ def debug_scan_tables(sec_type, coeffs, npt):
     t = np.zeros(nf + 32, np.float32)
     L.orion_b200_debug_scan_tables(sec_type, c.ctypes.data, npt, t.ctypes.data, t.size)
     m = t[:nf].reshape(-1, 4)
-    return {"lv": m[0:5], "lane": m[5:37], "warp": m[37:41], "lb": m[41:73], "lb32": m[73], "tile": m[74],
-            "depth": int(m[75].view(np.int32)[0]), "imp": t[nf:nf + 2 * npt].reshape(npt, 2)}
+    return {"lv": m[0:5], "lane": m[5:37], "lb": m[37:69], "lb32": m[69], "tile": m[70],
+            "depth": int(m[71].view(np.int32)[0]), "imp": t[nf:nf + 2 * npt].reshape(npt, 2)}
 
 
 _DT = {ITEM_F32: np.float32, ITEM_C32: np.complex64}

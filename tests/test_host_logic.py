@@ -13,7 +13,7 @@ import oracle
 import orion_b200 as ob
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KTHREADS = 128
+KTHREADS = 32
 
 
 def test_library_exports_every_declared_symbol():
@@ -130,7 +130,7 @@ def test_staged_fir_plan_reproduces_direct_fir(kind, L, M, rng):
     R, U, Mb = plan["R"], plan["U"], plan["Mb"]
     assert Mb == M * U and Mb % 2 == 0 and plan["P_pad"] % R == 0 and plan["HR"] * R == plan["P_pad"]
     assert plan["row_pitch"] % 16 == 0 and (plan["row_pitch"] // 16) % 2 == 1      # conflict-free lane stride
-    assert plan["rows"] == KTHREADS + plan["HR"] <= 256
+    assert plan["rows"] == KTHREADS + plan["HR"] <= 256 and plan["row_pitch"] <= 2048
     H = plan["H"]
     assert H % 2 == 0 and H >= L
     # the first staged sample of tile 0 must lie inside the history
@@ -145,7 +145,7 @@ def test_staged_fir_plan_reproduces_direct_fir(kind, L, M, rng):
 
 
 def test_large_shapes_fall_back_to_global_front(rng):
-    plan = ob.debug_fir_plan(ob.FIR_DECIM, rng.standard_normal(513).astype(np.float32), 128)
+    plan = ob.debug_fir_plan(ob.FIR_DECIM, rng.standard_normal(513).astype(np.float32), 256)
     assert plan["front"] == 2 and plan["H"] >= 513
 
 
@@ -177,7 +177,7 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
     c = np.zeros(5)
     c[:len(coef)] = np.asarray(coef, np.float32).astype(np.float64)
     T = ob.debug_scan_tables(sec_type, c, npt)
-    ntiles, tile_items = 3, KTHREADS * npt
+    ntiles, tile_items = 5, KTHREADS * npt
     x = rng.standard_normal(ntiles * tile_items)
     s_carry = rng.standard_normal(2) * (0.1 if sec_type != 2 else 1.0)
     if sec_type == 3:
@@ -203,20 +203,14 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
         e_dot = xs @ T["imp"].astype(np.float64)
         assert np.allclose(e_dot, e, rtol=1e-5, atol=1e-6 * max(1.0, np.max(np.abs(e))))
         E = e_dot.copy()
-        for w in range(4):                                   # Kogge-Stone inside each warp
-            for l in range(5):
-                d = 1 << l
-                prev = E[w * 32:(w + 1) * 32].copy()
-                for lane in range(d, 32):
-                    E[w * 32 + lane] = prev[lane] + _mat(T["lv"][l]) @ prev[lane - d]
+        for l in range(5):                                   # Kogge-Stone across the warp
+            d = 1 << l
+            prev = E.copy()
+            for lane in range(d, 32):
+                E[lane] = prev[lane] + _mat(T["lv"][l]) @ prev[lane - d]
         X = np.zeros_like(E)
-        for w in range(4):
-            X[w * 32 + 1:(w + 1) * 32] = E[w * 32:(w + 1) * 32 - 1]
-        S = np.zeros(2)
-        spre = []
-        for w in range(4):
-            spre.append(S.copy())
-            S = _mat(T["warp"][1]) @ S + E[w * 32 + 31]
+        X[1:] = E[:-1]
+        S = E[31].copy()
         aggs.append(S.copy())
         # look-back over aggregates down to the carried state (virtual tile -1)
         sin = np.zeros(2)
@@ -228,16 +222,14 @@ def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
             assert np.allclose(sin, tile_in, rtol=1e-5, atol=1e-6)
         tile_in = incl
         for th in range(KTHREADS):
-            w, lane = divmod(th, 32)
-            sw = spre[w] + _mat(T["warp"][w]) @ sin
-            st = X[th] + _mat(T["lane"][lane]) @ sw
+            st = X[th] + _mat(T["lane"][th]) @ sin
             for i in range(npt):
                 got[t * tile_items + th * npt + i], st = _step(sec_type, c, xs[th, i], st)
     scale = max(1.0, np.max(np.abs(want)))
     assert np.max(np.abs(got - want)) < 2e-5 * scale
     # look-back depth: A^(T*depth) vanishes, A^(T*(depth-1)) does not (fast poles: depth 1)
     if sec_type == 1:
-        assert T["depth"] == 1
+        assert 1 <= T["depth"] <= 8            # fast poles: a handful of predecessor tiles at most
     if sec_type == 2:
         r = float(np.float32(coef[0]))
         assert T["depth"] > 1 and r ** (KTHREADS * npt * T["depth"]) < 1e-30 <= r ** (KTHREADS * npt * (T["depth"] - 1))
