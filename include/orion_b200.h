@@ -226,9 +226,11 @@ uint64_t orion_b200_block_launch_count(const orion_b200_block *b);
  * P_pad, HR, row_samples, row_pitch, rows, H}; returns the polyphase tap-table length (floats). */
 size_t orion_b200_debug_fir_plan(int fir_kind, const float *taps, size_t ntaps, size_t m, int info[12],
                                  float *table, size_t cap, float *g, size_t gcap);
-/* Scan tables of one recursive section [host-only]: type 1 biquad {b0,b1,b2,a1,a2}, 2 DC {r},
- * 3 one-pole {a, 1-a}; npt = items per thread.  Returns the table length in floats. */
-size_t orion_b200_debug_scan_tables(int type, const float c[5], int npt, float *tables, size_t cap);
+/* Scan tables of one section group [host-only]: sections = nsec x {type, c0..c4}  (nsec <= 2; type 1 biquad
+ * {b0,b1,b2,a1,a2}, 2 DC {r}, 3 one-pole {a, 1-a}); npt = items per lane.  out receives
+ * {D, depth, agg_only, 0, imp[16][4], lv[5][16], lane[32][16], lb[32][16], lb32[16], tile[16]};
+ * returns the length in floats. */
+size_t orion_b200_debug_group_tables(const float *sections, size_t nsec, int npt, float *out, size_t cap);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,10 @@
 
 namespace orion {
 
-constexpr int kThreads     = 32;    // threads per CTA: one warp; one tile = 32 * NPT outputs
+constexpr int kThreads     = 32;    // lanes per (warp) tile: one tile = 32 * NPT outputs
+constexpr int kWarpsPerCta = 8;     // default warps per CTA; they share a ring of staged-tile slots
+constexpr int kMaxWarpsPerCta = 16;
+constexpr int kMaxStages   = 8;     // slots in the ring
 constexpr int kMaxSections = 8;     // recursive sections per chain (LR4 = 2, LpDc = 3, + post sections)
 constexpr int kMaxTapTable = 2560;  // float capacity of the polyphase tap table held in the parameter bank
 constexpr int kMaxRowSamples = 128; // R * Mb limit of the shared-memory staged FIR (row <= 1024 B + pad)
@@ -24,31 +27,39 @@ enum : int { FRONT_DIRECT = 0,   // no FIR: items are read straight from global 
              FRONT_STAGED = 1,   // polyphase FIR on a TMA / cooperatively staged shared-memory tile
              FRONT_GLOBAL = 2 }; // any-shape FIR evaluated from global memory (large M, huge tap sets)
 
-// One first/second-order recursive section.  Coefficients are the reference's f32 values;
-// the per-sample arithmetic in sec_step() follows the reference op for op.
-constexpr int kMaxNpt = 16;         // items per thread (R * U)
+constexpr int kMaxNpt      = 16;    // items per lane (R * U)
+constexpr int kMaxGroups   = 4;     // linear section groups per chain
+constexpr int kMaxGroupDim = 4;     // state dimension of one group (two second-order sections: 4x4 powers stay in registers)
 
+// One first/second-order recursive section.  Coefficients are the reference's f32 values;
+// the per-sample arithmetic in sec_step_t() follows the reference op for op.
 struct SecParam {
     int   type;        // SEC_*
     int   post_op;     // OP_* applied to the section's output before the next section
     float c[5];        // BIQUAD: b0,b1,b2,a1,a2 | DC: r | ONEPOLE: a, (1-a)
     float post_scale;  // OP_SCALE factor
-    // launch-plan data (filled by the host for the plan's items-per-thread n; parameter bank):
-    float2 imp[kMaxNpt];   // state impulse responses A^(n-1-i) B: zero-state end state = sum_i imp[i]*x[i]
-    float4 lv[5];          // A^(n*2^l), l = 0..4   (warp-level Kogge-Stone scan)
 };
 
-// 2x2 state-transition powers used by the chunked parallel scan (row-major a00,a01,a10,a11),
-// computed on the host in f64 from the f32 coefficients and rounded once.  n = items per
-// lane, T = 32 * n = items per (warp) tile.
-struct SecTables {
-    float4 lv[5];     // A^(n*2^l), l = 0..4        (copy of SecParam::lv, for the host-logic tests)
-    float4 lane[32];  // A^(n*lane)                  (carry into a lane's chunk)
-    float4 lb[32];    // A^(T*k), k = 0..31          (inter-tile look-back)
-    float4 lb32;      // A^(32*T)
-    float4 tile;      // A^T
-    int    depth;     // predecessor tiles with a non-zero weight: A^(T*k) == 0 in f32 for k >= depth
-    int    pad[3];
+// A group = a maximal run of sections handed over linearly (post_op == NONE inside the run).
+// For the chunked scan the whole run is ONE linear system with state x = (s^0, s^1, ...) of
+// dimension D = 2 * count, x' = Ac x + Bc u: its zero-state tile aggregate depends on the
+// tile's own input only, so one look-back per group and tile suffices and no aggregate ever
+// waits for a predecessor.  All powers are computed on the host in f64 and rounded once;
+// n = items per lane, T = 32 * n = items per (warp) tile.
+struct GroupParam {
+    int   first, count;      // sections [first, first + count)
+    int   D;                 // 2 * count
+    int   agg_only;          // depth <= 32: predecessors' aggregates alone determine the start state
+    float imp[kMaxNpt][kMaxGroupDim];                  // Ac^(n-1-i) Bc: zero-state end state = sum_i imp[i] * u[i]
+    float lv[5][kMaxGroupDim * kMaxGroupDim];          // Ac^(n*2^l), l = 0..4, row-major D x D (stride D)
+};
+struct GroupTables {         // global memory, one per group
+    float lane[32][kMaxGroupDim * kMaxGroupDim];       // Ac^(n*lane)   (carry into a lane's chunk)
+    float lb[32][kMaxGroupDim * kMaxGroupDim];         // Ac^(T*k)      (inter-tile look-back)
+    float lb32[kMaxGroupDim * kMaxGroupDim];           // Ac^(32*T)
+    float tile[kMaxGroupDim * kMaxGroupDim];           // Ac^T
+    int   depth;             // predecessor tiles with a non-zero weight: Ac^(T*k) == 0 in f32 for k >= depth
+    int   pad[3];
 };
 
 // Oscillator (Rotator / Nco).  Phase is a 64-bit fraction of a turn:
@@ -73,9 +84,10 @@ struct CarryState {              // streaming state carried between process() ca
     float2 pad;
 };
 
-struct TileLink {                // one per (tile, section): decoupled look-back records, each
-    uint4 agg;                   //   {state.x, state.y, epoch tag, 0} written/read as ONE 128-bit access:
-    uint4 incl;                  //   agg = end state from a zero start state, incl = true end state
+constexpr int kLinkRecs = 3;     // 16-byte records per link value: {x0, x1, x2, epoch tag} each
+struct TileLink {                // one per (tile, group): decoupled look-back records; every record is
+    uint4 agg[kLinkRecs];        //   written/read as ONE 128-bit access, so payload and tag travel together.
+    uint4 incl[kLinkRecs];       //   agg = tile end state from a zero start state, incl = true end state
 };
 
 struct ChainArgs {
@@ -102,6 +114,8 @@ struct ChainArgs {
     int   HR;                    // halo rows = P_pad / R
     int   row_samples;           // R * Mb
     int   row_pitch;             // bytes, odd multiple of 16
+    int   row_shift;             // log2(row_samples) when it is a power of two, else -1
+    int   nstages;               // slots in the CTA's stage ring (1 in serial mode)
     int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
     long long tma_row0;          // global row index of tensor-map row 0
     long long tma_rows;          // rows the tensor map covers
@@ -112,15 +126,15 @@ struct ChainArgs {
     NcoParam post;               // demod-rate oscillator (FM translate / SSB BFO / USB mix)
     // recursive sections
     int   nsec;
+    int   ngroups;
     SecParam sec[kMaxSections];
-    const SecTables *tabs;       // [nsec]
+    GroupParam grp[kMaxGroups];
+    const GroupTables *gtabs;    // [ngroups]
     // carried state, ping-pong across calls
     const CarryState *carry_in;
     CarryState       *carry_out;
     // inter-tile links
-    TileLink *links;             // [ntiles][kMaxSections]
-    unsigned long long *ticket;
-    unsigned long long  ticket_base;
+    TileLink *links;             // [ntiles][kMaxGroups]
     unsigned int epoch;
     int   ntiles;
     int   serial;                // debug: tiles run one after another (grid = 1)

@@ -127,8 +127,9 @@ DEV float2 mix_apply(int mix, float2 x, float2 p) {
     return make_float2(x.x * p.x - x.y * p.y, x.x * p.y + x.y * p.x);   // nco.rs:63-66
 }
 
-// util.rs:305-322, op for op
-DEV float atan2_approx(float y, float x) {
+// util.rs:305-322, op for op.  One shared copy: the per-item call sites would otherwise unroll it
+// NPT times and push the hot path out of the instruction cache.
+__device__ __noinline__ float atan2_approx(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const bool sw = ax < ay;
     const float mn = sw ? ax : ay, mx = sw ? ay : ax;
@@ -163,28 +164,82 @@ DEV float2 load_x_mixed(const ChainArgs &a, long long s) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// inter-tile decoupled look-back for one section (the whole warp).  Returns the section state at
-// the start of `tile`.
-//
-// A link record is 16 bytes {state.x, state.y, epoch tag, 0} written and read with single 128-bit
-// accesses, so payload and flag can never be observed apart (no fences, one L2 round trip per
-// window of 32 predecessors).  T->depth is the number of predecessor tiles whose transition power
-// A^(T*k) is still non-zero in f32: tiles further back contribute exactly nothing, so for fast
-// decaying sections (the LR4 biquads) the look-back reads a few aggregates and never waits for an
-// inclusive value; slow poles (the DC blocker) fall through to the classic chained form.
+// section groups: D-dimensional state-space scan (GroupParam / GroupTables in chain_args.h)
 // ----------------------------------------------------------------------------------------------
-DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int s, int lane) {
-    float2 acc = make_float2(0.f, 0.f);
-    float4 M = make_float4(1.f, 0.f, 0.f, 1.f);     // A^(T * 32 * window)
+template <int D>
+DEV void matvec(const float *__restrict__ M, const float (&v)[D], float (&out)[D]) {   // row-major D x D
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc = fmaf(M[r * D + c], v[c], acc);
+        out[r] = acc;
+    }
+}
+template <int D>
+DEV void load_mat(const float *__restrict__ g, float (&M)[D * D]) {      // D*D floats, 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < D * D; i += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(g + i));
+        M[i] = v.x; M[i + 1] = v.y; M[i + 2] = v.z; M[i + 3] = v.w;
+    }
+}
+
+// A link value is D floats in ceil(D/3) records of 16 bytes {x, x, x, epoch tag}; every record is
+// written and read with ONE 128-bit access, so payload and tag can never be observed apart (no
+// fences, one L2 round trip per window of 32 predecessors).
+template <int D>
+DEV void publish(const ChainArgs &a, long long tile, int g, const float (&v)[D], bool inclusive) {
+    TileLink *lk = a.links + tile * kMaxGroups + g;
+    uint4 *dst = inclusive ? lk->incl : lk->agg;
+#pragma unroll
+    for (int r = 0; r < (D + 2) / 3; ++r) {
+        uint4 rec = make_uint4(0u, 0u, 0u, a.epoch);
+        rec.x = __float_as_uint(v[3 * r]);
+        if (3 * r + 1 < D) rec.y = __float_as_uint(v[3 * r + 1]);
+        if (3 * r + 2 < D) rec.z = __float_as_uint(v[3 * r + 2]);
+        st_relaxed_b128(dst + r, rec);
+    }
+}
+template <int D>
+DEV bool read_link(const uint4 *src, unsigned epoch, float (&v)[D]) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < (D + 2) / 3; ++r) {
+        const uint4 rec = ld_relaxed_b128(src + r);
+        ok = ok && rec.w == epoch;
+        v[3 * r] = __uint_as_float(rec.x);
+        if (3 * r + 1 < D) v[3 * r + 1] = __uint_as_float(rec.y);
+        if (3 * r + 2 < D) v[3 * r + 2] = __uint_as_float(rec.z);
+    }
+    return ok;
+}
+
+// Inter-tile decoupled look-back for one group (the whole warp): the group state at the start of
+// `tile`.  T->depth is the number of predecessor tiles whose transition power Ac^(T*k) is still
+// non-zero in f32: tiles further back contribute exactly nothing, so for fast-decaying groups
+// (the LR4 biquads) the look-back reads a few aggregates -- published one whole tile earlier,
+// because the section phase of a tile runs one loop iteration behind its front -- and never waits
+// for an inclusive value; slow poles (the DC blocker) use the classic chained form.
+template <int D>
+DEV void lookback(const ChainArgs &a, int g, long long tile, int lane, float (&sin)[D]) {
+    const GroupParam &G = a.grp[g];
+    const GroupTables *T = a.gtabs + g;
+#pragma unroll
+    for (int d = 0; d < D; ++d) sin[d] = 0.f;
+    const int depth = __ldg(&T->depth);
+    const bool agg_only = G.agg_only != 0;
     long long base = tile - 1;
     int dist0 = 0;                                   // predecessor distance of lane 0 in this window
-    const float4 lbk = __ldg(&T->lb[lane]);
-    const int depth = __ldg(&T->depth);
+    int window = 0;
+    float Mw[D * D];                                 // Ac^(T * 32 * window), only used past the first window
     for (;;) {
         const long long idx = base - lane;
         const bool beyond = (dist0 + lane) >= depth;      // weight is exactly zero from here on
-        const TileLink *lk = a.links + (idx >= 0 ? idx : 0) * kMaxSections + s;
-        uint4 ra = make_uint4(0, 0, 0, 0), ri = make_uint4(0, 0, 0, 0);
+        const TileLink *lk = a.links + (idx >= 0 ? idx : 0) * kMaxGroups + g;
+        float pa[D], pi[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { pa[d] = 0.f; pi[d] = 0.f; }
         int first_incl = 32;
         int spins = 0;
         for (;;) {
@@ -193,10 +248,8 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
                 ready = true;
                 incl = true;
             } else {
-                ra = ld_relaxed_b128(&lk->agg);
-                ri = ld_relaxed_b128(&lk->incl);
-                incl = ri.z == a.epoch;
-                ready = incl || ra.z == a.epoch;
+                incl = agg_only ? false : read_link<D>(lk->incl, a.epoch, pi);
+                ready = incl || read_link<D>(lk->agg, a.epoch, pa);
             }
             const unsigned incl_mask = __ballot_sync(FULLMASK, incl);
             const unsigned ready_mask = __ballot_sync(FULLMASK, ready);
@@ -205,41 +258,70 @@ DEV float2 lookback(const ChainArgs &a, const SecTables *T, long long tile, int 
             if ((ready_mask & need) == need) break;
             if (++spins > (1 << 21)) {     // watchdog: never hang the device
                 if (lane == 0) atomicExch(a.err_flag, 1);
-                return acc;
+                return;
             }
             __nanosleep(32);
         }
-        float2 term = make_float2(0.f, 0.f);
+        float term[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) term[d] = 0.f;
         if (lane <= first_incl && !beyond) {
-            float2 pay;
-            if (idx < 0) pay = (idx == -1) ? a.carry_in->sec[s] : make_float2(0.f, 0.f);
-            else if (lane == first_incl) pay = make_float2(__uint_as_float(ri.x), __uint_as_float(ri.y));
-            else pay = make_float2(__uint_as_float(ra.x), __uint_as_float(ra.y));
-            term = mv(M, mv(lbk, pay));
+            float pay[D];
+            if (idx < 0) {
+#pragma unroll
+                for (int d = 0; d < D; d += 2) {
+                    const float2 c = (idx == -1) ? a.carry_in->sec[G.first + d / 2] : make_float2(0.f, 0.f);
+                    pay[d] = c.x; pay[d + 1] = c.y;
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) pay[d] = (lane == first_incl) ? pi[d] : pa[d];
+            }
+            float lbk[D * D], t1[D];
+            load_mat<D>(T->lb[lane], lbk);
+            matvec<D>(lbk, pay, t1);
+            if (window == 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) term[d] = t1[d];
+            } else {
+                matvec<D>(Mw, t1, term);
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            term.x += __shfl_xor_sync(FULLMASK, term.x, o);
-            term.y += __shfl_xor_sync(FULLMASK, term.y, o);
+        for (int d = 0; d < D; ++d) {
+            float v = term[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+            sin[d] += v;
         }
-        acc = add2(acc, term);
         if (first_incl < 32) break;
-        M = mm(M, __ldg(&T->lb32));
+        // next window of 32 predecessors: Mw <- Mw * Ac^(32 T)
+        float L32[D * D];
+        load_mat<D>(T->lb32, L32);
+        if (window == 0) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Mw[i] = L32[i];
+        } else {
+            float Mn[D * D];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc = fmaf(Mw[r * D + k], L32[k * D + c], acc);
+                    Mn[r * D + c] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Mw[i] = Mn[i];
+        }
+        ++window;
         base -= 32;
         dist0 += 32;
     }
-    return acc;
 }
 
-DEV void publish(const ChainArgs &a, long long tile, int s, float2 v, bool inclusive) {
-    TileLink *lk = a.links + tile * kMaxSections + s;
-    const uint4 rec = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), a.epoch, 0u);
-    st_relaxed_b128(inclusive ? (void *)&lk->incl : (void *)&lk->agg, rec);
-}
-
-// ----------------------------------------------------------------------------------------------
-// recursive sections: per-lane passes, specialised per section type (no per-item branches)
-// ----------------------------------------------------------------------------------------------
+// one recursive-section step, reference arithmetic
 template <int TYPE>
 DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
     float y;
@@ -258,10 +340,10 @@ DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
     return y;
 }
 
-// pass 2: the reference recursion from the true start state; writes the carried state when this
-// lane owns the last item of the call
+// pass 2 of one section over this lane's items (section by section == sample by sample for a
+// cascade); writes the carried state when this lane owns the last item of the call
 template <int TYPE, int NPT>
-DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT], float s0, float s1,
+DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT], float &s0, float &s1,
                    long long jt, bool full) {
     if (full) {
 #pragma unroll
@@ -282,6 +364,111 @@ DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT]
     }
 }
 
+// group front: zero-state end state of this lane's chunk (dot products with the impulse
+// responses), warp scan with constant transition powers, publish the tile aggregate.
+// X = state contribution of the lanes before this one; agg = whole-tile aggregate.
+template <int D, int NPT>
+DEV void group_front(const ChainArgs &a, int g, long long tile, int lane, const float (&u)[NPT], bool full,
+                     float (&X)[D], float (&agg)[D]) {
+    const GroupParam &G = a.grp[g];
+    float E[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) E[d] = 0.f;
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i)
+#pragma unroll
+            for (int d = 0; d < D; ++d) E[d] = fmaf(G.imp[i][d], u[i], E[d]);
+    }
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        float o[D], t[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = __shfl_up_sync(FULLMASK, E[d], 1 << l);
+        matvec<D>(G.lv[l], o, t);
+        if (lane >= (1 << l)) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) E[d] += t[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        X[d] = __shfl_up_sync(FULLMASK, E[d], 1);
+        if (lane == 0) X[d] = 0.f;
+        agg[d] = __shfl_sync(FULLMASK, E[d], 31);
+    }
+    if (lane == 0) publish<D>(a, tile, g, agg, false);
+}
+
+// group finish: look-back, true start state of this lane's chunk, the reference recursion
+template <int D, int NPT>
+DEV void group_finish(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt,
+                      const float (&X)[D], const float (&agg)[D]) {
+    const GroupParam &G = a.grp[g];
+    const GroupTables *T = a.gtabs + g;
+    float sin[D];
+    lookback<D>(a, g, tile, lane, sin);
+    if (!G.agg_only && lane == 0) {
+        float tm[D * D], inc[D];
+        load_mat<D>(T->tile, tm);
+        matvec<D>(tm, sin, inc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) inc[d] += agg[d];
+        publish<D>(a, tile, g, inc, true);
+    }
+    float lm[D * D], st[D];
+    load_mat<D>(T->lane[lane], lm);
+    matvec<D>(lm, sin, st);
+#pragma unroll
+    for (int d = 0; d < D; ++d) st[d] += X[d];
+#pragma unroll
+    for (int q = 0; q < D / 2; ++q) {
+        const int s = G.first + q;
+        const SecParam &P = a.sec[s];
+        if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
+        else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
+        else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
+    }
+}
+
+// dispatch on the group dimension
+template <int NPT>
+DEV void group_front_park(const ChainArgs &a, int g, long long tile, int lane, const float (&u)[NPT], bool full,
+                          float *park) {
+    // park layout (floats): [lane][8] X, then [8] agg
+#define ORION_GF(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, g, tile, lane, u, full, X, agg); \
+        _Pragma("unroll") for (int d = 0; d < DD; ++d) park[lane * kMaxGroupDim + d] = X[d]; \
+        if (lane == 0) { _Pragma("unroll") for (int d = 0; d < DD; ++d) park[32 * kMaxGroupDim + d] = agg[d]; } }
+    switch (a.grp[g].D) {
+        case 2: ORION_GF(2) break;
+        default: ORION_GF(4) break;
+    }
+#undef ORION_GF
+    __syncwarp();
+}
+template <int NPT>
+DEV void group_finish_parked(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full,
+                             long long jt, const float *park) {
+#define ORION_GP(DD) { float X[DD], agg[DD]; \
+        _Pragma("unroll") for (int d = 0; d < DD; ++d) { X[d] = park[lane * kMaxGroupDim + d]; agg[d] = park[32 * kMaxGroupDim + d]; } \
+        group_finish<DD, NPT>(a, g, tile, lane, u, full, jt, X, agg); }
+    switch (a.grp[g].D) {
+        case 2: ORION_GP(2) break;
+        default: ORION_GP(4) break;
+    }
+#undef ORION_GP
+}
+template <int NPT>
+DEV void group_whole(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt) {
+#define ORION_GW(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, g, tile, lane, u, full, X, agg); \
+        group_finish<DD, NPT>(a, g, tile, lane, u, full, jt, X, agg); }
+    switch (a.grp[g].D) {
+        case 2: ORION_GW(2) break;
+        default: ORION_GW(4) break;
+    }
+#undef ORION_GW
+}
+
 // ----------------------------------------------------------------------------------------------
 // staged-tile geometry (FRONT_STAGED)
 //   global row G covers samples [row_samples*G + O - Mb + 2, +row_samples)   (call-relative)
@@ -297,73 +484,57 @@ DEV bool tile_is_interior(const ChainArgs &a, long long tile) {
     return a.use_tma && G0 >= a.tma_row0 && (G0 + kThreads + a.HR) <= (a.tma_row0 + a.tma_rows);
 }
 
-// start the TMA load of an interior tile (one elected lane); edge tiles are loaded in stage_wait
-DEV void stage_issue(const ChainArgs &a, const CUtensorMap *tmap, long long tile, unsigned char *smem,
-                     uint32_t mbar, int lane) {
-    if (tile_is_interior(a, tile) && lane == 0) {
-        const long long G0 = tile * kThreads - a.HR;
-        fence_proxy_async();               // earlier generic-proxy accesses to the buffer vs the async write
-        mbar_expect_tx(mbar, (uint32_t)((kThreads + a.HR) * a.row_pitch));
-        tma_load_2d(smem_u32(smem), tmap, 0, (int)(G0 - a.tma_row0), mbar);
-    }
-}
-
-DEV void stage_wait(const ChainArgs &a, long long tile, unsigned char *smem, uint32_t mbar, unsigned &parity,
-                    int lane) {
+// cooperative (whole warp) load of an edge tile -- FIR history / ragged tail -- into the staged layout
+DEV void stage_load_generic(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
-    if (tile_is_interior(a, tile)) {
-        int spins = 0;
-        while (!mbar_try_wait(mbar, parity)) {
-            if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+    const int cpr = a.row_samples >> 1;                 // 16-byte chunks per row
+    const int total = rows * cpr;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
+    for (int c = lane; c < total; c += kThreads) {
+        const int rho = c / cpr;
+        const int cc = c - rho * cpr;
+        const long long s = row_start_sample(a, G0 + rho) + 2 * cc;
+        float4 v;
+        if (al16 && s >= 0 && s + 1 < a.n_in) {
+            v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.in) + s));
+        } else {
+            const float2 x0 = load_x(a, s), x1 = load_x(a, s + 1);
+            v = make_float4(x0.x, x0.y, x1.x, x1.y);
         }
-        parity ^= 1u;
-    } else {
-        const int cpr = a.row_samples >> 1;                 // 16-byte chunks per row
-        const int total = rows * cpr;
-        const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
-        for (int c = lane; c < total; c += kThreads) {
-            const int rho = c / cpr;
-            const int cc = c - rho * cpr;
-            const long long s = row_start_sample(a, G0 + rho) + 2 * cc;
-            float4 v;
-            if (al16 && s >= 0 && s + 1 < a.n_in) {
-                v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.in) + s));
-            } else {
-                const float2 x0 = load_x(a, s), x1 = load_x(a, s + 1);
-                v = make_float4(x0.x, x0.y, x1.x, x1.y);
-            }
-            *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v;
-        }
-        __syncwarp();
+        *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v;
     }
-    if (a.mix != MIX_NONE) {
-        // in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
-        const int cpr = a.row_samples >> 1;
-        const float2 w = make_float2(a.pre.wre, a.pre.wim);
-        for (int rho = lane; rho < rows; rho += kThreads) {
-            const long long s0 = row_start_sample(a, G0 + rho);
-            unsigned char *rp = smem + (size_t)rho * a.row_pitch;
-            float2 p = make_float2(1.f, 0.f);
-            for (int cc = 0; cc < cpr; ++cc) {
-                const unsigned long long k = a.pre.kbase + (unsigned long long)(s0 + 2 * cc) + 1ull;
-                if ((cc & 7) == 0) p = nco_unit(a.pre, k);
-                float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
-                const float2 y0 = mix_apply(a.mix, make_float2(v.x, v.y), scale2(p, nco_amp(a.pre, k)));
-                p = cmul_fma(p, w);
-                const float2 y1 = mix_apply(a.mix, make_float2(v.z, v.w), scale2(p, nco_amp(a.pre, k + 1ull)));
-                p = cmul_fma(p, w);
-                *reinterpret_cast<float4 *>(rp + cc * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
-            }
+    __syncwarp();
+}
+
+// in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
+DEV void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
+    const int rows = kThreads + a.HR;
+    const long long G0 = tile * kThreads - a.HR;
+    const int cpr = a.row_samples >> 1;
+    const float2 w = make_float2(a.pre.wre, a.pre.wim);
+    for (int rho = lane; rho < rows; rho += kThreads) {
+        const long long s0 = row_start_sample(a, G0 + rho);
+        unsigned char *rp = smem + (size_t)rho * a.row_pitch;
+        float2 p = make_float2(1.f, 0.f);
+        for (int cc = 0; cc < cpr; ++cc) {
+            const unsigned long long k = a.pre.kbase + (unsigned long long)(s0 + 2 * cc) + 1ull;
+            if ((cc & 7) == 0) p = nco_unit(a.pre, k);
+            float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
+            const float2 y0 = mix_apply(a.mix, make_float2(v.x, v.y), scale2(p, nco_amp(a.pre, k)));
+            p = cmul_fma(p, w);
+            const float2 y1 = mix_apply(a.mix, make_float2(v.z, v.w), scale2(p, nco_amp(a.pre, k + 1ull)));
+            p = cmul_fma(p, w);
+            *reinterpret_cast<float4 *>(rp + cc * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // shared-memory address of call-relative sample s inside the staged tile
 DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, long long G0, long long s) {
     const int d = (int)(s - row_start_sample(a, G0));           // tile-local: fits 32 bits
-    const int rho = d / a.row_samples;
+    const int rho = (a.row_shift >= 0) ? (d >> a.row_shift) : (d / a.row_samples);
     const int w = d - rho * a.row_samples;
     return reinterpret_cast<const float2 *>(smem + (size_t)rho * a.row_pitch + (size_t)w * 8);
 }
@@ -465,10 +636,11 @@ DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, long lo
 }
 
 // ----------------------------------------------------------------------------------------------
-// everything after the front: demod-rate oscillator, front map, recursive sections, store
+// after the front: demod-rate oscillator + demodulator front map  (z -> u), C32 store for
+// DEMOD_NONE, end-of-call duties
 // ----------------------------------------------------------------------------------------------
 template <int NPT>
-DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo) {
+DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo) {
     const long long j0 = tile * (long long)(kThreads * NPT);
     const long long jt = j0 + (long long)lane * NPT;
     const bool is_c32_in = a.demod != DEMOD_F32;
@@ -476,7 +648,6 @@ DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[N
     const bool post_osc = (a.demod == DEMOD_FM && a.translate) || a.demod == DEMOD_SSB || a.demod == DEMOD_USB;
     const bool full = jt + NPT <= a.n_out;
 
-    // ---------------- demod-rate oscillator + front map ------------------------------------------
     if (is_c32_in && a.demod != DEMOD_NONE) {
         float2 p = make_float2(1.f, 0.f);
         const float2 w = make_float2(a.post.wre, a.post.wim);
@@ -545,44 +716,6 @@ DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[N
         }
     }
 
-    // ---------------- recursive sections: serial in-lane, scanned across lanes and tiles ---------
-    if (a.demod != DEMOD_NONE) {
-        for (int s = 0; s < a.nsec; ++s) {
-            const SecParam &P = a.sec[s];
-            const SecTables *T = a.tabs + s;
-            // pass 1: end state of this lane's chunk from a zero start state, as the dot product
-            // with the section's state impulse responses  e = sum_i A^(NPT-1-i) B u[i]
-            float2 E = make_float2(0.f, 0.f);
-            if (full) {
-#pragma unroll
-                for (int i = 0; i < NPT; ++i) {
-                    E.x = fmaf(P.imp[i].x, u[i], E.x);
-                    E.y = fmaf(P.imp[i].y, u[i], E.y);
-                }
-            }
-            // warp-level inclusive scan with constant transition powers
-#pragma unroll
-            for (int l = 0; l < 5; ++l) {
-                const int d = 1 << l;
-                const float2 o = shfl_up2(E, d);
-                if (lane >= d) E = add2(E, mv(P.lv[l], o));
-            }
-            float2 X = shfl_up2(E, 1);
-            if (lane == 0) X = make_float2(0.f, 0.f);
-            const float2 agg = shfl2(E, 31);
-            // the tile aggregate is published as soon as it exists; then the look-back
-            if (lane == 0) publish(a, tile, s, agg, false);
-            const float2 sin = lookback(a, T, tile, s, lane);
-            if (lane == 0) publish(a, tile, s, add2(mv(__ldg(&T->tile), sin), agg), true);
-            // state at the start of this lane's chunk
-            const float2 st = add2(X, mv(__ldg(&T->lane[lane]), sin));
-            if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st.x, st.y, jt, full);
-            else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st.x, st.y, jt, full);
-            else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st.x, st.y, jt, full);
-        }
-    }
-
-    // ---------------- store -------------------------------------------------------------------
     if (a.demod == DEMOD_NONE) {
         float2 *out = reinterpret_cast<float2 *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
@@ -595,21 +728,9 @@ DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[N
             for (int i = 0; i < NPT; ++i)
                 if (jt + i < a.n_out) out[jt + i] = z[i];
         }
-    } else {
-        float *out = reinterpret_cast<float *>(a.out);
-        const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 4 == 0);
-        if (al16 && full) {
-#pragma unroll
-            for (int i = 0; i < NPT; i += 4)
-                *reinterpret_cast<float4 *>(out + jt + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NPT; ++i)
-                if (jt + i < a.n_out) out[jt + i] = u[i];
-        }
     }
 
-    // ---------------- end-of-call duties (last tile) ------------------------------------------
+    // end-of-call duties (last tile): FIR history and the state no stage of this call touches
     if (tile == a.ntiles - 1) {
         if (a.H > 0)
             for (int k = lane; k < a.H; k += kThreads) a.hist_out[k] = load_x(a, a.n_in - a.H + k);
@@ -619,6 +740,36 @@ DEV void finish_tile(const ChainArgs &a, long long tile, int lane, float2 (&z)[N
                 if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
         }
     }
+}
+
+// store the f32 outputs of a tile
+template <int NPT>
+DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u)[NPT]) {
+    const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
+    float *out = reinterpret_cast<float *>(a.out);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 4 == 0);
+    if (al16 && jt + NPT <= a.n_out) {
+#pragma unroll
+        for (int i = 0; i < NPT; i += 4)
+            *reinterpret_cast<float4 *>(out + jt + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i)
+            if (jt + i < a.n_out) out[jt + i] = u[i];
+    }
+}
+
+// the section phase of a tile whose group-0 front ran one loop iteration earlier (state parked in
+// shared memory): group 0 finish, then the remaining groups front + finish, then the store
+template <int NPT>
+DEV void finish_sections(const ChainArgs &a, long long tile, int lane, float (&u)[NPT], const float *park) {
+    const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
+    const bool full = jt + NPT <= a.n_out;
+    if (a.ngroups > 0) {
+        group_finish_parked<NPT>(a, 0, tile, lane, u, full, jt, park);
+        for (int g = 1; g < a.ngroups; ++g) group_whole<NPT>(a, g, tile, lane, u, full, jt);
+    }
+    store_f32<NPT>(a, tile, lane, u);
 }
 
 // direct front: items straight from global memory (rate-1 blocks)
@@ -670,64 +821,143 @@ DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[
     }
 }
 
+// CTA-level control block of the stage ring (FRONT_STAGED)
+struct __align__(16) RingCtl {
+    unsigned long long full[kMaxStages];     // mbarrier per slot: "the tile of this fill has landed"
+    int gen[kMaxStages];                     // index of the slot's latest fill (use k may only look at fill k)
+    unsigned int cons;                       // consume counter of the CTA
+    unsigned int pad;
+};
+
+// The kernel.  Tiles are assigned statically and round-robin: CTA b owns tiles b, b+G, b+2G, ...
+// (G = gridDim.x, all CTAs co-resident) and its NW warps take them in that order through a consume
+// counter; the i-th tile of the CTA is staged in ring slot i % NS by its (i / NS)-th fill.
+//   * NS < NW: a slot is busy only while its tile is in flight from HBM and under the FIR, about a
+//     quarter of a tile's life; the rest of the time a warp works from registers, so more warps than
+//     slots are resident and the register file -- not shared memory -- bounds the occupancy;
+//   * the warp that has run the FIR on a slot refills it at once with the CTA's tile NS places ahead
+//     (one cp.async.bulk.tensor), so loads run ahead of the consumers;
+//   * each warp is software-pipelined over its tiles: iteration i runs the front of tile_i (FIR,
+//     demod map, group-0 scan, publish) and then the section phase of tile_(i-1), whose look-back
+//     reads aggregates that the neighbouring CTAs published a whole iteration ago (round-robin
+//     assignment keeps neighbouring tiles in lock-step);
+//   * no deadlock by construction: the oldest unfinished tile of the stream is either in a warp's
+//     hands, and that warp never waits on a younger tile, or next in line at its CTA, whose warps
+//     all hold older tiles that wait on still older, finished ones.
 template <int FRONT, int R, int U>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads * kMaxWarpsPerCta, 1)
 chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int NPT = R * U;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long mbar_storage;
-    const int lane = threadIdx.x;
-    const uint32_t mbar = smem_u32(&mbar_storage);
-    unsigned parity = 0;
+    __shared__ __align__(16) float park_all[kMaxWarpsPerCta][2][33 * kMaxGroupDim];
+    __shared__ RingCtl ring;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int NW = blockDim.x >> 5;
+    const int NS = a.nstages;
+    const long long G = gridDim.x, cta = blockIdx.x;
+    const size_t stage_bytes = (size_t)(kThreads + a.HR) * a.row_pitch;      // bytes one TMA load delivers
+    const size_t stage_stride = (stage_bytes + 127) & ~(size_t)127;          // TMA destinations are 128-byte aligned
+    float (*park)[33 * kMaxGroupDim] = park_all[wid];
+
+    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    const bool has_sections = a.demod != DEMOD_NONE;
+
     if (FRONT == FRONT_STAGED) {
-        if (lane == 0) {
-            mbar_init(mbar, 1);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&ring.full[s]), 1); ring.gen[s] = -1; }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncwarp();
     }
-    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    if (threadIdx.x == 0) ring.cons = 0;
+    __syncthreads();
 
-    long long serial_next = 0;
-    auto take_ticket = [&]() -> long long {
-        if (a.serial) return serial_next++;
-        long long t = 0;
-        if (lane == 0) t = (long long)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
-        return __shfl_sync(FULLMASK, t, 0);
+    // fill k of slot s = the CTA's tile number i = k*NS + s (lane 0): TMA for interior tiles, a plain
+    // arrive for edge tiles (their consumer loads them cooperatively); nothing past the end
+    auto fill_slot = [&](int s, int k) {
+        const long long t = cta + G * ((long long)k * NS + s);
+        if (lane == 0 && t < a.ntiles) {
+            const uint32_t bar = smem_u32(&ring.full[s]);
+            *reinterpret_cast<volatile int *>(&ring.gen[s]) = k;      // before the arrive below (release)
+            if (tile_is_interior(a, t)) {
+                fence_proxy_async();          // earlier generic-proxy accesses to the slot vs the async write
+                mbar_expect_tx(bar, (uint32_t)stage_bytes);
+                tma_load_2d(smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
+                            (int)(t * kThreads - a.HR - a.tma_row0), bar);
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            }
+        }
     };
 
-    long long tile = take_ticket();
-    if (FRONT == FRONT_STAGED && tile < a.ntiles) stage_issue(a, &tmap, tile, smem, mbar, lane);
-    while (tile < a.ntiles) {
+    float u_pend[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) u_pend[i] = 0.f;
+    long long pend_tile = -1;
+    int slot_pp = 0;
+
+    if (FRONT == FRONT_STAGED)
+        for (int s = wid; s < NS; s += NW) fill_slot(s, 0);            // initial fill of the ring
+
+    for (;;) {
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(&ring.cons, 1u);
+        c = __shfl_sync(FULLMASK, c, 0);
+        const long long tile = cta + G * (long long)c;
+        if (tile >= a.ntiles) break;
+        int s = 0, k = 0;
+        unsigned char *stage = smem;
+        if (FRONT == FRONT_STAGED) {
+            s = (int)(c % (unsigned)NS);
+            k = (int)(c / (unsigned)NS);
+            const uint32_t bar = smem_u32(&ring.full[s]);
+            int spins = 0;
+            // use k of the slot looks at fill k only: a fast warp may be more than one lap ahead of
+            // the slot's current user, and the mbarrier parity alone cannot tell fill k from fill k-2
+            while (*reinterpret_cast<volatile int *>(&ring.gen[s]) != k) {
+                if (++spins > (1 << 24)) { atomicExch(a.err_flag, 3); break; }
+                __nanosleep(20);
+            }
+            spins = 0;
+            while (!mbar_try_wait(bar, (unsigned)k & 1u)) {
+                if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+            }
+            stage = smem + (size_t)s * stage_stride;
+        }
+
         float2 z[NPT];
         float  u[NPT];
 #pragma unroll
         for (int i = 0; i < NPT; ++i) { z[i] = make_float2(0.f, 0.f); u[i] = 0.f; }
         float2 zhalo = make_float2(0.f, 0.f);           // item j0-1 (lane 0 only)
         const long long j0 = tile * (long long)(kThreads * NPT);
-        long long next;
+        const long long jt = j0 + (long long)lane * NPT;
 
         if (FRONT == FRONT_STAGED) {
-            stage_wait(a, tile, smem, mbar, parity, lane);
-            fir_staged<R, U>(a, smem, lane, z);
-            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, smem, tile * kThreads - a.HR, j0 - 1, lane);
-            __syncwarp();                               // every lane is done with the staged buffer:
-            next = take_ticket();                       // prefetch the next tile behind the rest of this one
-            if (next < a.ntiles) stage_issue(a, &tmap, next, smem, mbar, lane);
+            if (!tile_is_interior(a, tile)) stage_load_generic(a, tile, stage, lane);
+            if (a.mix != MIX_NONE) stage_mix(a, tile, stage, lane);
+            fir_staged<R, U>(a, stage, lane, z);
+            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, tile * kThreads - a.HR, j0 - 1, lane);
+            __syncwarp();                               // every lane is done with the slot: refill it
+            fill_slot(s, k + 1);
         } else if (FRONT == FRONT_GLOBAL) {
-            const long long jt = j0 + (long long)lane * NPT;
 #pragma unroll
             for (int i = 0; i < NPT; ++i)
                 if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
             if (need_prev && j0 > 0 && lane == 0) zhalo = fir_global_one(a, j0 - 1);
-            next = take_ticket();
         } else {
             front_direct<NPT>(a, tile, lane, z, u, zhalo);
-            next = take_ticket();
         }
-        finish_tile<NPT>(a, tile, lane, z, u, zhalo);
-        tile = next;
+        front_map<NPT>(a, tile, lane, z, u, zhalo);
+        if (has_sections) {
+            if (a.ngroups > 0) group_front_park<NPT>(a, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
+            if (pend_tile >= 0) finish_sections<NPT>(a, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) u_pend[i] = u[i];
+            pend_tile = tile;
+            slot_pp ^= 1;
+        }
     }
+    if (pend_tile >= 0) finish_sections<NPT>(a, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -759,17 +989,18 @@ chain_kernel_t select_kernel(int front, int R, int U) {
     return nullptr;
 }
 
-cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int *ctas_per_sm) {
+cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm) {
     cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads * warps, dyn_smem);
 }
 
-cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid,
+cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
                                 size_t dyn_smem, cudaStream_t stream) {
-    k<<<grid, kThreads, dyn_smem, stream>>>(args, tmap);
+    // serial debug mode: one warp walks the tiles in order
+    k<<<grid, args.serial ? kThreads : kThreads * warps, dyn_smem, stream>>>(args, tmap);
     return cudaGetLastError();
 }
 

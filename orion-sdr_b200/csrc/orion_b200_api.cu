@@ -21,8 +21,8 @@
 namespace orion {
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 chain_kernel_t select_kernel(int front, int R, int U);
-cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int *ctas_per_sm);
-cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid,
+cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm);
+cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
                                 size_t dyn_smem, cudaStream_t stream);
 }  // namespace orion
 
@@ -124,72 +124,120 @@ float cw_alpha(float fs, float env_bw_hz) {                                    /
     return expf(-kTau * maxf_rs(env_bw_hz, 1.0f) / fs);
 }
 
-// ---- 2x2 helpers in f64 for the scan tables -----------------------------------------------------
-struct M2 { double a, b, c, d; };
-M2 mul(const M2 &x, const M2 &y) {
-    return { x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d };
+// ---- section groups: dense state-space powers in f64 for the scan tables -------------------------
+typedef std::vector<double> Mat;                       // row-major D x D
+Mat mat_mul(const Mat &x, const Mat &y, int D) {
+    Mat r((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) {
+            const double xv = x[i * D + k];
+            if (xv == 0.0) continue;
+            for (int j = 0; j < D; ++j) r[i * D + j] += xv * y[k * D + j];
+        }
+    return r;
 }
-M2 mpow(M2 base, unsigned long long e) {
-    M2 r = { 1, 0, 0, 1 };
+Mat mat_pow(Mat base, unsigned long long e, int D) {
+    Mat r((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i) r[i * D + i] = 1.0;
     while (e) {
-        if (e & 1ull) r = mul(r, base);
-        base = mul(base, base);
+        if (e & 1ull) r = mat_mul(r, base, D);
+        base = mat_mul(base, base, D);
         e >>= 1;
     }
     return r;
 }
-float4 f4(const M2 &m) { return make_float4((float)m.a, (float)m.b, (float)m.c, (float)m.d); }
+bool mat_is_zero(const Mat &m) {
+    for (double v : m)
+        if (std::fabs(v) >= 1e-30) return false;       // far below anything an f32 state sum can resolve
+    return true;
+}
+void mat_store(const Mat &m, float *dst) { for (size_t i = 0; i < m.size(); ++i) dst[i] = (float)m[i]; }
 
-M2 section_matrix(const SecParam &p) {
-    if (p.type == SEC_BIQUAD) return { -(double)p.c[3], 1.0, -(double)p.c[4], 0.0 };   // s' = A s + B x
-    if (p.type == SEC_DC) return { 0.0, 0.0, -1.0, (double)p.c[0] };                   // (x1, y1)
-    return { (double)p.c[0], 0.0, 0.0, 0.0 };                                           // one-pole
-}
-void section_input_vector(const SecParam &p, double B[2]) {
-    if (p.type == SEC_BIQUAD) {            // s' = A s + B x with y = b0 x + s0 substituted
-        B[0] = (double)p.c[1] - (double)p.c[3] * (double)p.c[0];
-        B[1] = (double)p.c[2] - (double)p.c[4] * (double)p.c[0];
-    } else if (p.type == SEC_DC) { B[0] = 1.0; B[1] = 1.0; }
-    else { B[0] = (double)p.c[1]; B[1] = 0.0; }
-}
-bool is_zero_f32(const M2 &m) {
-    const double t = 1e-30;                // far below anything an f32 state sum can resolve
-    return std::fabs(m.a) < t && std::fabs(m.b) < t && std::fabs(m.c) < t && std::fabs(m.d) < t;
-}
-// fills the launch-plan part of the section parameters (parameter bank) and the global tables
-void build_tables(SecParam &p, int npt, SecTables *t) {
-    const M2 A = section_matrix(p);
-    double B[2];
-    section_input_vector(p, B);
-    for (int i = 0; i < kMaxNpt; ++i) p.imp[i] = make_float2(0.f, 0.f);
-    for (int i = 0; i < npt; ++i) {
-        const M2 Ak = mpow(A, (unsigned long long)(npt - 1 - i));
-        p.imp[i] = make_float2((float)(Ak.a * B[0] + Ak.b * B[1]), (float)(Ak.c * B[0] + Ak.d * B[1]));
+// one step of a section cascade in f64 (the linear model of sec_step_t; state = (s0, s1) per section)
+void cascade_step(const SecParam *secs, int count, double *st, double u) {
+    double v = u;
+    for (int q = 0; q < count; ++q) {
+        const SecParam &p = secs[q];
+        double &s0 = st[2 * q], &s1 = st[2 * q + 1];
+        double y;
+        if (p.type == SEC_BIQUAD) {
+            y = v * p.c[0] + s0;
+            const double n0 = v * p.c[1] + s1 - (double)p.c[3] * y;
+            const double n1 = v * p.c[2] - (double)p.c[4] * y;
+            s0 = n0; s1 = n1;
+        } else if (p.type == SEC_DC) {
+            y = v - s0 + (double)p.c[0] * s1;
+            s0 = v; s1 = y;
+        } else {
+            y = (double)p.c[0] * s0 + (double)p.c[1] * v;
+            s0 = y; s1 = 0.0;
+        }
+        v = y;
     }
+}
+
+struct GroupHost { int first = 0, count = 0; };
+std::vector<GroupHost> split_groups(const std::vector<SecParam> &secs) {
+    std::vector<GroupHost> gs;
+    GroupHost cur;
+    for (size_t s = 0; s < secs.size(); ++s) {
+        if (cur.count == 0) cur.first = (int)s;
+        cur.count += 1;
+        if (secs[s].post_op != OP_NONE || cur.count == kMaxGroupDim / 2) { gs.push_back(cur); cur = GroupHost(); }
+    }
+    if (cur.count) gs.push_back(cur);
+    return gs;
+}
+
+// fills the launch-plan data of one group: parameter-bank part (gp) and global tables (gt)
+void build_group(const SecParam *secs, const GroupHost &gh, int npt, GroupParam *gp, GroupTables *gt) {
+    const int D = 2 * gh.count;
+    memset(gp, 0, sizeof(*gp));
+    memset(gt, 0, sizeof(*gt));
+    gp->first = gh.first; gp->count = gh.count; gp->D = D;
+    Mat A((size_t)D * D, 0.0);
+    std::vector<double> B(D, 0.0), st(D);
+    for (int k = 0; k < D; ++k) {                      // column k of Ac: one step from the unit state e_k
+        std::fill(st.begin(), st.end(), 0.0);
+        st[k] = 1.0;
+        cascade_step(secs + gh.first, gh.count, st.data(), 0.0);
+        for (int r = 0; r < D; ++r) A[r * D + k] = st[r];
+    }
+    std::fill(st.begin(), st.end(), 0.0);
+    cascade_step(secs + gh.first, gh.count, st.data(), 1.0);
+    B = st;
     const unsigned long long n = (unsigned long long)npt, T = n * kThreads;
-    for (int l = 0; l < 5; ++l) { t->lv[l] = f4(mpow(A, n << l)); p.lv[l] = t->lv[l]; }
-    for (int k = 0; k < 32; ++k) t->lane[k] = f4(mpow(A, n * k));
-    for (int k = 0; k < 32; ++k) t->lb[k] = f4(mpow(A, T * k));
-    t->lb32 = f4(mpow(A, T * 32ull));
-    t->tile = f4(mpow(A, T));
-    // look-back depth: first k with A^(T*k) == 0; geometric search then bisection (monotone decay
-    // of the norm is not exact for complex poles, so verify a margin of 4 further powers)
+    for (int i = 0; i < npt; ++i) {
+        const Mat Ak = mat_pow(A, (unsigned long long)(npt - 1 - i), D);
+        for (int r = 0; r < D; ++r) {
+            double acc = 0.0;
+            for (int c = 0; c < D; ++c) acc += Ak[r * D + c] * B[c];
+            gp->imp[i][r] = (float)acc;
+        }
+    }
+    for (int l = 0; l < 5; ++l) mat_store(mat_pow(A, n << l, D), gp->lv[l]);
+    for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, n * k, D), gt->lane[k]);
+    for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, T * k, D), gt->lb[k]);
+    mat_store(mat_pow(A, T * 32ull, D), gt->lb32);
+    mat_store(mat_pow(A, T, D), gt->tile);
+    // look-back depth: first k with Ac^(T*k) == 0; geometric search then bisection (the decay of the
+    // norm is not strictly monotone for complex poles, so a margin of 4 further powers is verified)
     int depth = 1 << 20;
     {
         int lo = 0, hi = 1;
-        while (hi < (1 << 20) && !is_zero_f32(mpow(A, T * (unsigned long long)hi))) hi <<= 1;
+        while (hi < (1 << 20) && !mat_is_zero(mat_pow(A, T * (unsigned long long)hi, D))) hi <<= 1;
         if (hi < (1 << 20)) {
             while (hi - lo > 1) {
                 const int mid = (lo + hi) / 2;
-                if (is_zero_f32(mpow(A, T * (unsigned long long)mid))) hi = mid; else lo = mid;
+                if (mat_is_zero(mat_pow(A, T * (unsigned long long)mid, D))) hi = mid; else lo = mid;
             }
             bool ok = true;
-            for (int e = 1; e <= 4; ++e) ok = ok && is_zero_f32(mpow(A, T * (unsigned long long)(hi + e)));
+            for (int e = 1; e <= 4; ++e) ok = ok && mat_is_zero(mat_pow(A, T * (unsigned long long)(hi + e), D));
             if (ok) depth = hi;
         }
     }
-    t->depth = depth;
-    t->pad[0] = t->pad[1] = t->pad[2] = 0;
+    gt->depth = depth;
+    gp->agg_only = depth <= 32 ? 1 : 0;
 }
 
 // ---- oscillator ------------------------------------------------------------------------------
@@ -226,12 +274,16 @@ struct FirPlan {
     int front = FRONT_DIRECT;
     int R = 8, U = 1, Mb = 0, O = 0, P = 0, P_pad = 0, HR = 0, row_samples = 0, row_pitch = 0, rows = 0;
     int H = 0;
+    int nstages = 0;
+    int warps = kWarpsPerCta;
+    size_t stage_bytes = 0;
     size_t dyn_smem = 0;
     std::vector<float> g;          // generic causal taps
     std::vector<float2> taps2;     // [u][q][c]
 };
 
-const size_t kMaxStagedSmem = 100 * 1024;
+const size_t kMaxStageBytes = 100 * 1024;      // one staged tile
+const size_t kRingBudget = 100 * 1024;         // per-CTA shared memory for the stage ring (two CTAs per SM)
 
 void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl) {
     const int L = (int)taps.size();
@@ -262,11 +314,17 @@ void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force
         const int rows = kThreads + HR;
         const size_t table = (size_t)U * (size_t)(Mb / 2) * (size_t)P_pad;
         const size_t smem = (size_t)rows * pitch;
-        if (table * 2 > (size_t)kMaxTapTable || rows > 256 || smem > kMaxStagedSmem) staged = false;
+        if (table * 2 > (size_t)kMaxTapTable || rows > 256 || smem > kMaxStageBytes) staged = false;
         else {
             pl->front = FRONT_STAGED;
             pl->R = R; pl->U = U; pl->Mb = (int)Mb; pl->O = O; pl->P = P; pl->P_pad = P_pad; pl->HR = HR;
-            pl->row_samples = row_samples; pl->row_pitch = pitch; pl->rows = rows; pl->dyn_smem = smem;
+            const size_t stride = (smem + 127) & ~(size_t)127;       // TMA destinations are 128-byte aligned
+            pl->row_samples = row_samples; pl->row_pitch = pitch; pl->rows = rows; pl->stage_bytes = stride;
+            pl->nstages = (int)std::min<size_t>(std::max<size_t>(kRingBudget / stride, 1), (size_t)std::min(kMaxStages, kWarpsPerCta - 2));
+            // tuning overrides (experiments): ORION_B200_WARPS = warps per CTA, ORION_B200_STAGES = ring slots
+            if (const char *e = getenv("ORION_B200_WARPS")) pl->warps = std::max(1, std::min(kMaxWarpsPerCta, atoi(e)));
+            if (const char *e = getenv("ORION_B200_STAGES")) pl->nstages = std::max(1, std::min(kMaxStages, atoi(e)));
+            pl->dyn_smem = stride * pl->nstages;
             pl->taps2.assign(table, make_float2(0.f, 0.f));
             for (int u = 0; u < U; ++u)
                 for (int q = 0; q < (int)(Mb / 2); ++q)
@@ -289,7 +347,7 @@ void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force
     if (!staged || force_global) {
         pl->front = FRONT_GLOBAL;
         pl->R = 8; pl->U = 1; pl->Mb = 0; pl->O = 0; pl->P = pl->P_pad = pl->HR = 0;
-        pl->row_samples = pl->row_pitch = pl->rows = 0; pl->dyn_smem = 0;
+        pl->row_samples = pl->row_pitch = pl->rows = 0; pl->dyn_smem = 0; pl->nstages = 0; pl->stage_bytes = 0;
         pl->taps2.clear();
     }
 }
@@ -343,7 +401,8 @@ struct orion_b200_block {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     float *d_g = nullptr;
-    SecTables *d_tabs = nullptr;
+    GroupTables *d_gtabs = nullptr;
+    std::vector<GroupParam> groups;
     float2 *d_hist[2] = { nullptr, nullptr };
     size_t hist_cap = 0;
     CarryState *d_carry[2] = { nullptr, nullptr };
@@ -386,7 +445,7 @@ int finalize_plan(orion_b200_block *b) {
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
-    CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, &b->ctas_per_sm));
+    CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, b->plan.warps, &b->ctas_per_sm));
     if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
     // FIR taps + history
     if (b->fir != FIR_NONE) {
@@ -409,13 +468,17 @@ int finalize_plan(orion_b200_block *b) {
             b->hist_cap = (size_t)b->plan.H;
         }
     }
-    // scan tables
+    // section groups + scan tables
+    b->groups.clear();
     if (!b->secs.empty()) {
-        std::vector<SecTables> tabs(b->secs.size());
-        for (size_t s = 0; s < b->secs.size(); ++s) build_tables(b->secs[s], npt_of(b), &tabs[s]);   // also fills secs[s].imp/.lv
-        if (b->d_tabs) { cudaFree(b->d_tabs); b->d_tabs = nullptr; }
-        CK(cudaMalloc(&b->d_tabs, tabs.size() * sizeof(SecTables)));
-        CK(cudaMemcpy(b->d_tabs, tabs.data(), tabs.size() * sizeof(SecTables), cudaMemcpyHostToDevice));
+        const std::vector<GroupHost> gh = split_groups(b->secs);
+        if (gh.size() > (size_t)kMaxGroups) return fail(b, ORION_B200_ERR_UNSUPPORTED, "too many section groups");
+        std::vector<GroupTables> tabs(gh.size());
+        b->groups.resize(gh.size());
+        for (size_t g = 0; g < gh.size(); ++g) build_group(b->secs.data(), gh[g], npt_of(b), &b->groups[g], &tabs[g]);
+        if (b->d_gtabs) { cudaFree(b->d_gtabs); b->d_gtabs = nullptr; }
+        CK(cudaMalloc(&b->d_gtabs, tabs.size() * sizeof(GroupTables)));
+        CK(cudaMemcpy(b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables), cudaMemcpyHostToDevice));
     }
     b->plan_dirty = false;
     return ORION_B200_OK;
@@ -457,8 +520,8 @@ int init_device_side(orion_b200_block *b) {
     CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
     b->stream = b->own_stream;
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
-    CK(cudaMalloc(&b->d_ticket, sizeof(unsigned long long)));
-    CK(cudaMemset(b->d_ticket, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_ticket, 2 * sizeof(unsigned long long)));        // {ticket, done}
+    CK(cudaMemset(b->d_ticket, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_err, sizeof(int)));
     CK(cudaMemset(b->d_err, 0, sizeof(int)));
     CK(cudaMallocHost(&b->h_err, sizeof(int)));
@@ -529,14 +592,14 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         if (b->d_links) cudaFree(b->d_links);
         size_t cap = std::max<size_t>((size_t)ntiles, 4096);
         cap += cap / 4;
-        CK(cudaMalloc(&b->d_links, cap * kMaxSections * sizeof(TileLink)));
-        CK(cudaMemset(b->d_links, 0, cap * kMaxSections * sizeof(TileLink)));
+        CK(cudaMalloc(&b->d_links, cap * kMaxGroups * sizeof(TileLink)));
+        CK(cudaMemset(b->d_links, 0, cap * kMaxGroups * sizeof(TileLink)));
         b->links_cap = cap;
         b->epoch = 0;
     }
     b->epoch += 1;
     if (b->epoch >= (1u << 30)) {                      // epoch wrap: clear the links once
-        CK(cudaMemsetAsync(b->d_links, 0, b->links_cap * kMaxSections * sizeof(TileLink), b->stream));
+        CK(cudaMemsetAsync(b->d_links, 0, b->links_cap * kMaxGroups * sizeof(TileLink), b->stream));
         b->epoch = 1;
     }
 
@@ -553,13 +616,18 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.fir = b->fir; a.M = (int)b->M; a.Lg = (int)b->plan.g.size(); a.g = b->d_g;
     a.Mb = b->plan.Mb; a.O = b->plan.O; a.P_pad = b->plan.P_pad; a.HR = b->plan.HR;
     a.row_samples = b->plan.row_samples; a.row_pitch = b->plan.row_pitch;
+    a.row_shift = -1;
+    for (int sh = 0; sh < 20; ++sh) if ((1 << sh) == b->plan.row_samples) a.row_shift = sh;
+    a.nstages = b->opt_serial ? std::min(b->plan.nstages, 1) : b->plan.nstages;
     a.demod = b->demod; a.translate = b->translate; a.k = b->k; a.k1 = b->k1; a.k2 = b->k2;
     a.post = b->post.param(b->k_post);
     a.nsec = nsec;
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
-    a.tabs = b->d_tabs;
+    a.ngroups = (int)b->groups.size();
+    for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
+    a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
-    a.links = b->d_links; a.ticket = b->d_ticket; a.ticket_base = b->ticket_base;
+    a.links = b->d_links;
     a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err;
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
 
@@ -591,13 +659,13 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     int grid = 1;
     if (!b->opt_serial) {
         const long long resident = (long long)b->sm_count * b->ctas_per_sm;
-        grid = (int)std::min<long long>(ntiles, resident);
+        const long long want = (ntiles + b->plan.warps - 1) / b->plan.warps;      // one tile per warp at least
+        grid = (int)std::max<long long>(1, std::min<long long>(want, resident));
     }
-    cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.dyn_smem, b->stream);
+    cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream);
     delete ap;
     if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "chain kernel launch", e);
     b->launches += 1;
-    if (!b->opt_serial) b->ticket_base += (unsigned long long)ntiles + (unsigned long long)grid;
     b->pp ^= 1;
     b->k_pre += n_in;
     b->k_post += n_out;
@@ -899,7 +967,7 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    cudaFree(b->d_g); cudaFree(b->d_tabs);
+    cudaFree(b->d_g); cudaFree(b->d_gtabs);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     cudaFree(b->d_carry[0]); cudaFree(b->d_carry[1]);
     cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err);
@@ -1061,17 +1129,31 @@ size_t orion_b200_debug_fir_plan(int fir_kind, const float *taps, size_t ntaps, 
     if (g && gcap >= pl.g.size()) memcpy(g, pl.g.data(), pl.g.size() * sizeof(float));
     return nf;
 }
-// scan tables for one section [host-only]; `tables` receives sizeof(SecTables)/4 floats
-size_t orion_b200_debug_scan_tables(int type, const float c[5], int npt, float *tables, size_t cap) {
-    const size_t nf = sizeof(SecTables) / sizeof(float);
-    if (!tables || cap < nf) return nf;
-    SecParam p; memset(&p, 0, sizeof(p));
-    p.type = type;
-    for (int i = 0; i < 5; ++i) p.c[i] = c[i];
-    SecTables t;
-    build_tables(p, npt, &t);
-    memcpy(tables, &t, sizeof(t));
-    if (cap >= nf + 2 * kMaxNpt) memcpy(tables + nf, p.imp, sizeof(p.imp));
+// scan tables of one section group [host-only]: sections = nsec x {type, b0|r|a, b1|1-a, b2, a1, a2};
+// out receives {D, depth, agg_only, 0, imp[16][4], lv[5][16], lane[32][16], lb[32][16], lb32[16], tile[16]}.
+size_t orion_b200_debug_group_tables(const float *sections, size_t nsec, int npt, float *out, size_t cap) {
+    const int MM = kMaxGroupDim * kMaxGroupDim;
+    const size_t nf = 4 + kMaxNpt * kMaxGroupDim + 5 * MM + 32 * MM + 32 * MM + MM + MM;
+    if (!sections || nsec == 0 || nsec > (size_t)(kMaxGroupDim / 2) || npt < 1 || npt > kMaxNpt || !out || cap < nf) return nf;
+    std::vector<SecParam> secs(nsec);
+    for (size_t q = 0; q < nsec; ++q) {
+        memset(&secs[q], 0, sizeof(SecParam));
+        secs[q].type = (int)sections[6 * q];
+        for (int i = 0; i < 5; ++i) secs[q].c[i] = sections[6 * q + 1 + i];
+    }
+    GroupHost gh; gh.first = 0; gh.count = (int)nsec;
+    GroupParam *gp = new GroupParam();
+    GroupTables *gt = new GroupTables();
+    build_group(secs.data(), gh, npt, gp, gt);
+    float *o = out;
+    *o++ = (float)gp->D; *o++ = (float)gt->depth; *o++ = (float)gp->agg_only; *o++ = 0.f;
+    memcpy(o, gp->imp, sizeof(gp->imp)); o += kMaxNpt * kMaxGroupDim;
+    memcpy(o, gp->lv, sizeof(gp->lv)); o += 5 * MM;
+    memcpy(o, gt->lane, sizeof(gt->lane)); o += 32 * MM;
+    memcpy(o, gt->lb, sizeof(gt->lb)); o += 32 * MM;
+    memcpy(o, gt->lb32, sizeof(gt->lb32)); o += MM;
+    memcpy(o, gt->tile, sizeof(gt->tile)); o += MM;
+    delete gp; delete gt;
     return nf;
 }
 

@@ -124,7 +124,7 @@ def lib():
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
     sig("orion_b200_debug_fir_plan", sz, i, vp, sz, sz, vp, vp, sz, vp, sz)
-    sig("orion_b200_debug_scan_tables", sz, i, vp, i, vp, sz)
+    sig("orion_b200_debug_group_tables", sz, vp, sz, i, vp, sz)
     _lib = L
     return L
 
@@ -147,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_block_decimation", "orion_b200_block_plan", "orion_b200_block_process",
     "orion_b200_block_process_dev", "orion_b200_block_synchronize", "orion_b200_block_set_stream",
     "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
-    "orion_b200_debug_fir_plan", "orion_b200_debug_scan_tables",
+    "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables",
 ]
 
 
@@ -226,16 +226,29 @@ def debug_fir_plan(fir_kind, taps, m):
     return plan
 
 
-def debug_scan_tables(sec_type, coeffs, npt):
+def debug_group_tables(sections, npt):
+    """Scan tables of one section group (tests only).  sections = [(type, [coefficients]), ...]."""
     L = lib()
-    c = np.zeros(5, np.float32)
-    c[:len(coeffs)] = coeffs
-    nf = L.orion_b200_debug_scan_tables(sec_type, c.ctypes.data, npt, None, 0)
-    t = np.zeros(nf + 32, np.float32)
-    L.orion_b200_debug_scan_tables(sec_type, c.ctypes.data, npt, t.ctypes.data, t.size)
-    m = t[:nf].reshape(-1, 4)
-    return {"lv": m[0:5], "lane": m[5:37], "lb": m[37:69], "lb32": m[69], "tile": m[70],
-            "depth": int(m[71].view(np.int32)[0]), "imp": t[nf:nf + 2 * npt].reshape(npt, 2)}
+    sec = np.zeros((len(sections), 6), np.float32)
+    for q, (t, c) in enumerate(sections):
+        sec[q, 0] = t
+        sec[q, 1:1 + len(c)] = c
+    nf = L.orion_b200_debug_group_tables(sec.ctypes.data, len(sections), npt, None, 0)
+    out = np.zeros(nf, np.float32)
+    L.orion_b200_debug_group_tables(sec.ctypes.data, len(sections), npt, out.ctypes.data, nf)
+    D = int(out[0])
+    o = 4
+    imp = out[o:o + 16 * 4].reshape(16, 4)[:npt, :D]; o += 16 * 4
+
+    def mats(n):
+        nonlocal o
+        m = out[o:o + n * 16].reshape(n, 16)[:, :D * D].reshape(n, D, D)
+        o += n * 16
+        return m
+    lv, lane, lb = mats(5), mats(32), mats(32)
+    lb32, tile = mats(1)[0], mats(1)[0]
+    return {"D": D, "depth": int(out[1]), "agg_only": bool(out[2]), "imp": imp, "lv": lv, "lane": lane, "lb": lb,
+            "lb32": lb32, "tile": tile}
 
 
 _DT = {ITEM_F32: np.float32, ITEM_C32: np.complex64}

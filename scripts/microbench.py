@@ -1,0 +1,40 @@
+"""Device-resident throughput of a few block shapes (CUDA events on a real stream)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "orion-sdr_b200", "python"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np, torch
+import orion_b200 as ob
+
+def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=10):
+    xs = [torch.randn(n_in * (2 if in_dtype == torch.complex64 else 1), device="cuda").view(-1) for _ in range(3)]
+    y = torch.empty(out_items * (2 if out_dtype == torch.complex64 else 1), dtype=torch.float32, device="cuda")
+    st = torch.cuda.Stream()
+    blk.set_stream(st.cuda_stream)
+    for i in range(3):
+        blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
+    blk.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(reps):
+        blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
+    e1.record(st)
+    blk.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:34s} {ms*1e3:8.1f} us  {n_in/ms/1e6:8.1f} GS/s  {bytes_per_in*n_in/ms/1e6:8.1f} GB/s", flush=True)
+
+n = 24_000_000
+taps = ob.fir_lowpass_design(2.4e6, 100e3, 38400.0)
+which = sys.argv[1:] or ["dec", "chain", "fm", "rot", "lp"]
+if "dec" in which:
+    bench("FirDecimator 63/8 (C32->C32)", ob.FirDecimator(2.4e6, 8, 100e3, 38400.0), n, torch.complex64, n // 8, torch.complex64, 9.0)
+if "chain" in which or "chainfm" in which:
+    bench("chain C1 FIR/8+NCO+FM+LR4", ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=8, demod=ob.DEMOD_FM, fs_demod=3e5, p0=25e3, audio_bw_hz=15e3, translate_hz=100e3), n, torch.complex64, n // 8, torch.float32, 8.5)
+if "chain" in which:
+    bench("chain FIR/8+AM (3 sections)", ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=8, demod=ob.DEMOD_AM, fs_demod=3e5, audio_bw_hz=15e3), n, torch.complex64, n // 8, torch.float32, 8.5)
+if "fm" in which:
+    bench("FmQuadratureDemod rate-1", ob.FmQuadratureDemod(3e5, 25e3, 15e3).with_translate(100e3), n, torch.complex64, n, torch.float32, 12.0)
+if "rot" in which:
+    bench("Rotator rate-1 (C32->C32)", ob.Rotator(1e5, 2.4e6), n, torch.complex64, n, torch.complex64, 16.0)
+if "lp" in which:
+    bench("LpCascade rate-1 (f32->f32)", ob.LpCascade(48e3, 4.5e3), n, torch.float32, n, torch.float32, 8.0)

@@ -150,7 +150,7 @@ def test_large_shapes_fall_back_to_global_front(rng):
 
 
 # --------------------------------------------------------------------------------------------------
-# scan tables: emulate pass 1 / warp scan / block combine / look-back in f64
+# section groups: emulate pass 1 (impulse-response dot products) / warp scan / look-back / pass 2 in f64
 # --------------------------------------------------------------------------------------------------
 def _step(sec_type, c, x, s):
     if sec_type == 1:
@@ -163,73 +163,92 @@ def _step(sec_type, c, x, s):
     return y, np.array([y, 0.0])
 
 
-def _mat(m):
-    return np.array([[m[0], m[1]], [m[2], m[3]]], np.float64)
+def _cascade(secs, x, st):
+    """One input sample through the cascade; st is the (2*count) state vector."""
+    st = st.copy()
+    v = x
+    for q, (t, c) in enumerate(secs):
+        v, st[2 * q:2 * q + 2] = _step(t, c, v, st[2 * q:2 * q + 2])
+    return v, st
 
 
-@pytest.mark.parametrize("sec_type,coef", [
-    (1, None), (2, [0.99973822]), (3, [0.98, 0.02]), (2, [0.9999]),
-])
+def _f32(c):
+    out = np.zeros(5)
+    out[:len(c)] = np.asarray(c, np.float32).astype(np.float64)
+    return out
+
+
+_BQ = lambda: list(ob.lp_biquad_design(48e3, 4.5e3).astype(np.float64))   # noqa: E731
+_GROUPS = {
+    "lr4": lambda: [(1, _BQ()), (1, _BQ())],
+    "bq_dc": lambda: [(1, _BQ()), (2, [0.99973822])],
+    "dc": lambda: [(2, [0.99973822])],
+    "dc_clamped": lambda: [(2, [0.9999])],
+    "onepole": lambda: [(3, [0.98, 0.02])],
+}
+
+
+@pytest.mark.parametrize("name", list(_GROUPS))
 @pytest.mark.parametrize("npt", [8, 16, 2])
-def test_scan_tables_stitch_chunks_exactly(sec_type, coef, npt, rng):
-    if coef is None:
-        coef = list(ob.lp_biquad_design(48e3, 4.5e3).astype(np.float64))
-    c = np.zeros(5)
-    c[:len(coef)] = np.asarray(coef, np.float32).astype(np.float64)
-    T = ob.debug_scan_tables(sec_type, c, npt)
+def test_group_tables_stitch_chunks_exactly(name, npt, rng):
+    secs = [(t, _f32(c)) for t, c in _GROUPS[name]()]
+    T = ob.debug_group_tables([(t, list(c)) for t, c in secs], npt)
+    D = T["D"]
+    assert D == 2 * len(secs)
     ntiles, tile_items = 5, KTHREADS * npt
     x = rng.standard_normal(ntiles * tile_items)
-    s_carry = rng.standard_normal(2) * (0.1 if sec_type != 2 else 1.0)
-    if sec_type == 3:
-        s_carry[1] = 0.0
+    s_carry = rng.standard_normal(D) * 0.1
+    for q, (t, _) in enumerate(secs):
+        if t == 3:
+            s_carry[2 * q + 1] = 0.0
     # sequential truth
-    s = s_carry.copy()
+    st = s_carry.copy()
     want = np.zeros_like(x)
     for n in range(x.size):
-        want[n], s = _step(sec_type, c, x[n], s)
-    # chunked: per-thread zero-state end states, warp scan, block combine, look-back with aggregates only
+        want[n], st = _cascade(secs, x[n], st)
+    # chunked, exactly as the kernel stitches it
     got = np.zeros_like(x)
     aggs = []
-    tile_in = None
+    prev_incl = None
+    lv, lane_m, lb = T["lv"].astype(np.float64), T["lane"].astype(np.float64), T["lb"].astype(np.float64)
     for t in range(ntiles):
         xs = x[t * tile_items:(t + 1) * tile_items].reshape(KTHREADS, npt)
-        e = np.zeros((KTHREADS, 2))
+        e = np.zeros((KTHREADS, D))
         for th in range(KTHREADS):
-            st = np.zeros(2)
+            z = np.zeros(D)
             for i in range(npt):
-                _, st = _step(sec_type, c, xs[th, i], st)
-            e[th] = st
-        # the kernel gets the same end states from the impulse-response dot product
-        e_dot = xs @ T["imp"].astype(np.float64)
+                _, z = _cascade(secs, xs[th, i], z)
+            e[th] = z
+        e_dot = xs @ T["imp"].astype(np.float64)          # the kernel's pass 1
         assert np.allclose(e_dot, e, rtol=1e-5, atol=1e-6 * max(1.0, np.max(np.abs(e))))
         E = e_dot.copy()
-        for l in range(5):                                   # Kogge-Stone across the warp
+        for l in range(5):                                 # Kogge-Stone across the warp
             d = 1 << l
             prev = E.copy()
-            for lane in range(d, 32):
-                E[lane] = prev[lane] + _mat(T["lv"][l]) @ prev[lane - d]
+            for ln in range(d, 32):
+                E[ln] = prev[ln] + lv[l] @ prev[ln - d]
         X = np.zeros_like(E)
         X[1:] = E[:-1]
-        S = E[31].copy()
-        aggs.append(S.copy())
-        # look-back over aggregates down to the carried state (virtual tile -1)
-        sin = np.zeros(2)
-        for k in range(min(t + 1, T["depth"])):              # predecessors past `depth` weigh nothing
+        aggs.append(E[31].copy())
+        sin = np.zeros(D)
+        for k in range(min(t + 1, T["depth"])):           # predecessors past `depth` weigh nothing
             pay = aggs[t - 1 - k] if t - 1 - k >= 0 else s_carry
-            sin = sin + _mat(T["lb"][k]) @ pay
-        incl = _mat(T["tile"]) @ sin + S
-        if tile_in is not None:
-            assert np.allclose(sin, tile_in, rtol=1e-5, atol=1e-6)
-        tile_in = incl
+            sin = sin + lb[k] @ pay
+        incl = T["tile"].astype(np.float64) @ sin + aggs[-1]
+        if prev_incl is not None:
+            assert np.allclose(sin, prev_incl, rtol=1e-5, atol=1e-6)
+        prev_incl = incl
         for th in range(KTHREADS):
-            st = X[th] + _mat(T["lane"][th]) @ sin
+            z = X[th] + lane_m[th] @ sin
             for i in range(npt):
-                got[t * tile_items + th * npt + i], st = _step(sec_type, c, xs[th, i], st)
+                got[t * tile_items + th * npt + i], z = _cascade(secs, xs[th, i], z)
     scale = max(1.0, np.max(np.abs(want)))
     assert np.max(np.abs(got - want)) < 2e-5 * scale
-    # look-back depth: A^(T*depth) vanishes, A^(T*(depth-1)) does not (fast poles: depth 1)
-    if sec_type == 1:
-        assert 1 <= T["depth"] <= 8            # fast poles: a handful of predecessor tiles at most
-    if sec_type == 2:
-        r = float(np.float32(coef[0]))
-        assert T["depth"] > 1 and r ** (KTHREADS * npt * T["depth"]) < 1e-30 <= r ** (KTHREADS * npt * (T["depth"] - 1))
+    # look-back depth: fast poles need a handful of predecessor tiles, the DC pole hundreds
+    if name == "lr4":
+        assert 1 <= T["depth"] <= 8 and T["agg_only"]
+    if name.startswith("dc") or name == "bq_dc":
+        r = float(np.float32(secs[-1][1][0]))
+        Tt = KTHREADS * npt
+        assert T["depth"] > 32 and not T["agg_only"]
+        assert r ** (Tt * T["depth"]) < 1e-29 and r ** (Tt * max(T["depth"] - 2, 0)) > 1e-31
