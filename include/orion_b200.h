@@ -222,6 +222,10 @@ size_t orion_b200_block_get_state(orion_b200_block *b, float *state, size_t cap)
 /* number of kernels this block has launched since creation (for bench accounting) [host-only] */
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b);
 
+/* Debug: per-tile SM-clock stamps of the kernel's phases, 8 x int64 per tile {consume, slot ready, FIR done,
+ * front done, section phase done, -, smid, warp}; d_trace is a device pointer (NULL disables). */
+int orion_b200_debug_set_trace(orion_b200_block *b, void *d_trace);
+
 /* Plan introspection for the host-logic tests [host-only].  info[12] = {front, R, U, Mb, O, P,
  * P_pad, HR, row_samples, row_pitch, rows, H}; returns the polyphase tap-table length (floats). */
 size_t orion_b200_debug_fir_plan(int fir_kind, const float *taps, size_t ntaps, size_t m, int info[12],

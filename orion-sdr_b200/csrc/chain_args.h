@@ -11,8 +11,8 @@ namespace orion {
 
 constexpr int kThreads     = 32;    // lanes per (warp) tile: one tile = 32 * NPT outputs
 constexpr int kWarpsPerCta = 8;     // default warps per CTA; they share a ring of staged-tile slots
-constexpr int kMaxWarpsPerCta = 16;
-constexpr int kMaxStages   = 8;     // slots in the ring
+constexpr int kMaxWarpsPerCta = 16;    // __launch_bounds__(512, 1): 128 registers per thread, 16 warps per SM
+constexpr int kMaxStages   = 12;    // slots in the ring
 constexpr int kMaxSections = 8;     // recursive sections per chain (LR4 = 2, LpDc = 3, + post sections)
 constexpr int kMaxTapTable = 2560;  // float capacity of the polyphase tap table held in the parameter bank
 constexpr int kMaxRowSamples = 128; // R * Mb limit of the shared-memory staged FIR (row <= 1024 B + pad)
@@ -116,6 +116,7 @@ struct ChainArgs {
     int   row_pitch;             // bytes, odd multiple of 16
     int   row_shift;             // log2(row_samples) when it is a power of two, else -1
     int   nstages;               // slots in the CTA's stage ring (1 in serial mode)
+    int   ntaps2;                // entries of taps2[] in use
     int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
     long long tma_row0;          // global row index of tensor-map row 0
     long long tma_rows;          // rows the tensor map covers
@@ -127,8 +128,8 @@ struct ChainArgs {
     // recursive sections
     int   nsec;
     int   ngroups;
+    GroupParam grp[kMaxGroups];  // grp immediately followed by sec: the kernels view the pair as one block
     SecParam sec[kMaxSections];
-    GroupParam grp[kMaxGroups];
     const GroupTables *gtabs;    // [ngroups]
     // carried state, ping-pong across calls
     const CarryState *carry_in;
@@ -139,6 +140,7 @@ struct ChainArgs {
     int   ntiles;
     int   serial;                // debug: tiles run one after another (grid = 1)
     int  *err_flag;
+    long long *trace;            // debug: 8 x int64 per tile {consume, ready, fir_done, front_done, finish_done, -, smid, warp}
     float2 taps2[kMaxTapTable / 2];   // [u][q][c] -> (g[t0], g[t0-1]); see DESIGN.md "staged FIR"
 };
 

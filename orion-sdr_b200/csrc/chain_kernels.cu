@@ -24,6 +24,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef ORION_TRACE
+#define ORION_TRACE 0
+#endif
+
 namespace orion {
 
 #define DEV __device__ __forceinline__
@@ -50,6 +54,25 @@ DEV float2 shfl2(float2 v, int src) {
 
 DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Packed FP32x2 FMA (sm_100 FFMA2): d = a * b + c on both halves of a 64-bit register pair, each
+// half a correctly rounded IEEE fma.  With a = (t, t) the SASS form takes t as a scalar operand.
+typedef unsigned long long f32x2;
+DEV f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+DEV float2 unpack2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+DEV f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // mbarrier / TMA (PTX ISA: mbarrier, cp.async.bulk.tensor)
 DEV void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
@@ -74,6 +97,33 @@ DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint3
 }
 DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Predicated forms for work that one elected lane does.  A C++ `if (lane == 0) { ... }` around these
+// would be a divergent branch; ptxas was seen to leave lane 0 split from the warp for the rest of the
+// loop iteration, after which every warp-synchronous shuffle takes its divergent slow path (~300
+// cycles each).  Predication keeps the warp converged.
+DEV void tma_fill_pred(bool p, uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t mbar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+        "@p fence.proxy.async.shared::cta;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%5], %6;\n\t"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%1], [%2, {%3, %4}], [%5];\n\t}"
+        ::"r"((uint32_t)p), "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar), "r"(bytes) : "memory");
+}
+DEV void mbar_arrive_pred(bool p, uint32_t mbar) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%1];\n\t}"
+                 ::"r"((uint32_t)p), "r"(mbar) : "memory");
+}
+DEV void st_shared_volatile_pred(bool p, uint32_t addr, int v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.volatile.shared.s32 [%1], %2;\n\t}"
+                 ::"r"((uint32_t)p), "r"(addr), "r"(v) : "memory");
+}
+DEV unsigned atom_add_shared_pred(bool p, uint32_t addr, unsigned v) {
+    unsigned old = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p atom.shared.add.u32 %0, [%2], %3;\n\t}"
+                 : "+r"(old) : "r"((uint32_t)p), "r"(addr), "r"(v) : "memory");
+    return old;
+}
+
 // 128-bit single-copy-atomic global accesses for the look-back records
 DEV uint4 ld_relaxed_b128(const void *p) {
     uint4 v;
@@ -86,14 +136,15 @@ DEV uint4 ld_relaxed_b128(const void *p) {
         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-DEV void st_relaxed_b128(void *p, uint4 v) {
+DEV void st_relaxed_b128(bool pred, void *p, uint4 v) {        // predicated: see tma_fill_pred
     asm volatile(
-        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t"
+        "{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\t.reg .pred q;\n\t"
+        "setp.ne.u32 q, %5, 0;\n\t"
         "mov.b64 lo, {%1, %2};\n\t"
         "mov.b64 hi, {%3, %4};\n\t"
         "mov.b128 t, {lo, hi};\n\t"
-        "st.relaxed.gpu.global.b128 [%0], t;\n\t}"
-        ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        "@q st.relaxed.gpu.global.b128 [%0], t;\n\t}"
+        ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -127,9 +178,8 @@ DEV float2 mix_apply(int mix, float2 x, float2 p) {
     return make_float2(x.x * p.x - x.y * p.y, x.x * p.y + x.y * p.x);   // nco.rs:63-66
 }
 
-// util.rs:305-322, op for op.  One shared copy: the per-item call sites would otherwise unroll it
-// NPT times and push the hot path out of the instruction cache.
-__device__ __noinline__ float atan2_approx(float y, float x) {
+// util.rs:305-322, op for op
+DEV float atan2_approx(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const bool sw = ax < ay;
     const float mn = sw ? ax : ay, mx = sw ? ay : ax;
@@ -163,6 +213,13 @@ DEV float2 load_x_mixed(const ChainArgs &a, long long s) {
     return x;
 }
 
+// Shared-memory copy of the per-section / per-group launch data.  Indexed reads of the kernel
+// parameter bank (LDC with a register offset) are not pipelined; broadcast LDS reads are.
+struct Hot {
+    GroupParam grp[kMaxGroups];
+    SecParam sec[kMaxSections];
+};
+
 // ----------------------------------------------------------------------------------------------
 // section groups: D-dimensional state-space scan (GroupParam / GroupTables in chain_args.h)
 // ----------------------------------------------------------------------------------------------
@@ -189,7 +246,7 @@ DEV void load_mat(const float *__restrict__ g, float (&M)[D * D]) {      // D*D 
 // written and read with ONE 128-bit access, so payload and tag can never be observed apart (no
 // fences, one L2 round trip per window of 32 predecessors).
 template <int D>
-DEV void publish(const ChainArgs &a, long long tile, int g, const float (&v)[D], bool inclusive) {
+DEV void publish(bool pred, const ChainArgs &a, long long tile, int g, const float (&v)[D], bool inclusive) {
     TileLink *lk = a.links + tile * kMaxGroups + g;
     uint4 *dst = inclusive ? lk->incl : lk->agg;
 #pragma unroll
@@ -198,7 +255,7 @@ DEV void publish(const ChainArgs &a, long long tile, int g, const float (&v)[D],
         rec.x = __float_as_uint(v[3 * r]);
         if (3 * r + 1 < D) rec.y = __float_as_uint(v[3 * r + 1]);
         if (3 * r + 2 < D) rec.z = __float_as_uint(v[3 * r + 2]);
-        st_relaxed_b128(dst + r, rec);
+        st_relaxed_b128(pred, dst + r, rec);
     }
 }
 template <int D>
@@ -222,8 +279,8 @@ DEV bool read_link(const uint4 *src, unsigned epoch, float (&v)[D]) {
 // because the section phase of a tile runs one loop iteration behind its front -- and never waits
 // for an inclusive value; slow poles (the DC blocker) use the classic chained form.
 template <int D>
-DEV void lookback(const ChainArgs &a, int g, long long tile, int lane, float (&sin)[D]) {
-    const GroupParam &G = a.grp[g];
+DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&sin)[D]) {
+    const GroupParam &G = hot->grp[g];
     const GroupTables *T = a.gtabs + g;
 #pragma unroll
     for (int d = 0; d < D; ++d) sin[d] = 0.f;
@@ -368,9 +425,10 @@ DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT]
 // responses), warp scan with constant transition powers, publish the tile aggregate.
 // X = state contribution of the lanes before this one; agg = whole-tile aggregate.
 template <int D, int NPT>
-DEV void group_front(const ChainArgs &a, int g, long long tile, int lane, const float (&u)[NPT], bool full,
+DEV void group_front(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, const float (&u)[NPT], bool full,
                      float (&X)[D], float (&agg)[D]) {
-    const GroupParam &G = a.grp[g];
+    const GroupParam &G = hot->grp[g];
+    __syncwarp();
     float E[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) E[d] = 0.f;
@@ -380,16 +438,21 @@ DEV void group_front(const ChainArgs &a, int g, long long tile, int lane, const 
 #pragma unroll
             for (int d = 0; d < D; ++d) E[d] = fmaf(G.imp[i][d], u[i], E[d]);
     }
+    if ((ORION_TRACE && a.trace) && g == 0) {
+        const unsigned am = __activemask();
+        if (lane == 0) { a.trace[tile * 16 + 11] = clock64(); a.trace[tile * 16 + 14] = am; }
+        if (lane == 31) a.trace[tile * 16 + 15] = am;
+    }
+    __syncwarp();                                  // converged here: the shuffles below take the fast path
 #pragma unroll
     for (int l = 0; l < 5; ++l) {
         float o[D], t[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) o[d] = __shfl_up_sync(FULLMASK, E[d], 1 << l);
         matvec<D>(G.lv[l], o, t);
-        if (lane >= (1 << l)) {
+        const bool take = lane >= (1 << l);        // select, not a branch: the warp stays converged
 #pragma unroll
-            for (int d = 0; d < D; ++d) E[d] += t[d];
-        }
+        for (int d = 0; d < D; ++d) E[d] += take ? t[d] : 0.f;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -397,24 +460,27 @@ DEV void group_front(const ChainArgs &a, int g, long long tile, int lane, const 
         if (lane == 0) X[d] = 0.f;
         agg[d] = __shfl_sync(FULLMASK, E[d], 31);
     }
-    if (lane == 0) publish<D>(a, tile, g, agg, false);
+    if ((ORION_TRACE && a.trace) && lane == 0 && g == 0) a.trace[tile * 16 + 12] = clock64();
+    publish<D>(lane == 0, a, tile, g, agg, false);
+    if ((ORION_TRACE && a.trace) && lane == 0 && g == 0) a.trace[tile * 16 + 13] = clock64();
 }
 
 // group finish: look-back, true start state of this lane's chunk, the reference recursion
 template <int D, int NPT>
-DEV void group_finish(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt,
+DEV void group_finish(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt,
                       const float (&X)[D], const float (&agg)[D]) {
-    const GroupParam &G = a.grp[g];
+    const GroupParam &G = hot->grp[g];
     const GroupTables *T = a.gtabs + g;
     float sin[D];
-    lookback<D>(a, g, tile, lane, sin);
-    if (!G.agg_only && lane == 0) {
+    lookback<D>(a, hot, g, tile, lane, sin);
+    if ((ORION_TRACE && a.trace) && lane == 0 && g == 0) a.trace[tile * 16 + 10] = clock64();
+    if (!G.agg_only) {                            // uniform branch; the store itself is predicated on lane 0
         float tm[D * D], inc[D];
         load_mat<D>(T->tile, tm);
         matvec<D>(tm, sin, inc);
 #pragma unroll
         for (int d = 0; d < D; ++d) inc[d] += agg[d];
-        publish<D>(a, tile, g, inc, true);
+        publish<D>(lane == 0, a, tile, g, inc, true);
     }
     float lm[D * D], st[D];
     load_mat<D>(T->lane[lane], lm);
@@ -424,7 +490,7 @@ DEV void group_finish(const ChainArgs &a, int g, long long tile, int lane, float
 #pragma unroll
     for (int q = 0; q < D / 2; ++q) {
         const int s = G.first + q;
-        const SecParam &P = a.sec[s];
+        const SecParam &P = hot->sec[s];
         if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
         else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
         else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
@@ -433,13 +499,13 @@ DEV void group_finish(const ChainArgs &a, int g, long long tile, int lane, float
 
 // dispatch on the group dimension
 template <int NPT>
-DEV void group_front_park(const ChainArgs &a, int g, long long tile, int lane, const float (&u)[NPT], bool full,
+DEV void group_front_park(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, const float (&u)[NPT], bool full,
                           float *park) {
     // park layout (floats): [lane][8] X, then [8] agg
-#define ORION_GF(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, g, tile, lane, u, full, X, agg); \
+#define ORION_GF(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, hot, g, tile, lane, u, full, X, agg); \
         _Pragma("unroll") for (int d = 0; d < DD; ++d) park[lane * kMaxGroupDim + d] = X[d]; \
         if (lane == 0) { _Pragma("unroll") for (int d = 0; d < DD; ++d) park[32 * kMaxGroupDim + d] = agg[d]; } }
-    switch (a.grp[g].D) {
+    switch (hot->grp[g].D) {
         case 2: ORION_GF(2) break;
         default: ORION_GF(4) break;
     }
@@ -447,22 +513,22 @@ DEV void group_front_park(const ChainArgs &a, int g, long long tile, int lane, c
     __syncwarp();
 }
 template <int NPT>
-DEV void group_finish_parked(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full,
+DEV void group_finish_parked(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&u)[NPT], bool full,
                              long long jt, const float *park) {
 #define ORION_GP(DD) { float X[DD], agg[DD]; \
         _Pragma("unroll") for (int d = 0; d < DD; ++d) { X[d] = park[lane * kMaxGroupDim + d]; agg[d] = park[32 * kMaxGroupDim + d]; } \
-        group_finish<DD, NPT>(a, g, tile, lane, u, full, jt, X, agg); }
-    switch (a.grp[g].D) {
+        group_finish<DD, NPT>(a, hot, g, tile, lane, u, full, jt, X, agg); }
+    switch (hot->grp[g].D) {
         case 2: ORION_GP(2) break;
         default: ORION_GP(4) break;
     }
 #undef ORION_GP
 }
 template <int NPT>
-DEV void group_whole(const ChainArgs &a, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt) {
-#define ORION_GW(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, g, tile, lane, u, full, X, agg); \
-        group_finish<DD, NPT>(a, g, tile, lane, u, full, jt, X, agg); }
-    switch (a.grp[g].D) {
+DEV void group_whole(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt) {
+#define ORION_GW(DD) { float X[DD], agg[DD]; group_front<DD, NPT>(a, hot, g, tile, lane, u, full, X, agg); \
+        group_finish<DD, NPT>(a, hot, g, tile, lane, u, full, jt, X, agg); }
+    switch (hot->grp[g].D) {
         case 2: ORION_GW(2) break;
         default: ORION_GW(4) break;
     }
@@ -484,25 +550,44 @@ DEV bool tile_is_interior(const ChainArgs &a, long long tile) {
     return a.use_tma && G0 >= a.tma_row0 && (G0 + kThreads + a.HR) <= (a.tma_row0 + a.tma_rows);
 }
 
-// cooperative (whole warp) load of an edge tile -- FIR history / ragged tail -- into the staged layout
+// cooperative (whole warp) load of an edge tile -- FIR history / ragged tail -- into the staged layout.
+// Loads are issued in batches of 16 independent chunks per lane: an edge tile sits in the same ring
+// as the TMA-staged ones, so a latency-serialised loader would stall the whole CTA behind its slot.
 DEV void stage_load_generic(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
+    constexpr int B = 16;
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
     const int cpr = a.row_samples >> 1;                 // 16-byte chunks per row
     const int total = rows * cpr;
+    const long long s_base = row_start_sample(a, G0);   // rows are contiguous in the stream: chunk c starts at s_base + 2c
     const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
-    for (int c = lane; c < total; c += kThreads) {
-        const int rho = c / cpr;
-        const int cc = c - rho * cpr;
-        const long long s = row_start_sample(a, G0 + rho) + 2 * cc;
-        float4 v;
-        if (al16 && s >= 0 && s + 1 < a.n_in) {
-            v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.in) + s));
-        } else {
-            const float2 x0 = load_x(a, s), x1 = load_x(a, s + 1);
-            v = make_float4(x0.x, x0.y, x1.x, x1.y);
+    const float2 *in = reinterpret_cast<const float2 *>(a.in);
+    for (int cb = 0; cb < total; cb += kThreads * B) {      // uniform trip count
+        const int c0 = cb + lane;
+        float4 v[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int c = c0 + k * kThreads;
+            const long long s = s_base + 2 * (long long)c;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < total) {
+                if (al16 && s >= 0 && s + 1 < a.n_in) {
+                    v[k] = __ldg(reinterpret_cast<const float4 *>(in + s));
+                } else {
+                    const float2 x0 = load_x(a, s), x1 = load_x(a, s + 1);
+                    v[k] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                }
+            }
         }
-        *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int c = c0 + k * kThreads;
+            if (c < total) {
+                const int rho = c / cpr;
+                const int cc = c - rho * cpr;
+                *reinterpret_cast<float4 *>(smem + (size_t)rho * a.row_pitch + (size_t)cc * 16) = v[k];
+            }
+        }
     }
     __syncwarp();
 }
@@ -513,7 +598,9 @@ DEV void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int 
     const long long G0 = tile * kThreads - a.HR;
     const int cpr = a.row_samples >> 1;
     const float2 w = make_float2(a.pre.wre, a.pre.wim);
-    for (int rho = lane; rho < rows; rho += kThreads) {
+    for (int rb = 0; rb < rows; rb += kThreads) {           // uniform trip count
+        const int rho = rb + lane;
+        if (rho >= rows) continue;
         const long long s0 = row_start_sample(a, G0 + rho);
         unsigned char *rp = smem + (size_t)rho * a.row_pitch;
         float2 p = make_float2(1.f, 0.f);
@@ -540,10 +627,92 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 }
 
 // polyphase FIR over the staged tile: lane l produces the outputs of blocks l*R .. l*R+R-1.
-// Per tap step: one LDS.128 (two adjacent samples), one tap pair from the parameter bank,
-// 4*R*U FMAs on an R-deep sliding register window.
+// Per tap step: one LDS.128 (two adjacent samples), one tap pair (broadcast LDS.64),
+// 2*R*U packed FP32x2 FMAs (FFMA2: re and im of one output in one instruction) on an R-deep
+// sliding register window.
+// Build-time variants (measured on the B200; DESIGN.md "tuning log"):
+//   ORION_FIR_PACKED  1: FFMA2 (packed f32x2) inner loop, loads hoisted per row; 0: scalar FFMA, rotating window
+//   ORION_TAPS_SMEM   1: tap pairs from a shared-memory copy; 0: from the kernel parameter bank
+//   ORION_HOT_SMEM    1: section / group launch data from a shared-memory copy; 0: from the parameter bank
+//   ORION_TRACE       1: per-tile SM-clock stamps into ChainArgs::trace (debug builds only: the stamps sit in the hot path)
+#ifndef ORION_FIR_PACKED
+#define ORION_FIR_PACKED 1
+#endif
+#ifndef ORION_TAPS_SMEM
+#define ORION_TAPS_SMEM 0
+#endif
+#ifndef ORION_HOT_SMEM
+#define ORION_HOT_SMEM 0
+#endif
+#if ORION_TAPS_SMEM
+#define ORION_TAPS taps_sh
+#else
+#define ORION_TAPS a.taps2
+#endif
+
+#if ORION_FIR_PACKED
 template <int R, int U>
-DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int lane, float2 (&z)[R * U]) {
+DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
+    f32x2 acc[U][R];                                 // (re, im) of every output, one packed register pair each
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < R; ++i) acc[u][i] = pack2(0.f, 0.f);
+
+    const int Mb = a.Mb, pitch = a.row_pitch, P_pad = a.P_pad, HR = a.HR;
+    const int blk_bytes = Mb * 8;
+    const unsigned char *row_own = smem + (size_t)lane * pitch;
+    const int npairs = Mb >> 1;
+    for (int q = 0; q < npairs; ++q) {
+        const int off_q = (Mb - 2 - 2 * q) * 8;
+        // sliding window of sample pairs (x[s], x[s+1]), each sample a packed (re, im) pair:
+        // W[0 .. R-2] = carried in, W[R-1 .. 2R-2] = the R blocks of the next row
+        f32x2 wlo[2 * R - 1], whi[2 * R - 1];
+#pragma unroll
+        for (int k = 0; k + 1 < R; ++k) {
+            const float4 v = *reinterpret_cast<const float4 *>(row_own + (k + 1) * blk_bytes + off_q);
+            wlo[k] = pack2(v.x, v.y);
+            whi[k] = pack2(v.z, v.w);
+        }
+        const float2 *tp0 = ORION_TAPS + (size_t)q * P_pad;
+        const float2 *tp1 = ORION_TAPS + (size_t)(npairs + q) * P_pad;     // U == 2 only
+        const unsigned char *rb = row_own + pitch + off_q;
+        for (int rr = 0; rr < HR; ++rr, rb += pitch) {
+            // all loads of this row first (R LDS.128 + R*U broadcast LDS.64), then 2*R*R*U packed FMAs
+            // in an order that touches every accumulator once per tap: dependent FMAs are R apart
+            float2 t[U][R];
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+                const float4 v = *reinterpret_cast<const float4 *>(rb + kk * blk_bytes);
+                wlo[R - 1 + kk] = pack2(v.x, v.y);
+                whi[R - 1 + kk] = pack2(v.z, v.w);
+                t[0][kk] = tp0[rr * R + kk];
+                if (U == 2) t[U - 1][kk] = tp1[rr * R + kk];
+            }
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const f32x2 t0 = pack2(t[u][kk].x, t[u][kk].x), t1 = pack2(t[u][kk].y, t[u][kk].y);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) acc[u][i] = ffma2(t0, wlo[kk + i], acc[u][i]);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) acc[u][i] = ffma2(t1, whi[kk + i], acc[u][i]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k + 1 < R; ++k) { wlo[k] = wlo[k + R]; whi[k] = whi[k + R]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int u = 0; u < U; ++u) z[i * U + u] = unpack2(acc[u][i]);
+}
+
+#else
+template <int R, int U>
+DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
     float2 acc[U][R];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -560,8 +729,8 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int lane, flo
 #pragma unroll
         for (int k = 0; k + 1 < R; ++k)
             w[k] = *reinterpret_cast<const float4 *>(row_own + (k + 1) * blk_bytes + off_q);
-        const float2 *tp0 = a.taps2 + (size_t)q * P_pad;
-        const float2 *tp1 = a.taps2 + (size_t)(npairs + q) * P_pad;     // U == 2 only
+        const float2 *tp0 = ORION_TAPS + (size_t)q * P_pad;
+        const float2 *tp1 = ORION_TAPS + (size_t)(npairs + q) * P_pad;     // U == 2 only
         const unsigned char *rb = row_own + pitch + off_q;
         for (int rr = 0; rr < HR; ++rr, rb += pitch) {
 #pragma unroll
@@ -588,6 +757,8 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, int lane, flo
 #pragma unroll
         for (int u = 0; u < U; ++u) z[i * U + u] = acc[u][i];
 }
+
+#endif
 
 // one FIR output evaluated straight from the virtual stream (any shape), in the reference's
 // accumulation order and rounding (fir.rs:57-66 unfused; fir.rs:229-247 fused)
@@ -618,15 +789,21 @@ DEV float2 fir_global_one(const ChainArgs &a, long long j) {
 }
 
 // warp-cooperative evaluation of one FIR output from the staged tile (discriminator halo)
-DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, long long G0, long long j, int lane) {
+DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, const float *g_sh, long long G0, long long j, int lane) {
     const long long n = (long long)a.M * j;
     float re = 0.f, im = 0.f;
-    for (int k = lane; k < a.Lg; k += 32) {
-        const float2 x = *staged_sample(a, smem, G0, n - k);
-        const float t = __ldg(a.g + k);
-        re = fmaf(x.x, t, re);
-        im = fmaf(x.y, t, im);
+    // uniform trip count: a lane-dependent loop bound would leave the warp split, and every
+    // warp-synchronous shuffle after it would then take the compiler's (very slow) divergent path
+    for (int k0 = 0; k0 < a.Lg; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < a.Lg) {
+            const float2 x = *staged_sample(a, smem, G0, n - k);
+            const float t = g_sh[k];
+            re = fmaf(x.x, t, re);
+            im = fmaf(x.y, t, im);
+        }
     }
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         re += __shfl_xor_sync(FULLMASK, re, o);
@@ -667,10 +844,12 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
                 const float cr = ph.x, ci = -ph.y;
                 zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
             }
+            __syncwarp();
         }
         if (need_prev) {
             float2 prev = shfl_up2(z[NPT - 1], 1);
             if (lane == 0) prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+            __syncwarp();
             // carried discriminator state for the next call
             if (a.n_out > 0 && jt <= a.n_out - 1 && a.n_out - 1 < jt + NPT) {
                 float2 last = z[0];
@@ -730,15 +909,20 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         }
     }
 
-    // end-of-call duties (last tile): FIR history and the state no stage of this call touches
-    if (tile == a.ntiles - 1) {
-        if (a.H > 0)
-            for (int k = lane; k < a.H; k += kThreads) a.hist_out[k] = load_x(a, a.n_in - a.H + k);
-        if (lane == 0) {
-            if (!need_prev || a.n_out == 0) a.carry_out->prev = a.carry_in->prev;
-            for (int s = 0; s < kMaxSections; ++s)
-                if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
-        }
+}
+
+// end-of-call duties that depend on the input only: the FIR history for the next call and the carried
+// state no stage of this call touches.  Run by one warp at the START of the kernel (off the tail).
+DEV void end_of_call_duties(const ChainArgs &a, int lane) {
+    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    if (a.H > 0)
+        for (int k0 = 0; k0 < a.H; k0 += kThreads)
+            if (k0 + lane < a.H) a.hist_out[k0 + lane] = load_x(a, a.n_in - a.H + k0 + lane);
+    __syncwarp();
+    if (lane == 0) {
+        if (!need_prev || a.n_out == 0) a.carry_out->prev = a.carry_in->prev;
+        for (int s = 0; s < kMaxSections; ++s)
+            if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
     }
 }
 
@@ -762,12 +946,12 @@ DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u
 // the section phase of a tile whose group-0 front ran one loop iteration earlier (state parked in
 // shared memory): group 0 finish, then the remaining groups front + finish, then the store
 template <int NPT>
-DEV void finish_sections(const ChainArgs &a, long long tile, int lane, float (&u)[NPT], const float *park) {
+DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&u)[NPT], const float *park) {
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
     const bool full = jt + NPT <= a.n_out;
     if (a.ngroups > 0) {
-        group_finish_parked<NPT>(a, 0, tile, lane, u, full, jt, park);
-        for (int g = 1; g < a.ngroups; ++g) group_whole<NPT>(a, g, tile, lane, u, full, jt);
+        group_finish_parked<NPT>(a, hot, 0, tile, lane, u, full, jt, park);
+        for (int g = 1; g < a.ngroups; ++g) group_whole<NPT>(a, hot, g, tile, lane, u, full, jt);
     }
     store_f32<NPT>(a, tile, lane, u);
 }
@@ -849,7 +1033,6 @@ __global__ void __launch_bounds__(kThreads * kMaxWarpsPerCta, 1)
 chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int NPT = R * U;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(16) float park_all[kMaxWarpsPerCta][2][33 * kMaxGroupDim];
     __shared__ RingCtl ring;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int NW = blockDim.x >> 5;
@@ -857,10 +1040,36 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     const long long G = gridDim.x, cta = blockIdx.x;
     const size_t stage_bytes = (size_t)(kThreads + a.HR) * a.row_pitch;      // bytes one TMA load delivers
     const size_t stage_stride = (stage_bytes + 127) & ~(size_t)127;          // TMA destinations are 128-byte aligned
-    float (*park)[33 * kMaxGroupDim] = park_all[wid];
+    // group-0 scan state of the two tiles a warp has in flight: behind the stage ring in dynamic smem
+    float (*park)[33 * kMaxGroupDim] = reinterpret_cast<float (*)[33 * kMaxGroupDim]>(
+        smem + (size_t)NS * stage_stride + (size_t)wid * 2 * 33 * kMaxGroupDim * sizeof(float));
+    // polyphase tap table: behind the park area
+    float2 *taps_sh = reinterpret_cast<float2 *>(smem + (size_t)NS * stage_stride +
+                                                 (size_t)NW * 2 * 33 * kMaxGroupDim * sizeof(float));
+    // ... then the generic taps g[] (discriminator halo) and the section / group launch data
+    float *g_sh = reinterpret_cast<float *>(taps_sh + a.ntaps2);
+    Hot *hot_sh = reinterpret_cast<Hot *>(reinterpret_cast<unsigned char *>(g_sh) + (((size_t)a.Lg * sizeof(float) + 15) & ~(size_t)15));
+    // Hot's layout equals ChainArgs::grp followed by ChainArgs::sec (static_assert below)
+    const Hot *hot = ORION_HOT_SMEM ? hot_sh : reinterpret_cast<const Hot *>(a.grp);
+    if (FRONT == FRONT_STAGED) {
+        for (int i = threadIdx.x; i < a.ntaps2; i += blockDim.x) taps_sh[i] = a.taps2[i];
+        for (int i = threadIdx.x; i < a.Lg; i += blockDim.x) g_sh[i] = __ldg(a.g + i);
+    }
+    if (ORION_HOT_SMEM) {
+        const int n_grp = (int)(sizeof(GroupParam) * kMaxGroups / sizeof(float)), n_sec = (int)(sizeof(SecParam) * kMaxSections / sizeof(float));
+        const float *src_g = reinterpret_cast<const float *>(a.grp), *src_s = reinterpret_cast<const float *>(a.sec);
+        float *dst_g = reinterpret_cast<float *>(hot_sh->grp), *dst_s = reinterpret_cast<float *>(hot_sh->sec);
+        for (int i = threadIdx.x; i < n_grp; i += blockDim.x) dst_g[i] = src_g[i];
+        for (int i = threadIdx.x; i < n_sec; i += blockDim.x) dst_s[i] = src_s[i];
+    }
 
     const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
     const bool has_sections = a.demod != DEMOD_NONE;
+    if ((ORION_TRACE && a.trace) && threadIdx.x == 0) {                  // debug: kernel span in %globaltimer ns
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long *>(a.trace + (long long)a.ntiles * 16), gt);
+    }
 
     if (FRONT == FRONT_STAGED) {
         if (threadIdx.x == 0) {
@@ -870,22 +1079,20 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     }
     if (threadIdx.x == 0) ring.cons = 0;
     __syncthreads();
+    if (cta == (long long)(a.ntiles - 1) % G && wid == NW - 1) end_of_call_duties(a, lane);
 
     // fill k of slot s = the CTA's tile number i = k*NS + s (lane 0): TMA for interior tiles, a plain
     // arrive for edge tiles (their consumer loads them cooperatively); nothing past the end
     auto fill_slot = [&](int s, int k) {
         const long long t = cta + G * ((long long)k * NS + s);
-        if (lane == 0 && t < a.ntiles) {
-            const uint32_t bar = smem_u32(&ring.full[s]);
-            *reinterpret_cast<volatile int *>(&ring.gen[s]) = k;      // before the arrive below (release)
-            if (tile_is_interior(a, t)) {
-                fence_proxy_async();          // earlier generic-proxy accesses to the slot vs the async write
-                mbar_expect_tx(bar, (uint32_t)stage_bytes);
-                tma_load_2d(smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
-                            (int)(t * kThreads - a.HR - a.tma_row0), bar);
-            } else {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-            }
+        const bool pred = lane == 0 && t < a.ntiles;
+        const uint32_t bar = smem_u32(&ring.full[s]);
+        st_shared_volatile_pred(pred, smem_u32(&ring.gen[s]), k);        // before the arrive below (release)
+        if (tile_is_interior(a, t)) {                                     // warp-uniform
+            tma_fill_pred(pred, smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
+                          (int)(t * kThreads - a.HR - a.tma_row0), bar, (uint32_t)stage_bytes);
+        } else {
+            mbar_arrive_pred(pred, bar);
         }
     };
 
@@ -894,16 +1101,25 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     for (int i = 0; i < NPT; ++i) u_pend[i] = 0.f;
     long long pend_tile = -1;
     int slot_pp = 0;
+    auto stamp = [&](long long t, int k) {
+        if ((ORION_TRACE && a.trace) && lane == 0) a.trace[t * 16 + k] = clock64();
+        __syncwarp();
+    };
 
     if (FRONT == FRONT_STAGED)
         for (int s = wid; s < NS; s += NW) fill_slot(s, 0);            // initial fill of the ring
 
     for (;;) {
-        unsigned c = 0;
-        if (lane == 0) c = atomicAdd(&ring.cons, 1u);
+        unsigned c = atom_add_shared_pred(lane == 0, smem_u32(&ring.cons), 1u);
         c = __shfl_sync(FULLMASK, c, 0);
         const long long tile = cta + G * (long long)c;
         if (tile >= a.ntiles) break;
+        stamp(tile, 0);
+        if ((ORION_TRACE && a.trace) && lane == 0) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            a.trace[tile * 16 + 5] = (long long)gt;
+        }
         int s = 0, k = 0;
         unsigned char *stage = smem;
         if (FRONT == FRONT_STAGED) {
@@ -923,6 +1139,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             }
             stage = smem + (size_t)s * stage_stride;
         }
+        stamp(tile, 1);
 
         float2 z[NPT];
         float  u[NPT];
@@ -935,10 +1152,12 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         if (FRONT == FRONT_STAGED) {
             if (!tile_is_interior(a, tile)) stage_load_generic(a, tile, stage, lane);
             if (a.mix != MIX_NONE) stage_mix(a, tile, stage, lane);
-            fir_staged<R, U>(a, stage, lane, z);
-            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, tile * kThreads - a.HR, j0 - 1, lane);
+            fir_staged<R, U>(a, stage, taps_sh, lane, z);
+            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, g_sh, tile * kThreads - a.HR, j0 - 1, lane);
             __syncwarp();                               // every lane is done with the slot: refill it
+            stamp(tile, 2);
             fill_slot(s, k + 1);
+            stamp(tile, 8);
         } else if (FRONT == FRONT_GLOBAL) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i)
@@ -948,16 +1167,30 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             front_direct<NPT>(a, tile, lane, z, u, zhalo);
         }
         front_map<NPT>(a, tile, lane, z, u, zhalo);
+        if ((ORION_TRACE && a.trace) && lane == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.trace[tile * 16 + 6] = smid;
+            a.trace[tile * 16 + 7] = wid + 100 * (long long)blockIdx.x;
+            a.trace[tile * 16 + 9] = clock64();
+            if (!has_sections) a.trace[tile * 16 + 3] = clock64();
+        }
         if (has_sections) {
-            if (a.ngroups > 0) group_front_park<NPT>(a, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
-            if (pend_tile >= 0) finish_sections<NPT>(a, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+            if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
+            stamp(tile, 3);
+            if (pend_tile >= 0) { finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]); stamp(pend_tile, 4); }
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u_pend[i] = u[i];
             pend_tile = tile;
             slot_pp ^= 1;
         }
     }
-    if (pend_tile >= 0) finish_sections<NPT>(a, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+    if (pend_tile >= 0) finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+    if ((ORION_TRACE && a.trace) && lane == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long *>(a.trace + (long long)a.ntiles * 16 + 1), gt);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1005,3 +1238,6 @@ cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const C
 }
 
 }  // namespace orion
+
+static_assert(offsetof(orion::ChainArgs, sec) == offsetof(orion::ChainArgs, grp) + sizeof(orion::GroupParam) * orion::kMaxGroups,
+              "ChainArgs::grp must be followed directly by ChainArgs::sec");

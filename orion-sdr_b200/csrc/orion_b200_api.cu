@@ -275,7 +275,7 @@ struct FirPlan {
     int R = 8, U = 1, Mb = 0, O = 0, P = 0, P_pad = 0, HR = 0, row_samples = 0, row_pitch = 0, rows = 0;
     int H = 0;
     int nstages = 0;
-    int warps = kWarpsPerCta;
+    int warps = kMaxWarpsPerCta;
     size_t stage_bytes = 0;
     size_t dyn_smem = 0;
     std::vector<float> g;          // generic causal taps
@@ -283,7 +283,7 @@ struct FirPlan {
 };
 
 const size_t kMaxStageBytes = 100 * 1024;      // one staged tile
-const size_t kRingBudget = 100 * 1024;         // per-CTA shared memory for the stage ring (two CTAs per SM)
+const size_t kRingBudget = 176 * 1024;         // per-CTA shared memory for the stage ring (two CTAs per SM)
 
 void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl) {
     const int L = (int)taps.size();
@@ -320,11 +320,11 @@ void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force
             pl->R = R; pl->U = U; pl->Mb = (int)Mb; pl->O = O; pl->P = P; pl->P_pad = P_pad; pl->HR = HR;
             const size_t stride = (smem + 127) & ~(size_t)127;       // TMA destinations are 128-byte aligned
             pl->row_samples = row_samples; pl->row_pitch = pitch; pl->rows = rows; pl->stage_bytes = stride;
-            pl->nstages = (int)std::min<size_t>(std::max<size_t>(kRingBudget / stride, 1), (size_t)std::min(kMaxStages, kWarpsPerCta - 2));
+            pl->nstages = (int)std::min<size_t>(std::max<size_t>(kRingBudget / stride, 1), (size_t)kMaxStages);
             // tuning overrides (experiments): ORION_B200_WARPS = warps per CTA, ORION_B200_STAGES = ring slots
             if (const char *e = getenv("ORION_B200_WARPS")) pl->warps = std::max(1, std::min(kMaxWarpsPerCta, atoi(e)));
             if (const char *e = getenv("ORION_B200_STAGES")) pl->nstages = std::max(1, std::min(kMaxStages, atoi(e)));
-            pl->dyn_smem = stride * pl->nstages;
+            pl->dyn_smem = stride * pl->nstages;       // + the per-warp park area, added in finalize_plan
             pl->taps2.assign(table, make_float2(0.f, 0.f));
             for (int u = 0; u < U; ++u)
                 for (int q = 0; q < (int)(Mb / 2); ++q)
@@ -397,6 +397,7 @@ struct orion_b200_block {
     int ctas_per_sm = 1, sm_count = 1;
     // ---- options ----
     int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0;
+    long long *trace = nullptr;           // debug: device buffer of 8 x int64 per tile
     // ---- device ----
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -445,6 +446,11 @@ int finalize_plan(orion_b200_block *b) {
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
+    b->plan.dyn_smem = b->plan.stage_bytes * b->plan.nstages +
+                       (size_t)b->plan.warps * 2 * 33 * kMaxGroupDim * sizeof(float) +     // stage ring + park area
+                       b->plan.taps2.size() * sizeof(float2) +                              // + tap table
+                       ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +            // + generic taps
+                       sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 16;  // + section/group data
     CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, b->plan.warps, &b->ctas_per_sm));
     if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
     // FIR taps + history
@@ -629,7 +635,9 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
     a.links = b->d_links;
     a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err;
+    a.trace = b->trace;
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
+    a.ntaps2 = (int)b->plan.taps2.size();
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
@@ -1112,6 +1120,13 @@ size_t orion_b200_block_get_state(orion_b200_block *b, float *state, size_t cap)
 }
 
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b) { return b ? b->launches : 0; }
+
+// debug: per-tile SM clock stamps (8 x int64 per tile, device pointer; NULL disables)
+int orion_b200_debug_set_trace(orion_b200_block *b, void *d_trace) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    b->trace = (long long *)d_trace;
+    return ORION_B200_OK;
+}
 
 // plan introspection for the host-logic tests [host-only]: fills `info` (12 ints) and, when
 // `table` has room, the polyphase tap table as floats.  Returns the table length in floats.

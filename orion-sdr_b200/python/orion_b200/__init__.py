@@ -16,7 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))           # .../orion-sdr_b200
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "liborion_b200.so")
+LIB_PATH = os.environ.get("ORION_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "liborion_b200.so")
 
 WorkReport = namedtuple("WorkReport", ["in_read", "out_written"])   # src/core.rs:7-10
 
@@ -123,6 +123,7 @@ def lib():
     sig("orion_b200_block_set_option", i, vp, i, d)
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
+    sig("orion_b200_debug_set_trace", i, vp, vp)
     sig("orion_b200_debug_fir_plan", sz, i, vp, sz, sz, vp, vp, sz, vp, sz)
     sig("orion_b200_debug_group_tables", sz, vp, sz, i, vp, sz)
     _lib = L
@@ -147,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_block_decimation", "orion_b200_block_plan", "orion_b200_block_process",
     "orion_b200_block_process_dev", "orion_b200_block_synchronize", "orion_b200_block_set_stream",
     "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
-    "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables",
+    "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables", "orion_b200_debug_set_trace",
 ]
 
 
@@ -328,6 +329,9 @@ class Block:
         s = np.zeros(n, np.float32)
         lib().orion_b200_block_get_state(self._h, s.ctypes.data, n)
         return s
+
+    def set_trace(self, d_ptr: int):
+        _check(lib().orion_b200_debug_set_trace(self._h, C.c_void_p(d_ptr)), self._h)
 
     @property
     def decimation(self) -> int:

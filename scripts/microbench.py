@@ -6,14 +6,16 @@ for p in (ROOT, os.path.join(ROOT, "orion-sdr_b200", "python"), os.path.join(ROO
 import numpy as np, torch
 import orion_b200 as ob
 
-def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=10):
+def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30):
     xs = [torch.randn(n_in * (2 if in_dtype == torch.complex64 else 1), device="cuda").view(-1) for _ in range(3)]
     y = torch.empty(out_items * (2 if out_dtype == torch.complex64 else 1), dtype=torch.float32, device="cuda")
     st = torch.cuda.Stream()
     blk.set_stream(st.cuda_stream)
-    for i in range(3):
-        blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
-    blk.synchronize()
+    t_end = time.perf_counter() + float(os.environ.get("WARM_S", "1.5"))      # sustained load: let the SM clock ramp up
+    while time.perf_counter() < t_end:
+        for i in range(30):
+            blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
+        blk.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(reps):
