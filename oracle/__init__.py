@@ -104,6 +104,13 @@ def lib():
     sig("oo_cw_demod_new", vp, f, f, f)
     sig("oo_cw_demod_set_gain", None, vp, f)
     sig("oo_get_state", sz, vp, vp, sz)
+    sig("oo_fm_mod_new", vp, f, f, f)
+    sig("oo_pm_mod_new", vp, f, f, f)
+    sig("oo_am_mod_new", vp, f, f, f, f)
+    sig("oo_am_mod_set_clamp", None, vp, i)
+    sig("oo_ssb_mod_new", vp, f, f, f, f, i)
+    sig("oo_cw_mod_new", vp, f, f, f, f)
+    sig("oo_mod_set_gain", None, vp, f)
     _lib = L
     return L
 
@@ -390,6 +397,44 @@ class CwEnvelopeDemod(Block):
 
     def set_gain(self, g):
         lib().oo_cw_demod_set_gain(self._h, g)
+
+
+# ---- modulators, f32 -> c32 (src/modulate/*.rs; SURVEY.md 8(f) row 1, CPU oracle only) ----
+
+class _Mod(Block):
+    In = np.float32
+    Out = np.complex64
+
+    def set_gain(self, g):
+        lib().oo_mod_set_gain(self._h, g)
+
+
+class FmPhaseAccumMod(_Mod):                          # src/modulate/fm.rs:11-75
+    def __init__(self, sample_rate, deviation_hz, rf_hz):
+        super().__init__(lib().oo_fm_mod_new(sample_rate, deviation_hz, rf_hz))
+
+
+class PmDirectPhaseMod(_Mod):                         # src/modulate/pm.rs:10-47
+    def __init__(self, sample_rate, kp_rad_per_unit, rf_hz):
+        super().__init__(lib().oo_pm_mod_new(sample_rate, kp_rad_per_unit, rf_hz))
+
+
+class AmDsbMod(_Mod):                                 # src/modulate/am.rs:10-120
+    def __init__(self, fs, rf_hz, carrier_level, modulation_index):
+        super().__init__(lib().oo_am_mod_new(fs, rf_hz, carrier_level, modulation_index))
+
+    def set_clamp(self, on):
+        lib().oo_am_mod_set_clamp(self._h, int(bool(on)))
+
+
+class SsbPhasingMod(_Mod):                            # src/modulate/ssb.rs:11-114
+    def __init__(self, fs, audio_bw_hz, audio_if_hz, rf_hz, usb):
+        super().__init__(lib().oo_ssb_mod_new(fs, audio_bw_hz, audio_if_hz, rf_hz, int(bool(usb))))
+
+
+class CwKeyedMod(_Mod):                               # src/modulate/cw.rs:10-102
+    def __init__(self, sample_rate, tone_hz, rise_ms, fall_ms):
+        super().__init__(lib().oo_cw_mod_new(sample_rate, tone_hz, rise_ms, fall_ms))
 
 
 # ---- chain wrappers (src/core.rs:25-109): single-block, return input.len() items ----

@@ -168,7 +168,8 @@ float oo_atan2_approx(float y, float x) {
 
 enum {
     K_FIR_LOWPASS = 1, K_FIR_DECIM, K_FIR_IQ, K_ROTATOR, K_NCO, K_BIQUAD, K_LP_CASCADE,
-    K_LP_DC_CASCADE, K_DC_BLOCKER, K_FM, K_PM, K_AM, K_SSB, K_CW
+    K_LP_DC_CASCADE, K_DC_BLOCKER, K_FM, K_PM, K_AM, K_SSB, K_CW,
+    K_MOD_FM, K_MOD_PM, K_MOD_AM, K_MOD_SSB, K_MOD_CW      /* f32 -> c32; SURVEY.md 8(f) row 1 */
 };
 
 typedef struct { float *taps; float *delay; size_t len, idx; } fir_real;     /* fir.rs:7-12 */
@@ -196,6 +197,12 @@ struct oo_block {
     float fs, k; oo_c32 prev;
     int abs_approx; float k1, k2;
     float alpha, y, gain;
+    /* modulators (src/modulate/{fm,pm,am,ssb,cw}.rs) */
+    rotator rot2;                    /* second oscillator: SSB rf_nco */
+    biquad bq2[2];                   /* SSB lp_q */
+    oo_c32 mz; uint32_t mctr;        /* FM running phasor + its renorm counter */
+    float carrier, mindex; int clamp, usb;
+    float env, a_rise, a_fall;
 };
 
 static void fir_real_init(fir_real *f, const float *taps, size_t n) {
@@ -482,6 +489,61 @@ oo_block *oo_cw_demod_new(float fs, float tone_hz, float env_bw_hz) {
 void oo_cw_demod_set_gain(oo_block *b, float g) { b->gain = g; }
 
 /* ---- reset --------------------------------------------------------------- */
+
+/* ---- modulators (f32 -> c32): the step before the path in the reference's round-trip tests ---- */
+
+/* mix_with_nco, src/dsp/nco.rs:63-66 (num-complex Mul is unfused) */
+static inline oo_c32 mix_nco_step(rotator *r, oo_c32 x) {
+    oo_c32 p = rotator_step(r);
+    oo_c32 y = { x.re * p.re - x.im * p.im, x.re * p.im + x.im * p.re };
+    return y;
+}
+
+oo_block *oo_fm_mod_new(float fs, float deviation_hz, float rf_hz) {            /* modulate/fm.rs:22-31 */
+    oo_block *b = blk_new(K_MOD_FM);
+    b->fs = fs; b->k = deviation_hz; b->gain = 1.0f;
+    b->mz.re = 1.0f; b->mz.im = 0.0f; b->mctr = 0;
+    rotator_init(&b->rot, rf_hz, fs);
+    return b;
+}
+oo_block *oo_pm_mod_new(float fs, float kp_rad_per_unit, float rf_hz) {         /* modulate/pm.rs:17-23 */
+    oo_block *b = blk_new(K_MOD_PM);
+    b->k = kp_rad_per_unit; b->gain = 1.0f;
+    rotator_init(&b->rot, rf_hz, fs);
+    return b;
+}
+oo_block *oo_am_mod_new(float fs, float rf_hz, float carrier_level, float modulation_index) {   /* modulate/am.rs:21-30 */
+    oo_block *b = blk_new(K_MOD_AM);
+    b->gain = 1.0f; b->carrier = carrier_level; b->mindex = modulation_index; b->clamp = 0;
+    rotator_init(&b->rot, rf_hz, fs);
+    return b;
+}
+void oo_am_mod_set_clamp(oo_block *b, int on) { b->clamp = on; }                 /* modulate/am.rs:34-36 */
+oo_block *oo_ssb_mod_new(float fs, float audio_bw_hz, float audio_if_hz, float rf_hz, int usb) { /* modulate/ssb.rs:23-35 */
+    oo_block *b = blk_new(K_MOD_SSB);
+    float c[5];
+    oo_lp_biquad_design(fs, audio_bw_hz * 0.9f, c);
+    for (int i = 0; i < 2; ++i) {
+        biquad q = { c[0], c[1], c[2], c[3], c[4], 0.0f, 0.0f };
+        b->bq[i] = q; b->bq2[i] = q;
+    }
+    b->usb = usb;
+    rotator_init(&b->rot, audio_if_hz, fs);
+    rotator_init(&b->rot2, rf_hz, fs);
+    return b;
+}
+oo_block *oo_cw_mod_new(float fs, float tone_hz, float rise_ms, float fall_ms) { /* modulate/cw.rs:21-34 */
+    oo_block *b = blk_new(K_MOD_CW);
+    float tau_r = (oo_maxf(rise_ms, 0.1f) * 1e-3f) * fs;
+    float tau_f = (oo_maxf(fall_ms, 0.1f) * 1e-3f) * fs;
+    b->a_rise = expf(-1.0f / tau_r);
+    b->a_fall = expf(-1.0f / tau_f);
+    b->env = 0.0f; b->gain = 1.0f;
+    rotator_init(&b->rot, tone_hz, fs);
+    return b;
+}
+void oo_mod_set_gain(oo_block *b, float g) { b->gain = g; }
+
 void oo_reset(oo_block *b) {
     if (b->fi.delay) { memset(b->fi.delay, 0, b->fi.len * sizeof(float)); b->fi.idx = 0; }
     if (b->fq.delay) { memset(b->fq.delay, 0, b->fq.len * sizeof(float)); b->fq.idx = 0; }
@@ -684,6 +746,70 @@ oo_work_report oo_process(oo_block *b, const void *in, size_t n_in, void *out, s
         wr.in_read = n; wr.out_written = n;
         break;
     }
+    case K_MOD_FM: {                                         /* modulate/fm.rs:45-72 */
+        float kf = OO_TAU * b->k / b->fs;
+        for (size_t i = 0; i < n; ++i) {
+            float dphi = kf * fin[i];
+            float ds = sinf(dphi), dc = cosf(dphi);
+            float zr = fmaf(b->mz.re, dc, -(b->mz.im * ds));
+            float zi = fmaf(b->mz.im, dc, b->mz.re * ds);
+            b->mz.re = zr; b->mz.im = zi;
+            b->mctr += 1u;
+            if ((b->mctr & 0x3FFu) == 0u) {
+                float inv = 1.0f / sqrtf(b->mz.re * b->mz.re + b->mz.im * b->mz.im);
+                b->mz.re *= inv; b->mz.im *= inv;
+            }
+            oo_c32 base = { b->mz.re * b->gain, b->mz.im * b->gain };
+            cout[i] = mix_nco_step(&b->rot, base);
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+    }
+    case K_MOD_PM:                                           /* modulate/pm.rs:37-47 */
+        for (size_t i = 0; i < n; ++i) {
+            float phi = b->k * fin[i];
+            oo_c32 base = { cosf(phi) * b->gain, sinf(phi) * b->gain };
+            cout[i] = mix_nco_step(&b->rot, base);
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
+    case K_MOD_AM:                                           /* modulate/am.rs:44-120 (the 4x unroll is order-preserving) */
+        for (size_t i = 0; i < n; ++i) {
+            float m = b->carrier + b->mindex * fin[i];
+            if (b->clamp) m = oo_minf(oo_maxf(m, -1.0f), 1.0f);
+            m = m * b->gain;
+            oo_c32 r = rotator_step(&b->rot);
+            cout[i].re = m * r.re; cout[i].im = m * r.im;
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
+    case K_MOD_SSB: {                                        /* modulate/ssb.rs:42-114 */
+        float side = b->usb ? 1.0f : -1.0f;
+        for (size_t i = 0; i < n; ++i) {
+            oo_c32 p = rotator_step(&b->rot);
+            float ii = biquad_step(&b->bq[1], biquad_step(&b->bq[0], fin[i] * p.re));
+            float qq = biquad_step(&b->bq2[1], biquad_step(&b->bq2[0], fin[i] * p.im));
+            oo_c32 z = { ii, side * qq };
+            oo_c32 r = rotator_step(&b->rot2);
+            cout[i].re = fmaf(z.re, r.re, -(z.im * r.im));
+            cout[i].im = fmaf(z.im, r.re, z.re * r.im);
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+    }
+    case K_MOD_CW:                                           /* modulate/cw.rs:44-102 */
+        for (size_t i = 0; i < n; ++i) {
+            float tgt = oo_minf(oo_maxf(fin[i], 0.0f), 1.0f);
+            b->env = (tgt >= b->env) ? b->a_rise * b->env + (1.0f - b->a_rise) * tgt
+                                     : b->a_fall * b->env + (1.0f - b->a_fall) * tgt;
+            oo_c32 base = { b->env * b->gain, 0.0f };
+            cout[i] = mix_nco_step(&b->rot, base);
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
     default: break;
     }
     return wr;

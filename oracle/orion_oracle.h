@@ -92,6 +92,16 @@ oo_block *oo_ssb_demod_new(float fs, float bfo_hz, float audio_bw_hz);          
 oo_block *oo_cw_demod_new(float fs, float tone_hz, float env_bw_hz);            /* cw.rs:15-24 */
 void      oo_cw_demod_set_gain(oo_block *b, float g);                           /* cw.rs:25-27 */
 
+/* modulators, f32 -> c32 (src/modulate/{fm,pm,am,ssb,cw}.rs) -- SURVEY.md 8(f) row 1: the step before the path in the
+ * reference's round-trip tests; CPU only */
+oo_block *oo_fm_mod_new(float fs, float deviation_hz, float rf_hz);             /* modulate/fm.rs:22-75 */
+oo_block *oo_pm_mod_new(float fs, float kp_rad_per_unit, float rf_hz);          /* modulate/pm.rs:17-47 */
+oo_block *oo_am_mod_new(float fs, float rf_hz, float carrier_level, float modulation_index); /* modulate/am.rs:21-120 */
+void      oo_am_mod_set_clamp(oo_block *b, int on);
+oo_block *oo_ssb_mod_new(float fs, float audio_bw_hz, float audio_if_hz, float rf_hz, int usb); /* modulate/ssb.rs:23-114 */
+oo_block *oo_cw_mod_new(float fs, float tone_hz, float rise_ms, float fall_ms); /* modulate/cw.rs:21-102 */
+void      oo_mod_set_gain(oo_block *b, float g);
+
 /* streaming-state snapshot for tests (floats; layout documented per block in the .c) */
 size_t oo_get_state(const oo_block *b, float *state, size_t cap);
 
