@@ -252,3 +252,31 @@ def test_group_tables_stitch_chunks_exactly(name, npt, rng):
         Tt = KTHREADS * npt
         assert T["depth"] > 32 and not T["agg_only"]
         assert r ** (Tt * T["depth"]) < 1e-29 and r ** (Tt * max(T["depth"] - 2, 0)) > 1e-31
+
+
+def test_rust_ffi_declares_every_symbol():
+    """ffi/orion-b200-sys/src/lib.rs (source only: no Rust toolchain here) must declare every non-debug
+    entry point of the header, and nothing the header does not have."""
+    hdr = open(os.path.join(ROOT, "include", "orion_b200.h")).read()
+    declared = set(re.findall(r"\b(orion_b200_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "ffi", "orion-b200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (orion_b200_[a-z0-9_]+)\s*\(", rs))
+    assert bound <= declared, sorted(bound - declared)
+    missing = {s for s in declared - bound if "_debug_" not in s}
+    assert not missing, sorted(missing)
+
+
+def test_product_does_not_reference_oracle():
+    """The oracle is test infrastructure: nothing under the package, include/ or ffi/ may import, link or
+    load it (a product path through the oracle, or any CPU fallback, would void every parity claim)."""
+    bad = []
+    for top in ("orion-sdr_b200", "include", "ffi"):
+        for d, _, files in os.walk(os.path.join(ROOT, top)):
+            if os.sep + "build" in d or os.sep + "lib" in d[len(ROOT):] and d.endswith("lib") or "variants" in d or "__pycache__" in d:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".rs", ".toml", "Makefile")):
+                    txt = open(os.path.join(d, f), errors="ignore").read()
+                    if re.search(r"\boracle\b|orion_oracle|np_oracle", txt):
+                        bad.append(os.path.join(d, f))
+    assert not bad, bad
