@@ -33,6 +33,20 @@ namespace orion {
 #define DEV __device__ __forceinline__
 #define FULLMASK 0xffffffffu
 
+// Shape specialisation.  SP = 0 keeps every staged-geometry value a launch argument; SP = 1 fixes the geometry
+// of the decimate-by-8, <= 64-tap shape (C1 / C3: Mb = 8, one halo row, 8 tap steps, 528-byte rows), so the FIR
+// loops unroll and every shared-memory offset folds into the instruction.
+template <int SP> struct Geo { static constexpr bool fixed = false; static constexpr int Mb = 0, HR = 0, P_pad = 0, pitch = 0; };
+template <> struct Geo<1> { static constexpr bool fixed = true; static constexpr int Mb = 8, HR = 1, P_pad = 8, pitch = 528; };
+// Demodulator specialisation.  DM = -1: demodulator kind and section structure are launch arguments;
+// DM = DEMOD_NONE (0): C32 out, no sections; DM = DM_FM_LR4: FM discriminator followed by exactly one group of
+// two biquads (the LR4 of fm.rs:27) and nothing else -- the C1 chain.
+constexpr int DM_FM_LR4 = 100;
+template <int DM> struct Dm {
+    static constexpr bool fixed = DM >= 0;
+    static DEV int demod(const ChainArgs &a) { return DM < 0 ? a.demod : (DM == DM_FM_LR4 ? (int)DEMOD_FM : DM); }
+};
+
 // ----------------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------------
@@ -399,14 +413,14 @@ DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
 
 // pass 2 of one section over this lane's items (section by section == sample by sample for a
 // cascade); writes the carried state when this lane owns the last item of the call
-template <int TYPE, int NPT>
+template <int TYPE, int NPT, bool NOPOST = false>
 DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT], float &s0, float &s1,
                    long long jt, bool full) {
     if (full) {
 #pragma unroll
         for (int i = 0; i < NPT; ++i) {
             const float y = sec_step_t<TYPE>(P, u[i], s0, s1);
-            u[i] = (P.post_op == OP_NONE) ? y : post_apply(P, y);
+            u[i] = (NOPOST || P.post_op == OP_NONE) ? y : post_apply(P, y);
         }
         if (jt + NPT == a.n_out) a.carry_out->sec[s] = make_float2(s0, s1);
     } else {
@@ -466,7 +480,7 @@ DEV void group_front(const ChainArgs &a, const Hot *hot, int g, long long tile, 
 }
 
 // group finish: look-back, true start state of this lane's chunk, the reference recursion
-template <int D, int NPT>
+template <int D, int NPT, bool ALLBIQ = false>
 DEV void group_finish(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&u)[NPT], bool full, long long jt,
                       const float (&X)[D], const float (&agg)[D]) {
     const GroupParam &G = hot->grp[g];
@@ -491,7 +505,7 @@ DEV void group_finish(const ChainArgs &a, const Hot *hot, int g, long long tile,
     for (int q = 0; q < D / 2; ++q) {
         const int s = G.first + q;
         const SecParam &P = hot->sec[s];
-        if (P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
+        if (ALLBIQ || P.type == SEC_BIQUAD) sec_pass2<SEC_BIQUAD, NPT, ALLBIQ>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
         else if (P.type == SEC_DC) sec_pass2<SEC_DC, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
         else sec_pass2<SEC_ONEPOLE, NPT>(a, P, s, u, st[2 * q], st[2 * q + 1], jt, full);
     }
@@ -651,18 +665,21 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 #endif
 
 #if ORION_FIR_PACKED
-template <int R, int U>
+template <int R, int U, int SP>
 DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
+    typedef Geo<SP> GE;
     f32x2 acc[U][R];                                 // (re, im) of every output, one packed register pair each
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int i = 0; i < R; ++i) acc[u][i] = pack2(0.f, 0.f);
 
-    const int Mb = a.Mb, pitch = a.row_pitch, P_pad = a.P_pad, HR = a.HR;
+    const int Mb = GE::fixed ? GE::Mb : a.Mb, pitch = GE::fixed ? GE::pitch : a.row_pitch;
+    const int P_pad = GE::fixed ? GE::P_pad : a.P_pad, HR = GE::fixed ? GE::HR : a.HR;
     const int blk_bytes = Mb * 8;
     const unsigned char *row_own = smem + (size_t)lane * pitch;
     const int npairs = Mb >> 1;
+#pragma unroll (GE::fixed ? 4 : 1)
     for (int q = 0; q < npairs; ++q) {
         const int off_q = (Mb - 2 - 2 * q) * 8;
         // sliding window of sample pairs (x[s], x[s+1]), each sample a packed (re, im) pair:
@@ -711,7 +728,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
 }
 
 #else
-template <int R, int U>
+template <int R, int U, int SP>
 DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
     float2 acc[U][R];
 #pragma unroll
@@ -816,21 +833,22 @@ DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, const f
 // after the front: demod-rate oscillator + demodulator front map  (z -> u), C32 store for
 // DEMOD_NONE, end-of-call duties
 // ----------------------------------------------------------------------------------------------
-template <int NPT>
+template <int NPT, int DM>
 DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo) {
     const long long j0 = tile * (long long)(kThreads * NPT);
     const long long jt = j0 + (long long)lane * NPT;
-    const bool is_c32_in = a.demod != DEMOD_F32;
-    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
-    const bool post_osc = (a.demod == DEMOD_FM && a.translate) || a.demod == DEMOD_SSB || a.demod == DEMOD_USB;
+    const int demod = Dm<DM>::demod(a);
+    const bool is_c32_in = demod != DEMOD_F32;
+    const bool need_prev = demod == DEMOD_FM || demod == DEMOD_PM;
+    const bool post_osc = (demod == DEMOD_FM && a.translate) || demod == DEMOD_SSB || demod == DEMOD_USB;
     const bool full = jt + NPT <= a.n_out;
 
-    if (is_c32_in && a.demod != DEMOD_NONE) {
+    if (is_c32_in && demod != DEMOD_NONE) {
         float2 p = make_float2(1.f, 0.f);
         const float2 w = make_float2(a.post.wre, a.post.wim);
         const unsigned long long kp0 = a.post.kbase + (unsigned long long)jt + 1ull;
         if (post_osc) p = nco_unit(a.post, kp0);
-        if (a.demod == DEMOD_FM && a.translate) {
+        if (demod == DEMOD_FM && a.translate) {
             // z = in * conj(p)   (num-complex Mul, unfused; fm.rs:49)
 #pragma unroll
             for (int i = 0; i < NPT; ++i) {
@@ -858,7 +876,7 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
                     if (jt + i == a.n_out - 1) last = z[i];
                 a.carry_out->prev = last;
             }
-            if (a.demod == DEMOD_FM) {
+            if (demod == DEMOD_FM) {
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) {             // fm.rs:50-56
                     const float pr = z[i].x * prev.x + z[i].y * prev.y;
@@ -876,26 +894,26 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
                     prev = z[i];
                 }
             }
-        } else if (a.demod == DEMOD_AM) {
+        } else if (demod == DEMOD_AM) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u[i] = fmaf(z[i].x, z[i].x, z[i].y * z[i].y);          // am.rs:53
-        } else if (a.demod == DEMOD_AM_ABS) {
+        } else if (demod == DEMOD_AM_ABS) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u[i] = fmaf(a.k1, fabsf(z[i].x), a.k2 * fabsf(z[i].y)); // am.rs:86
-        } else if (a.demod == DEMOD_SSB || a.demod == DEMOD_USB) {
+        } else if (demod == DEMOD_SSB || demod == DEMOD_USB) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) {                                                      // ssb.rs:36-37
                 const float2 pa = scale2(p, nco_amp(a.post, kp0 + i));
                 u[i] = fmaf(z[i].x, pa.x, z[i].y * pa.y);
                 p = cmul_fma(p, w);
             }
-        } else if (a.demod == DEMOD_CW) {
+        } else if (demod == DEMOD_CW) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u[i] = sqrtf(z[i].x * z[i].x + z[i].y * z[i].y);        // cw.rs:37
         }
     }
 
-    if (a.demod == DEMOD_NONE) {
+    if (demod == DEMOD_NONE) {
         float2 *out = reinterpret_cast<float2 *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
         if (al16 && full) {
@@ -941,6 +959,26 @@ DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u
         for (int i = 0; i < NPT; ++i)
             if (jt + i < a.n_out) out[jt + i] = u[i];
     }
+}
+
+// DM_FM_LR4: the one group is known to be two biquads (D = 4) -- no dispatch, no section-type tests
+template <int NPT>
+DEV void lr4_front_park(const ChainArgs &a, const Hot *hot, long long tile, int lane, const float (&u)[NPT], bool full, float *park) {
+    float X[4], agg[4];
+    group_front<4, NPT>(a, hot, 0, tile, lane, u, full, X, agg);
+    *reinterpret_cast<float4 *>(park + lane * kMaxGroupDim) = make_float4(X[0], X[1], X[2], X[3]);
+    if (lane == 0) *reinterpret_cast<float4 *>(park + 32 * kMaxGroupDim) = make_float4(agg[0], agg[1], agg[2], agg[3]);
+    __syncwarp();
+}
+template <int NPT>
+DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&u)[NPT], const float *park) {
+    const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
+    const bool full = jt + NPT <= a.n_out;
+    const float4 xv = *reinterpret_cast<const float4 *>(park + lane * kMaxGroupDim);
+    const float4 av = *reinterpret_cast<const float4 *>(park + 32 * kMaxGroupDim);
+    const float X[4] = { xv.x, xv.y, xv.z, xv.w }, agg[4] = { av.x, av.y, av.z, av.w };
+    group_finish<4, NPT, true>(a, hot, 0, tile, lane, u, full, jt, X, agg);
+    store_f32<NPT>(a, tile, lane, u);
 }
 
 // the section phase of a tile whose group-0 front ran one loop iteration earlier (state parked in
@@ -1028,17 +1066,20 @@ struct __align__(16) RingCtl {
 //   * no deadlock by construction: the oldest unfinished tile of the stream is either in a warp's
 //     hands, and that warp never waits on a younger tile, or next in line at its CTA, whose warps
 //     all hold older tiles that wait on still older, finished ones.
-template <int FRONT, int R, int U>
+template <int FRONT, int R, int U, int SP, int DM>
 __global__ void __launch_bounds__(kThreads * kMaxWarpsPerCta, 1)
 chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int NPT = R * U;
+    typedef Geo<SP> GE;
+    const int HRc = GE::fixed ? GE::HR : a.HR;
+    const int demod = Dm<DM>::demod(a);
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ RingCtl ring;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int NW = blockDim.x >> 5;
     const int NS = a.nstages;
     const long long G = gridDim.x, cta = blockIdx.x;
-    const size_t stage_bytes = (size_t)(kThreads + a.HR) * a.row_pitch;      // bytes one TMA load delivers
+    const size_t stage_bytes = (size_t)(kThreads + HRc) * (GE::fixed ? GE::pitch : a.row_pitch);      // bytes one TMA load delivers
     const size_t stage_stride = (stage_bytes + 127) & ~(size_t)127;          // TMA destinations are 128-byte aligned
     // group-0 scan state of the two tiles a warp has in flight: behind the stage ring in dynamic smem
     float (*park)[33 * kMaxGroupDim] = reinterpret_cast<float (*)[33 * kMaxGroupDim]>(
@@ -1063,8 +1104,8 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         for (int i = threadIdx.x; i < n_sec; i += blockDim.x) dst_s[i] = src_s[i];
     }
 
-    const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
-    const bool has_sections = a.demod != DEMOD_NONE;
+    const bool need_prev = demod == DEMOD_FM || demod == DEMOD_PM;
+    const bool has_sections = demod != DEMOD_NONE;
     if ((ORION_TRACE && a.trace) && threadIdx.x == 0) {                  // debug: kernel span in %globaltimer ns
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -1090,7 +1131,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         st_shared_volatile_pred(pred, smem_u32(&ring.gen[s]), k);        // before the arrive below (release)
         if (tile_is_interior(a, t)) {                                     // warp-uniform
             tma_fill_pred(pred, smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
-                          (int)(t * kThreads - a.HR - a.tma_row0), bar, (uint32_t)stage_bytes);
+                          (int)(t * kThreads - HRc - a.tma_row0), bar, (uint32_t)stage_bytes);
         } else {
             mbar_arrive_pred(pred, bar);
         }
@@ -1126,16 +1167,20 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             s = (int)(c % (unsigned)NS);
             k = (int)(c / (unsigned)NS);
             const uint32_t bar = smem_u32(&ring.full[s]);
+            // Use k of the slot waits for fill k: first on the mbarrier phase (a hardware-suspended wait, no
+            // polling traffic), then ONE look at the fill index -- a warp more than one lap ahead of the
+            // slot's current user sees the phase of fill k-2 as complete (the parity is one bit), finds the
+            // index short, and only then falls back to a sleeping poll until fill k is announced.
             int spins = 0;
-            // use k of the slot looks at fill k only: a fast warp may be more than one lap ahead of
-            // the slot's current user, and the mbarrier parity alone cannot tell fill k from fill k-2
-            while (*reinterpret_cast<volatile int *>(&ring.gen[s]) != k) {
-                if (++spins > (1 << 24)) { atomicExch(a.err_flag, 3); break; }
-                __nanosleep(20);
-            }
-            spins = 0;
-            while (!mbar_try_wait(bar, (unsigned)k & 1u)) {
-                if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+            for (;;) {
+                while (!mbar_try_wait(bar, (unsigned)k & 1u)) {
+                    if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+                }
+                if (*reinterpret_cast<volatile int *>(&ring.gen[s]) == k || spins > (1 << 22)) break;
+                while (*reinterpret_cast<volatile int *>(&ring.gen[s]) != k) {
+                    if (++spins > (1 << 22)) { atomicExch(a.err_flag, 3); break; }
+                    __nanosleep(64);
+                }
             }
             stage = smem + (size_t)s * stage_stride;
         }
@@ -1152,8 +1197,8 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         if (FRONT == FRONT_STAGED) {
             if (!tile_is_interior(a, tile)) stage_load_generic(a, tile, stage, lane);
             if (a.mix != MIX_NONE) stage_mix(a, tile, stage, lane);
-            fir_staged<R, U>(a, stage, taps_sh, lane, z);
-            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, g_sh, tile * kThreads - a.HR, j0 - 1, lane);
+            fir_staged<R, U, SP>(a, stage, taps_sh, lane, z);
+            if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, g_sh, tile * kThreads - HRc, j0 - 1, lane);
             __syncwarp();                               // every lane is done with the slot: refill it
             stamp(tile, 2);
             fill_slot(s, k + 1);
@@ -1166,7 +1211,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         } else {
             front_direct<NPT>(a, tile, lane, z, u, zhalo);
         }
-        front_map<NPT>(a, tile, lane, z, u, zhalo);
+        front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
         if ((ORION_TRACE && a.trace) && lane == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1176,16 +1221,24 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             if (!has_sections) a.trace[tile * 16 + 3] = clock64();
         }
         if (has_sections) {
-            if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
+            if (DM == DM_FM_LR4) lr4_front_park<NPT>(a, hot, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
+            else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
             stamp(tile, 3);
-            if (pend_tile >= 0) { finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]); stamp(pend_tile, 4); }
+            if (pend_tile >= 0) {
+                if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                stamp(pend_tile, 4);
+            }
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u_pend[i] = u[i];
             pend_tile = tile;
             slot_pp ^= 1;
         }
     }
-    if (pend_tile >= 0) finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+    if (pend_tile >= 0) {
+        if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+        else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+    }
     if ((ORION_TRACE && a.trace) && lane == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -1198,12 +1251,19 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
 // ----------------------------------------------------------------------------------------------
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 
-template <int FRONT, int R, int U>
-static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U>; }
+template <int FRONT, int R, int U, int SP = 0, int DM = -1>
+static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM>; }
 
-chain_kernel_t select_kernel(int front, int R, int U) {
+// sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, DEMOD_NONE, DM_FM_LR4
+chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
     if (front == FRONT_DIRECT) return kptr<FRONT_DIRECT, 16, 1>();
     if (front == FRONT_GLOBAL) return kptr<FRONT_GLOBAL, 8, 1>();
+    if (sp == 1 && R == 8 && U == 1) {
+        if (dm == DEMOD_NONE) return kptr<FRONT_STAGED, 8, 1, 1, DEMOD_NONE>();
+        if (dm == DM_FM_LR4) return kptr<FRONT_STAGED, 8, 1, 1, DM_FM_LR4>();
+        return kptr<FRONT_STAGED, 8, 1, 1, -1>();
+    }
+#ifndef ORION_ONLY_HOT_SHAPES
     if (U == 1) {
         switch (R) {
             case 8: return kptr<FRONT_STAGED, 8, 1>();
@@ -1219,6 +1279,7 @@ chain_kernel_t select_kernel(int front, int R, int U) {
             case 1: return kptr<FRONT_STAGED, 1, 2>();
         }
     }
+#endif
     return nullptr;
 }
 

@@ -20,7 +20,7 @@
 
 namespace orion {
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
-chain_kernel_t select_kernel(int front, int R, int U);
+chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm);
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm);
 cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
                                 size_t dyn_smem, cudaStream_t stream);
@@ -444,7 +444,18 @@ int finalize_plan(orion_b200_block *b) {
     CK(cudaSetDevice(b->device));
     if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
-    b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U);
+    // shape / demodulator specialisations of the kernel family (chain_kernels.cu, Geo<SP> and Dm<DM>)
+    int sp = 0, dm = -1;
+    if (b->plan.front == FRONT_STAGED && b->plan.R == 8 && b->plan.U == 1 && b->plan.Mb == 8 && b->plan.HR == 1 &&
+        b->plan.P_pad == 8 && b->plan.row_pitch == 528) {
+        sp = 1;
+        if (b->demod == DEMOD_NONE) dm = DEMOD_NONE;
+        else if (b->demod == DEMOD_FM && b->secs.size() == 2 && b->secs[0].type == SEC_BIQUAD && b->secs[1].type == SEC_BIQUAD &&
+                 b->secs[0].post_op == OP_NONE && b->secs[1].post_op == OP_NONE)
+            dm = 100;                                                   // DM_FM_LR4
+    }
+    if (getenv("ORION_B200_NO_SPECIALIZE")) { sp = 0; dm = -1; }
+    b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
     b->plan.dyn_smem = b->plan.stage_bytes * b->plan.nstages +
                        (size_t)b->plan.warps * 2 * 33 * kMaxGroupDim * sizeof(float) +     // stage ring + park area
