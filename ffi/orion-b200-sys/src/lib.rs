@@ -32,6 +32,10 @@ pub const ORION_B200_DEMOD_USB: i32 = 7;
 pub struct orion_b200_block {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct orion_b200_bank {
+    _private: [u8; 0],
+}
 
 /// `num_complex::Complex32` is `#[repr(C)] { re: f32, im: f32 }`, so `&[Complex32]` can be passed as
 /// `*const orion_b200_c32` without a copy.
@@ -111,6 +115,18 @@ extern "C" {
     pub fn orion_b200_cw_demod_create(sample_rate: f32, tone_hz: f32, env_bw_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_cw_demod_set_gain(b: *mut orion_b200_block, gain: f32) -> c_int;
     pub fn orion_b200_chain_create(spec: *const orion_b200_chain_spec, out: *mut *mut orion_b200_block) -> c_int;
+
+    pub fn orion_b200_bank_create(specs: *const orion_b200_chain_spec, n_channels: usize, out: *mut *mut orion_b200_bank) -> c_int;
+    pub fn orion_b200_bank_destroy(k: *mut orion_b200_bank);
+    pub fn orion_b200_bank_reset(k: *mut orion_b200_bank) -> c_int;
+    pub fn orion_b200_bank_channels(k: *const orion_b200_bank) -> usize;
+    pub fn orion_b200_bank_last_error(k: *const orion_b200_bank) -> *const c_char;
+    pub fn orion_b200_bank_process(k: *mut orion_b200_bank, input: *const c_void, n_in: usize, output: *mut c_void,
+                                   out_stride: usize, in_read: *mut usize, out_written: *mut usize) -> c_int;
+    pub fn orion_b200_bank_process_dev(k: *mut orion_b200_bank, d_in: *const c_void, n_in: usize, d_out: *mut c_void,
+                                       out_stride: usize, in_read: *mut usize, out_written: *mut usize) -> c_int;
+    pub fn orion_b200_bank_synchronize(k: *mut orion_b200_bank) -> c_int;
+    pub fn orion_b200_bank_launch_count(k: *const orion_b200_bank) -> u64;
 
     pub fn orion_b200_block_destroy(b: *mut orion_b200_block);
     pub fn orion_b200_block_reset(b: *mut orion_b200_block) -> c_int;

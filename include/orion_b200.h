@@ -182,6 +182,30 @@ typedef struct orion_b200_chain_spec {
 int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block **out);
 
 /* ------------------------------------------------------------------------------------
+ * Channel bank: C independent narrowband chains fed by ONE wideband input (BASELINE config 5).
+ * Channel c is exactly the block `orion_b200_chain_create(&specs[c])` would build -- typically
+ * Rotator(-f_c).rotate_block -> FirDecimator -> FM/AM demod -- with its own streaming state, i.e. what the
+ * reference does today with C separate Block chains run one after another over the same input slice.
+ * All channels must share the input item type, the decimation factor and the output item type.  Output is
+ * row-major [channel][out_stride] items.  Channels are independent, so a bank over a channel sub-range
+ * is how the workload is sharded across GPUs (one bank per process / GPU, no collective).
+ * ---------------------------------------------------------------------------------- */
+typedef struct orion_b200_bank orion_b200_bank;
+int    orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels, orion_b200_bank **out);
+void   orion_b200_bank_destroy(orion_b200_bank *k);
+int    orion_b200_bank_reset(orion_b200_bank *k);
+size_t orion_b200_bank_channels(const orion_b200_bank *k);                         /* [host-only] */
+const char *orion_b200_bank_last_error(const orion_b200_bank *k);                  /* [host-only] */
+/* host pointers: H2D of the wideband slice once, C kernel launches, one D2H of the [C][out_stride] block */
+int orion_b200_bank_process(orion_b200_bank *k, const void *in, size_t n_in, void *out, size_t out_stride,
+                            size_t *in_read, size_t *out_written);
+/* device pointers; asynchronous on the bank's streams */
+int orion_b200_bank_process_dev(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
+                                size_t *in_read, size_t *out_written);
+int orion_b200_bank_synchronize(orion_b200_bank *k);
+uint64_t orion_b200_bank_launch_count(const orion_b200_bank *k);                   /* [host-only] */
+
+/* ------------------------------------------------------------------------------------
  * Common block operations
  * ---------------------------------------------------------------------------------- */
 void        orion_b200_block_destroy(orion_b200_block *b);

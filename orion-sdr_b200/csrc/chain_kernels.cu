@@ -435,6 +435,8 @@ DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT]
     }
 }
 
+template <int D>
+DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&E)[D], float (&X)[D], float (&agg)[D]);
 // group front: zero-state end state of this lane's chunk (dot products with the impulse
 // responses), warp scan with constant transition powers, publish the tile aggregate.
 // X = state contribution of the lanes before this one; agg = whole-tile aggregate.
@@ -452,6 +454,12 @@ DEV void group_front(const ChainArgs &a, const Hot *hot, int g, long long tile, 
 #pragma unroll
             for (int d = 0; d < D; ++d) E[d] = fmaf(G.imp[i][d], u[i], E[d]);
     }
+    group_scan<D>(a, hot, g, tile, lane, E, X, agg);
+}
+// warp scan of the lanes' zero-state end states E with constant transition powers; publishes the tile aggregate
+template <int D>
+DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&E)[D], float (&X)[D], float (&agg)[D]) {
+    const GroupParam &G = hot->grp[g];
     if ((ORION_TRACE && a.trace) && g == 0) {
         const unsigned am = __activemask();
         if (lane == 0) { a.trace[tile * 16 + 11] = clock64(); a.trace[tile * 16 + 14] = am; }
@@ -679,7 +687,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
     const int blk_bytes = Mb * 8;
     const unsigned char *row_own = smem + (size_t)lane * pitch;
     const int npairs = Mb >> 1;
-#pragma unroll (GE::fixed ? 4 : 1)
+#pragma unroll 1
     for (int q = 0; q < npairs; ++q) {
         const int off_q = (Mb - 2 - 2 * q) * 8;
         // sliding window of sample pairs (x[s], x[s+1]), each sample a packed (re, im) pair:
@@ -851,14 +859,15 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         if (demod == DEMOD_FM && a.translate) {
             // z = in * conj(p)   (num-complex Mul, unfused; fm.rs:49)
 #pragma unroll
+            // the unit phasor is enough: |p| = 1 + O(1e-5) (rotator.rs renormalises every 1024 steps) scales
+            // both discriminator arguments alike, and atan2_approx only sees their ratio
             for (int i = 0; i < NPT; ++i) {
-                const float am = nco_amp(a.post, kp0 + i);
-                const float cr = p.x * am, ci = -(p.y * am);
+                const float cr = p.x, ci = -p.y;
                 z[i] = make_float2(z[i].x * cr - z[i].y * ci, z[i].x * ci + z[i].y * cr);
                 p = cmul_fma(p, w);
             }
             if (j0 > 0 && lane == 0) {
-                const float2 ph = nco_phasor(a.post, a.post.kbase + (unsigned long long)j0);
+                const float2 ph = nco_unit(a.post, a.post.kbase + (unsigned long long)j0);
                 const float cr = ph.x, ci = -ph.y;
                 zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
             }
@@ -961,23 +970,152 @@ DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u
     }
 }
 
-// DM_FM_LR4: the one group is known to be two biquads (D = 4) -- no dispatch, no section-type tests
+// DM_FM_LR4: the one group is known to be two biquads (D = 4, sections 0 and 1) -- no dispatch, no section-type
+// tests, section coefficients at compile-time offsets of the parameter bank, scan tables in shared memory.
+struct Lr4Tabs {                                   // shared-memory copy of GroupTables::lane / ::lb of group 0
+    float lane[32][16];
+    float lb[32][16];
+    float imp[kMaxNpt][4];                         // ... and of GroupParam::imp (indexed at run time by the rolled front loop)
+};
+DEV void load_mat4_sh(const float *m, float (&M)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(m + i);
+        M[i] = v.x; M[i + 1] = v.y; M[i + 2] = v.z; M[i + 3] = v.w;
+    }
+}
+// The FM front of one lane as ONE rolled loop over its NPT items: translate (fm.rs:49), conj-product discriminator
+// (fm.rs:50-56), atan2_approx, the group's zero-state dot product.  The item arrays rotate through registers
+// (z[0] is always the current item, the new u enters at the top), so the loop body exists once in the
+// instruction cache instead of NPT times -- the kernel is instruction-fetch bound, not issue bound.
 template <int NPT>
-DEV void lr4_front_park(const ChainArgs &a, const Hot *hot, long long tile, int lane, const float (&u)[NPT], bool full, float *park) {
+DEV void fm_front_rolled(const ChainArgs &a, const Lr4Tabs *tabs, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT],
+                         float2 zhalo, float (&E)[4]) {
+    const long long j0 = tile * (long long)(kThreads * NPT);
+    const long long jt = j0 + (long long)lane * NPT;
+    const bool xlate = a.translate != 0;
+    const float2 w = make_float2(a.post.wre, a.post.wim);
+    float2 p = make_float2(1.f, 0.f);
+    if (xlate) {
+        p = nco_unit(a.post, a.post.kbase + (unsigned long long)jt + 1ull);
+        if (j0 > 0 && lane == 0) {
+            const float2 ph = nco_unit(a.post, a.post.kbase + (unsigned long long)j0);
+            const float cr = ph.x, ci = -ph.y;
+            zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
+        }
+        __syncwarp();
+    }
+    // previous item of the lane's first one: the neighbour lane's last item, translated there
+    float2 zl = z[NPT - 1];
+    if (xlate) {
+        const float2 pl = nco_unit(a.post, a.post.kbase + (unsigned long long)jt + (unsigned long long)NPT);
+        const float cr = pl.x, ci = -pl.y;
+        zl = make_float2(zl.x * cr - zl.y * ci, zl.x * ci + zl.y * cr);
+    }
+    float2 prev = shfl_up2(zl, 1);
+    if (lane == 0) prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+    __syncwarp();
+    const int last = (int)max(min(a.n_out - 1 - jt, (long long)NPT), -1ll);      // item of this lane that ends the call
+#pragma unroll
+    for (int d = 0; d < 4; ++d) E[d] = 0.f;
+#pragma unroll 1
+    for (int it = 0; it < NPT; ++it) {
+        float2 zz = z[0];
+        if (xlate) {
+            const float cr = p.x, ci = -p.y;
+            zz = make_float2(zz.x * cr - zz.y * ci, zz.x * ci + zz.y * cr);
+            p = cmul_fma(p, w);
+        }
+        const float pr = zz.x * prev.x + zz.y * prev.y;
+        const float pi = zz.y * prev.x - zz.x * prev.y;
+        const float uu = atan2_approx(pi, pr) * a.k;
+        prev = zz;
+        if (it == last) a.carry_out->prev = zz;
+        const float4 im = *reinterpret_cast<const float4 *>(tabs->imp[it]);
+        E[0] = fmaf(im.x, uu, E[0]); E[1] = fmaf(im.y, uu, E[1]); E[2] = fmaf(im.z, uu, E[2]); E[3] = fmaf(im.w, uu, E[3]);
+#pragma unroll
+        for (int i = 0; i + 1 < NPT; ++i) { z[i] = z[i + 1]; u[i] = u[i + 1]; }
+        u[NPT - 1] = uu;
+    }
+}
+template <int NPT>
+DEV void lr4_front_park(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&E)[4], float *park) {
     float X[4], agg[4];
-    group_front<4, NPT>(a, hot, 0, tile, lane, u, full, X, agg);
+    __syncwarp();
+    group_scan<4>(a, hot, 0, tile, lane, E, X, agg);
     *reinterpret_cast<float4 *>(park + lane * kMaxGroupDim) = make_float4(X[0], X[1], X[2], X[3]);
     if (lane == 0) *reinterpret_cast<float4 *>(park + 32 * kMaxGroupDim) = make_float4(agg[0], agg[1], agg[2], agg[3]);
     __syncwarp();
 }
+// Look-back when every predecessor weight beyond `depth` (<= 32) tiles is exactly zero: lane l reads the
+// aggregate of tile - 1 - l (published a whole loop iteration ago), weighs it with Ac^(T*l), one warp sum.
+DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long tile, int lane, int depth, float (&sin)[4]) {
+    const long long idx = tile - 1 - lane;
+    float pay[4] = { 0.f, 0.f, 0.f, 0.f };
+    const bool want = lane < depth && idx >= -1;
+    if (want) {
+        if (idx < 0) {                              // the state carried into this call sits "before tile 0"
+            const float2 c0 = a.carry_in->sec[0], c1 = a.carry_in->sec[1];
+            pay[0] = c0.x; pay[1] = c0.y; pay[2] = c1.x; pay[3] = c1.y;
+        } else {
+            const TileLink *lk = a.links + idx * kMaxGroups;
+            int spins = 0;
+            while (!read_link<4>(lk->agg, a.epoch, pay)) {
+                if (++spins > (1 << 21)) { atomicExch(a.err_flag, 1); break; }    // watchdog: never hang the device
+                __nanosleep(32);
+            }
+        }
+    }
+    __syncwarp();
+    float term[4] = { 0.f, 0.f, 0.f, 0.f };
+    if (want) {
+        float m[16];
+        load_mat4_sh(tabs->lb[lane], m);
+        matvec<4>(m, pay, term);
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        float v = term[d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+        sin[d] = v;
+    }
+}
 template <int NPT>
-DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&u)[NPT], const float *park) {
+DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *tabs, long long tile, int lane, float (&u)[NPT],
+                           const float *park) {
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
-    const bool full = jt + NPT <= a.n_out;
     const float4 xv = *reinterpret_cast<const float4 *>(park + lane * kMaxGroupDim);
-    const float4 av = *reinterpret_cast<const float4 *>(park + 32 * kMaxGroupDim);
-    const float X[4] = { xv.x, xv.y, xv.z, xv.w }, agg[4] = { av.x, av.y, av.z, av.w };
-    group_finish<4, NPT, true>(a, hot, 0, tile, lane, u, full, jt, X, agg);
+    float sin[4];
+    const GroupParam &G = hot->grp[0];
+    if (G.agg_only) {
+        lr4_lookback_short(a, tabs, tile, lane, __ldg(&a.gtabs->depth), sin);
+    } else {                                       // slow poles: the general chained look-back, inclusive values published
+        const float4 av = *reinterpret_cast<const float4 *>(park + 32 * kMaxGroupDim);
+        lookback<4>(a, hot, 0, tile, lane, sin);
+        float tm[16], inc[4];
+        load_mat<4>(a.gtabs->tile, tm);
+        matvec<4>(tm, sin, inc);
+        inc[0] += av.x; inc[1] += av.y; inc[2] += av.z; inc[3] += av.w;
+        publish<4>(lane == 0, a, tile, 0, inc, true);
+    }
+    float lm[16], st[4];
+    load_mat4_sh(tabs->lane[lane], lm);
+    matvec<4>(lm, sin, st);
+    st[0] += xv.x; st[1] += xv.y; st[2] += xv.z; st[3] += xv.w;
+    // the reference recursion, sample by sample through both sections (iir.rs:78-83); items past the end of the
+    // call are computed from zero-padded input and never stored, the carried state is taken at the last real one
+    const SecParam &P0 = hot->sec[0], &P1 = hot->sec[1];
+    const long long last = a.n_out - 1 - jt;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+        const float y = sec_step_t<SEC_BIQUAD>(P0, u[i], st[0], st[1]);
+        u[i] = sec_step_t<SEC_BIQUAD>(P1, y, st[2], st[3]);
+        if (last == i) {
+            a.carry_out->sec[0] = make_float2(st[0], st[1]);
+            a.carry_out->sec[1] = make_float2(st[2], st[3]);
+        }
+    }
     store_f32<NPT>(a, tile, lane, u);
 }
 
@@ -1092,6 +1230,16 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     Hot *hot_sh = reinterpret_cast<Hot *>(reinterpret_cast<unsigned char *>(g_sh) + (((size_t)a.Lg * sizeof(float) + 15) & ~(size_t)15));
     // Hot's layout equals ChainArgs::grp followed by ChainArgs::sec (static_assert below)
     const Hot *hot = ORION_HOT_SMEM ? hot_sh : reinterpret_cast<const Hot *>(a.grp);
+    // DM_FM_LR4: per-lane scan tables of the one group, behind the section data
+    Lr4Tabs *tabs_sh = reinterpret_cast<Lr4Tabs *>(reinterpret_cast<unsigned char *>(hot_sh) + ((sizeof(Hot) + 15) & ~(size_t)15));
+    if (DM == DM_FM_LR4) {
+        const float *src_l = &a.gtabs->lane[0][0], *src_b = &a.gtabs->lb[0][0];
+        for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
+            (&tabs_sh->lane[0][0])[i] = __ldg(src_l + i);
+            (&tabs_sh->lb[0][0])[i] = __ldg(src_b + i);
+        }
+        for (int i = threadIdx.x; i < kMaxNpt * 4; i += blockDim.x) (&tabs_sh->imp[0][0])[i] = a.grp[0].imp[i >> 2][i & 3];
+    }
     if (FRONT == FRONT_STAGED) {
         for (int i = threadIdx.x; i < a.ntaps2; i += blockDim.x) taps_sh[i] = a.taps2[i];
         for (int i = threadIdx.x; i < a.Lg; i += blockDim.x) g_sh[i] = __ldg(a.g + i);
@@ -1211,7 +1359,9 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         } else {
             front_direct<NPT>(a, tile, lane, z, u, zhalo);
         }
-        front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
+        float E4[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (DM == DM_FM_LR4) fm_front_rolled<NPT>(a, tabs_sh, tile, lane, z, u, zhalo, E4);
+        else front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
         if ((ORION_TRACE && a.trace) && lane == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1221,11 +1371,11 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             if (!has_sections) a.trace[tile * 16 + 3] = clock64();
         }
         if (has_sections) {
-            if (DM == DM_FM_LR4) lr4_front_park<NPT>(a, hot, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
+            if (DM == DM_FM_LR4) lr4_front_park<NPT>(a, hot, tile, lane, E4, park[slot_pp]);
             else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
             stamp(tile, 3);
             if (pend_tile >= 0) {
-                if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
                 else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
                 stamp(pend_tile, 4);
             }
@@ -1236,7 +1386,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         }
     }
     if (pend_tile >= 0) {
-        if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+        if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
         else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
     }
     if ((ORION_TRACE && a.trace) && lane == 0) {

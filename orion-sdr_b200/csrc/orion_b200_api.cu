@@ -415,6 +415,7 @@ struct orion_b200_block {
     unsigned epoch = 0;
     int *d_err = nullptr;
     int *h_err = nullptr;                 // pinned
+    int *d_err_ext = nullptr;             // a channel bank's shared watchdog word (not owned)
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
     // ---- counters ----
@@ -461,7 +462,8 @@ int finalize_plan(orion_b200_block *b) {
                        (size_t)b->plan.warps * 2 * 33 * kMaxGroupDim * sizeof(float) +     // stage ring + park area
                        b->plan.taps2.size() * sizeof(float2) +                              // + tap table
                        ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +            // + generic taps
-                       sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 16;  // + section/group data
+                       sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
+                       (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float);                               // + per-lane scan tables (LR4 instance)
     CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, b->plan.warps, &b->ctas_per_sm));
     if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
     // FIR taps + history
@@ -645,7 +647,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
     a.links = b->d_links;
-    a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err;
+    a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err_ext ? b->d_err_ext : b->d_err;
     a.trace = b->trace;
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
     a.ntaps2 = (int)b->plan.taps2.size();
@@ -979,6 +981,154 @@ int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block 
         for (size_t s = 0; s < spec->n_post; ++s) b->secs.push_back(sec_biquad(spec->post_sos + 5 * s));
     }
     return finish_create(b, out);
+}
+
+// ---- channel bank --------------------------------------------------------------------------------
+struct orion_b200_bank {
+    std::vector<orion_b200_block *> ch;
+    std::vector<cudaStream_t> streams;
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_done;
+    int device = 0;
+    void *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    int *d_err = nullptr, *h_err = nullptr;       // one watchdog word for all channels
+    std::string err;
+};
+namespace {
+const int kBankStreams = 8;
+int bank_fail(orion_b200_bank *k, int st, const std::string &what) { if (k) k->err = what; return st; }
+int bank_launch_all(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
+                    size_t *in_read, size_t *out_written) {
+    const size_t ob = out_item_bytes(k->ch[0]);
+    size_t r = 0, w = 0;
+    for (size_t c = 0; c < k->ch.size(); ++c) {
+        const int st = orion_b200_block_process_dev(k->ch[c], d_in, n_in, (char *)d_out + c * out_stride * ob, out_stride, &r, &w);
+        if (st != ORION_B200_OK) return bank_fail(k, st, "channel " + std::to_string(c) + ": " + k->ch[c]->err);
+    }
+    if (in_read) *in_read = r;
+    if (out_written) *out_written = w;
+    return ORION_B200_OK;
+}
+}  // namespace
+
+int orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels, orion_b200_bank **out) {
+    if (!out) return ORION_B200_ERR_INVALID;
+    *out = nullptr;
+    if (!specs || n_channels == 0) return ORION_B200_ERR_INVALID;
+    orion_b200_bank *k = new (std::nothrow) orion_b200_bank();
+    if (!k) return ORION_B200_ERR_ALLOC;
+    k->device = t_device;
+    int st = ORION_B200_OK;
+    for (size_t c = 0; c < n_channels && st == ORION_B200_OK; ++c) {
+        orion_b200_block *b = nullptr;
+        st = orion_b200_chain_create(&specs[c], &b);
+        if (st == ORION_B200_OK) {
+            k->ch.push_back(b);
+            if (b->in_item != k->ch[0]->in_item || b->out_item != k->ch[0]->out_item ||
+                orion_b200_block_decimation(b) != orion_b200_block_decimation(k->ch[0]))
+                st = ORION_B200_ERR_UNSUPPORTED;
+        }
+    }
+    if (st == ORION_B200_OK) {
+        cudaSetDevice(k->device);
+        const int ns = (int)std::min<size_t>(kBankStreams, n_channels);
+        k->streams.resize(ns, nullptr);
+        for (int i = 0; i < ns && st == ORION_B200_OK; ++i)
+            if (cudaStreamCreateWithFlags(&k->streams[i], cudaStreamNonBlocking) != cudaSuccess) st = ORION_B200_ERR_CUDA;
+        k->ev_done.resize(ns, nullptr);
+        for (int i = 0; i < ns && st == ORION_B200_OK; ++i)
+            if (cudaEventCreateWithFlags(&k->ev_done[i], cudaEventDisableTiming) != cudaSuccess) st = ORION_B200_ERR_CUDA;
+        if (st == ORION_B200_OK && cudaEventCreateWithFlags(&k->ev_in, cudaEventDisableTiming) != cudaSuccess) st = ORION_B200_ERR_CUDA;
+        if (st == ORION_B200_OK && (cudaMalloc(&k->d_err, sizeof(int)) != cudaSuccess || cudaMemset(k->d_err, 0, sizeof(int)) != cudaSuccess ||
+                                    cudaMallocHost(&k->h_err, sizeof(int)) != cudaSuccess)) st = ORION_B200_ERR_ALLOC;
+        for (size_t c = 0; c < k->ch.size() && st == ORION_B200_OK; ++c) {
+            k->ch[c]->d_err_ext = k->d_err;
+            st = orion_b200_block_set_stream(k->ch[c], (void *)k->streams[c % ns]);
+        }
+    }
+    if (st != ORION_B200_OK) { orion_b200_bank_destroy(k); return st; }
+    *out = k;
+    return ORION_B200_OK;
+}
+void orion_b200_bank_destroy(orion_b200_bank *k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    for (cudaStream_t s : k->streams) if (s) cudaStreamSynchronize(s);
+    for (orion_b200_block *b : k->ch) { if (b) { b->stream = b->own_stream; orion_b200_block_destroy(b); } }
+    for (cudaStream_t s : k->streams) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : k->ev_done) if (e) cudaEventDestroy(e);
+    if (k->ev_in) cudaEventDestroy(k->ev_in);
+    cudaFree(k->d_in); cudaFree(k->d_out); cudaFree(k->d_err);
+    if (k->h_err) cudaFreeHost(k->h_err);
+    cudaGetLastError();
+    delete k;
+}
+int orion_b200_bank_reset(orion_b200_bank *k) {
+    if (!k) return ORION_B200_ERR_INVALID;
+    for (orion_b200_block *b : k->ch) { const int st = reset_state(b); if (st) return bank_fail(k, st, b->err); }
+    return ORION_B200_OK;
+}
+size_t orion_b200_bank_channels(const orion_b200_bank *k) { return k ? k->ch.size() : 0; }
+const char *orion_b200_bank_last_error(const orion_b200_bank *k) { return k ? k->err.c_str() : "null bank"; }
+uint64_t orion_b200_bank_launch_count(const orion_b200_bank *k) {
+    uint64_t n = 0;
+    if (k) for (const orion_b200_block *b : k->ch) n += b->launches;
+    return n;
+}
+int orion_b200_bank_process_dev(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
+                                size_t *in_read, size_t *out_written) {
+    if (in_read) *in_read = 0;
+    if (out_written) *out_written = 0;
+    if (!k || (n_in && !d_in) || (out_stride && !d_out)) return k ? bank_fail(k, ORION_B200_ERR_INVALID, "null buffer") : ORION_B200_ERR_INVALID;
+    if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
+    return bank_launch_all(k, d_in, n_in, d_out, out_stride, in_read, out_written);
+}
+int orion_b200_bank_synchronize(orion_b200_bank *k) {
+    if (!k) return ORION_B200_ERR_INVALID;
+    if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
+    for (cudaStream_t s : k->streams)
+        if (cudaStreamSynchronize(s) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaStreamSynchronize");
+    if (cudaMemcpy(k->h_err, k->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "watchdog read");
+    if (*k->h_err != 0) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "device watchdog tripped (code %d) in a bank channel", *k->h_err);
+        *k->h_err = 0;
+        cudaMemset(k->d_err, 0, sizeof(int));
+        return bank_fail(k, ORION_B200_ERR_INTERNAL, msg);
+    }
+    return ORION_B200_OK;
+}
+int orion_b200_bank_process(orion_b200_bank *k, const void *in, size_t n_in, void *out, size_t out_stride,
+                            size_t *in_read, size_t *out_written) {
+    if (in_read) *in_read = 0;
+    if (out_written) *out_written = 0;
+    if (!k || (n_in && !in) || (out_stride && !out)) return k ? bank_fail(k, ORION_B200_ERR_INVALID, "null buffer") : ORION_B200_ERR_INVALID;
+    if (n_in == 0) return ORION_B200_OK;
+    if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
+    const size_t ib = n_in * in_item_bytes(k->ch[0]);
+    const size_t ob = k->ch.size() * out_stride * out_item_bytes(k->ch[0]);
+    if (ib > k->d_in_cap) {
+        for (cudaStream_t s : k->streams) cudaStreamSynchronize(s);
+        cudaFree(k->d_in); k->d_in = nullptr; k->d_in_cap = 0;
+        if (cudaMalloc(&k->d_in, ib + ib / 4 + 256) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_ALLOC, "bank input");
+        k->d_in_cap = ib + ib / 4 + 256;
+    }
+    if (ob > k->d_out_cap) {
+        for (cudaStream_t s : k->streams) cudaStreamSynchronize(s);
+        cudaFree(k->d_out); k->d_out = nullptr; k->d_out_cap = 0;
+        if (cudaMalloc(&k->d_out, ob + 256) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_ALLOC, "bank output");
+        k->d_out_cap = ob + 256;
+    }
+    // the wideband slice goes up once on stream 0; every other stream waits for it
+    if (cudaMemcpyAsync(k->d_in, in, ib, cudaMemcpyHostToDevice, k->streams[0]) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "H2D");
+    cudaEventRecord(k->ev_in, k->streams[0]);
+    for (size_t i = 1; i < k->streams.size(); ++i) cudaStreamWaitEvent(k->streams[i], k->ev_in, 0);
+    int st = bank_launch_all(k, k->d_in, n_in, k->d_out, out_stride, in_read, out_written);
+    if (st != ORION_B200_OK) return st;
+    for (size_t i = 1; i < k->streams.size(); ++i) { cudaEventRecord(k->ev_done[i], k->streams[i]); cudaStreamWaitEvent(k->streams[0], k->ev_done[i], 0); }
+    if (ob && cudaMemcpyAsync(out, k->d_out, ob, cudaMemcpyDeviceToHost, k->streams[0]) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "D2H");
+    return orion_b200_bank_synchronize(k);
 }
 
 // ---- common operations ---------------------------------------------------------------------------

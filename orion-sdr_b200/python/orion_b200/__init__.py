@@ -124,6 +124,15 @@ def lib():
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
     sig("orion_b200_debug_set_trace", i, vp, vp)
+    sig("orion_b200_bank_create", i, vp, sz, vp)
+    sig("orion_b200_bank_destroy", None, vp)
+    sig("orion_b200_bank_reset", i, vp)
+    sig("orion_b200_bank_channels", sz, vp)
+    sig("orion_b200_bank_last_error", C.c_char_p, vp)
+    sig("orion_b200_bank_process", i, vp, vp, sz, vp, sz, vp, vp)
+    sig("orion_b200_bank_process_dev", i, vp, vp, sz, vp, sz, vp, vp)
+    sig("orion_b200_bank_synchronize", i, vp)
+    sig("orion_b200_bank_launch_count", C.c_uint64, vp)
     sig("orion_b200_debug_fir_plan", sz, i, vp, sz, sz, vp, vp, sz, vp, sz)
     sig("orion_b200_debug_group_tables", sz, vp, sz, i, vp, sz)
     _lib = L
@@ -149,6 +158,9 @@ EXPORTED_SYMBOLS = [
     "orion_b200_block_process_dev", "orion_b200_block_synchronize", "orion_b200_block_set_stream",
     "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
     "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables", "orion_b200_debug_set_trace",
+    "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
+    "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
+    "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
 ]
 
 
@@ -513,6 +525,125 @@ class Chain(Block):
         h = C.c_void_p(0)
         _check(lib().orion_b200_chain_create(C.byref(sp), C.byref(h)))
         super().__init__(h.value)
+
+
+def _fill_spec(sp, keep, *, mix=MIX_NONE, mix_freq_hz=0.0, mix_fs=1.0, fir=FIR_NONE, taps=None, decim=1, demod=DEMOD_NONE,
+               fs_demod=1.0, p0=0.0, p1=0.0, audio_bw_hz=0.0, translate_hz=None, post_sos=None):
+    """Fill one orion_b200_chain_spec; `keep` collects the arrays its pointers refer to."""
+    sp.struct_size = C.sizeof(ChainSpec)
+    sp.mix, sp.mix_freq_hz, sp.mix_fs = mix, mix_freq_hz, mix_fs
+    sp.fir = fir
+    t = _f32(taps) if taps is not None else np.zeros(0, np.float32)
+    sos = _f32(post_sos).reshape(-1, 5) if post_sos is not None else np.zeros((0, 5), np.float32)
+    keep += [t, sos]
+    sp.taps = t.ctypes.data_as(C.POINTER(C.c_float)) if t.size else None
+    sp.ntaps, sp.decim = t.size, int(decim)
+    sp.demod, sp.fs_demod, sp.p0, sp.p1, sp.audio_bw_hz = demod, fs_demod, p0, p1, audio_bw_hz
+    sp.translate = int(translate_hz is not None)
+    sp.translate_hz = float(translate_hz or 0.0)
+    sp.post_sos = sos.ctypes.data_as(C.POINTER(C.c_float)) if sos.size else None
+    sp.n_post = sos.shape[0]
+
+
+# ---- channel bank (BASELINE config 5) and its sharding across processes ---------------------------------
+def shard_range(n_channels: int, rank: int, world: int) -> range:
+    """Channels [g*C/G, (g+1)*C/G) of rank g: contiguous, covers every channel once."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside world")
+    return range(rank * n_channels // world, (rank + 1) * n_channels // world)
+
+
+def gather_channels(local: np.ndarray, n_channels: int, rank: int, world: int, group=None, dst: int = 0):
+    """Host-side gather of the per-rank [local_channels, n_out] outputs into [n_channels, n_out] on `dst`
+    (None elsewhere).  torch.distributed carries host tensors only (gloo, or the CPU side of a mixed
+    group): there is no device collective on the data path."""
+    if world == 1:
+        return np.ascontiguousarray(local)
+    import torch
+    import torch.distributed as dist
+    mine = shard_range(n_channels, rank, world)
+    assert local.shape[0] == len(mine), (local.shape, mine)
+    n_out = local.shape[1] if local.ndim > 1 else 0
+    biggest = max(len(shard_range(n_channels, r, world)) for r in range(world))
+    buf = torch.zeros((biggest, n_out), dtype=torch.from_numpy(np.zeros(0, local.dtype)).dtype)
+    buf[:len(mine)] = torch.from_numpy(np.ascontiguousarray(local))
+    outs = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, outs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = np.zeros((n_channels, n_out), local.dtype)
+    for r in range(world):
+        rr = shard_range(n_channels, r, world)
+        full[rr.start:rr.stop] = outs[r][:len(rr)].numpy()
+    return full
+
+
+class ChannelBank:
+    """C independent narrowband chains on one wideband input (orion_b200_bank_*): channel c is the block
+    `Chain(**specs[c])`.  `channels` selects a sub-range of the specs -- one bank per GPU / process."""
+
+    def __init__(self, specs, channels=None):
+        specs = list(specs)
+        self.channel_ids = list(channels) if channels is not None else list(range(len(specs)))
+        arr = (ChainSpec * len(self.channel_ids))()
+        self._keep = []
+        for i, c in enumerate(self.channel_ids):
+            _fill_spec(arr[i], self._keep, **specs[c])
+        h = C.c_void_p(0)
+        st = lib().orion_b200_bank_create(arr, len(self.channel_ids), C.byref(h))
+        _check(st)
+        self._h = h
+        self.decim = max(int(specs[self.channel_ids[0]].get("decim", 1)), 1) if specs[self.channel_ids[0]].get("fir", FIR_NONE) != FIR_NONE else 1
+        self.out_dtype = np.complex64 if specs[self.channel_ids[0]].get("demod", DEMOD_NONE) == DEMOD_NONE else np.float32
+
+    def _ck(self, st):
+        if st != OK:
+            raise OrionB200Error(st, lib().orion_b200_status_string(st).decode() + " -- " +
+                                 (lib().orion_b200_bank_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orion_b200_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().orion_b200_bank_channels(self._h))
+
+    def out_items(self, n_in: int) -> int:
+        return -(-n_in // self.decim)
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        """Host slices: one wideband input -> [channels, ceil(n/m)] outputs."""
+        x = np.ascontiguousarray(x, np.complex64)
+        n_out = self.out_items(x.size)
+        out = np.zeros((len(self), n_out), self.out_dtype)
+        ir, ow = C.c_size_t(0), C.c_size_t(0)
+        self._ck(lib().orion_b200_bank_process(self._h, x.ctypes.data if x.size else None, x.size,
+                                               out.ctypes.data if out.size else None, n_out, C.byref(ir), C.byref(ow)))
+        assert ow.value == n_out or x.size == 0
+        return out
+
+    def process_dev(self, d_in: int, n_in: int, d_out: int, out_stride: int) -> WorkReport:
+        ir, ow = C.c_size_t(0), C.c_size_t(0)
+        self._ck(lib().orion_b200_bank_process_dev(self._h, C.c_void_p(d_in), n_in, C.c_void_p(d_out), out_stride,
+                                                   C.byref(ir), C.byref(ow)))
+        return WorkReport(ir.value, ow.value)
+
+    def synchronize(self):
+        self._ck(lib().orion_b200_bank_synchronize(self._h))
+
+    def reset(self):
+        self._ck(lib().orion_b200_bank_reset(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().orion_b200_bank_launch_count(self._h))
 
 
 # ---- src/core.rs chain wrappers --------------------------------------------------------------------

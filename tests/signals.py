@@ -87,3 +87,46 @@ def bit_equal(a, b):
     fb = b.view(np.float32)
     nan = np.isnan(fa)
     return bool(np.array_equal(nan, np.isnan(fb)) and np.array_equal(fa.view(np.uint32)[~nan], fb.view(np.uint32)[~nan]))
+
+
+# ---- C5: many narrowband channels in one wideband stream ------------------------
+def c5_channel_freqs(n_channels, spacing_hz):
+    return [(c - n_channels // 2) * spacing_hz for c in range(n_channels)]
+
+
+def c5_wideband(n, fs, n_channels, spacing_hz, amp=0.02, dev_hz=2.5e3, sigma=1e-4, seed=0x0514):
+    """Channel c sits at (c - C/2) * spacing and carries FM (c even) or AM (c odd) with a per-channel tone."""
+    t = np.arange(n) / fs
+    x = awgn(n, sigma, seed)
+    for c, fc in enumerate(c5_channel_freqs(n_channels, spacing_hz)):
+        tone = 300.0 + (c % 17) * 100.0
+        if c % 2 == 0:
+            ph = 2 * np.pi * fc * t + (dev_hz / tone) * np.sin(2 * np.pi * tone * t)
+            x = x + amp * np.exp(1j * ph)
+        else:
+            x = x + amp * (1.0 + 0.5 * np.cos(2 * np.pi * tone * t)) * np.exp(2j * np.pi * fc * t)
+    return x.astype(np.complex64)
+
+
+def c5_specs(ob, fs, m, n_channels, spacing_hz, cutoff_hz, trans_hz, dev_hz=2.5e3, audio_bw_hz=3e3):
+    """One chain spec per channel: Rotator(-f_c) -> FirDecimator(fs, m, cutoff, trans) -> FM (even) / AM (odd)."""
+    taps = ob.fir_lowpass_design(fs, cutoff_hz, trans_hz)
+    specs = []
+    for c, fc in enumerate(c5_channel_freqs(n_channels, spacing_hz)):
+        sp = dict(mix=ob.MIX_ROTATE, mix_freq_hz=-fc, mix_fs=fs, fir=ob.FIR_DECIM, taps=taps, decim=m, fs_demod=fs / m,
+                  audio_bw_hz=audio_bw_hz)
+        if c % 2 == 0:
+            sp.update(demod=ob.DEMOD_FM, p0=dev_hz)
+        else:
+            sp.update(demod=ob.DEMOD_AM)
+        specs.append(sp)
+    return specs
+
+
+def c5_oracle_channel(oracle, x, c, fs, m, n_channels, spacing_hz, cutoff_hz, trans_hz, dev_hz=2.5e3, audio_bw_hz=3e3):
+    """The reference composition for channel c: three blocks run back to back through intermediate vectors."""
+    fc = c5_channel_freqs(n_channels, spacing_hz)[c]
+    y = oracle.Rotator(-fc, fs).rotate_block(x)
+    y = oracle.FirDecimator(fs, m, cutoff_hz, trans_hz).run(y)
+    dem = oracle.FmQuadratureDemod(fs / m, dev_hz, audio_bw_hz) if c % 2 == 0 else oracle.AmEnvelopeDemod(fs / m, audio_bw_hz)
+    return dem.run(y)

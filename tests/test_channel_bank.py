@@ -1,0 +1,101 @@
+"""Channel bank (BASELINE config 5) and its sharding across processes.
+
+CPU half: the sharding arithmetic and the host-side gather over `gloo` with world_size 2 -- each rank
+computes its channel range (with the CPU oracle standing in for the GPU bank, which this container
+cannot run) and rank 0 must assemble exactly the single-process result.
+GPU half: `ChannelBank` through the C ABI against the oracle's block-by-block composition per channel."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import orion_b200 as ob
+from signals import assert_parity, c5_oracle_channel, c5_specs, c5_wideband
+
+CFG = dict(fs=1.024e6, m=16, n_channels=12, spacing_hz=16e3, cutoff_hz=3.5e3, trans_hz=16e3)
+
+
+def test_shard_ranges_partition_the_channels():
+    for C in (1, 7, 12, 1024):
+        for W in (1, 2, 3, 4, 8):
+            got = [c for r in range(W) for c in ob.shard_range(C, r, W)]
+            assert got == list(range(C))
+            sizes = [len(ob.shard_range(C, r, W)) for r in range(W)]
+            assert max(sizes) - min(sizes) <= 1
+    assert list(ob.shard_range(1024, 3, 8)) == list(range(384, 512))
+    with pytest.raises(ValueError):
+        ob.shard_range(8, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_main(rank, world, port, n, path):
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here), os.path.join(os.path.dirname(here), "orion-sdr_b200", "python")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])      # every rank regenerates it from the seed
+        mine = ob.shard_range(CFG["n_channels"], rank, world)
+        local = np.stack([c5_oracle_channel(oracle, x, c, **CFG) for c in mine])
+        full = ob.gather_channels(local, CFG["n_channels"], rank, world)
+        if rank == 0:
+            np.save(path, full)
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_gather_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    n = 8192
+    path = str(tmp_path / "gathered.npy")
+    mp.spawn(_rank_main, args=(2, _free_port(), n, path), nprocs=2, join=True)
+    got = np.load(path)
+    x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    want = np.stack([c5_oracle_channel(oracle, x, c, **CFG) for c in range(CFG["n_channels"])])
+    assert got.shape == want.shape == (CFG["n_channels"], n // CFG["m"])
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_bank_matches_block_by_block_composition():
+    n = 65_536
+    x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    specs = c5_specs(ob, **CFG)
+    bank = ob.ChannelBank(specs)
+    assert len(bank) == CFG["n_channels"]
+    out = bank.process(x)
+    assert out.shape == (CFG["n_channels"], n // CFG["m"]) and out.dtype == np.float32
+    for c in range(CFG["n_channels"]):
+        assert_parity(out[c], c5_oracle_channel(oracle, x, c, **CFG), what=f"channel {c}")
+    assert bank.launch_count == CFG["n_channels"]
+    # streaming: a second call continues every channel's state
+    x2 = c5_wideband(2 * n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    bank.reset()
+    a = np.concatenate([bank.process(x2[:n]), bank.process(x2[n:])], axis=1)
+    b = ob.ChannelBank(specs).process(x2)
+    for c in range(CFG["n_channels"]):
+        assert_parity(a[c], b[c], what=f"channel {c} two calls vs one")
+
+
+@pytest.mark.gpu
+def test_sharded_banks_cover_the_full_bank():
+    n = 32_768
+    x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    specs = c5_specs(ob, **CFG)
+    full = ob.ChannelBank(specs).process(x)
+    parts = [ob.ChannelBank(specs, channels=ob.shard_range(CFG["n_channels"], r, 3)).process(x) for r in range(3)]
+    np.testing.assert_array_equal(np.concatenate(parts, axis=0), full)        # same kernels, same inputs: bit-equal
