@@ -236,6 +236,11 @@ int orion_b200_block_set_stream(orion_b200_block *b, void *cuda_stream);
 #define ORION_B200_OPT_USE_TMA       2  /* 1 (default): interior tiles are staged with cp.async.bulk.tensor;
                                            0: every tile uses the cooperative loader */
 #define ORION_B200_OPT_SERIAL_TILES  3  /* 1: debug -- one CTA walks the tiles in order */
+#define ORION_B200_OPT_OVERLAP_LAUNCHES 4 /* 1: on a stream attached with orion_b200_block_set_stream, let the kernel of call N+1
+                                           start while call N drains (programmatic dependent launch; state handed over between
+                                           calls is still waited for).  The caller promises that the input of a call is complete
+                                           when the call is enqueued (not produced by the kernel enqueued just before it).  On the
+                                           block's own stream this overlap is always on: nothing foreign can be enqueued there. */
 int orion_b200_block_set_option(orion_b200_block *b, int option, double value);
 
 /* Streaming-state snapshot for the parity harness.  Layout (20 floats):

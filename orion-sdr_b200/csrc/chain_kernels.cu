@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifndef ORION_TRACE
 #define ORION_TRACE 0
@@ -108,6 +109,32 @@ DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint3
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+// Overlapping consecutive calls (programmatic dependent launch).  With the launch attribute set, the CTAs of call
+// N+1 are scheduled as SMs drain from call N.  Nothing waits for the whole previous grid: the few items call N
+// hands to call N+1 -- FIR history (written when N starts), discriminator `prev` and section states (written by
+// N's last tile) -- are guarded by two monotonic counters in global memory, bumped with release semantics by the
+// writers and polled with acquire semantics by the handful of warps of N+1 that read them; those reads bypass L1.
+DEV void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DEV unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void handoff_wait(const ChainArgs &a, int which, unsigned target) {          // whole warp; which: 0 history, 1 carried state
+    if (target == 0u) return;
+    int spins = 0;
+    while ((int)(ld_acquire_u32(a.handoff + which) - target) < 0) {
+        if (++spins > (1 << 22)) { atomicExch(a.err_flag, 4); break; }           // watchdog: never hang the device
+        __nanosleep(100);
+    }
+    __syncwarp();
+}
+DEV void handoff_signal(const ChainArgs &a, int which, int lane) {               // after the warp's hand-over stores
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(a.handoff + which, 1u);
+    __syncwarp();
 }
 DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -216,7 +243,7 @@ DEV float post_apply(const SecParam &P, float y) {
 DEV float2 load_x(const ChainArgs &a, long long s) {
     if (s < 0) {
         const long long h = s + a.H;
-        return h >= 0 ? __ldg(a.hist_in + h) : make_float2(0.f, 0.f);
+        return h >= 0 ? __ldcg(a.hist_in + h) : make_float2(0.f, 0.f);
     }
     if (s < a.n_in) return __ldg(reinterpret_cast<const float2 *>(a.in) + s);
     return make_float2(0.f, 0.f);
@@ -341,7 +368,7 @@ DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int
             if (idx < 0) {
 #pragma unroll
                 for (int d = 0; d < D; d += 2) {
-                    const float2 c = (idx == -1) ? a.carry_in->sec[G.first + d / 2] : make_float2(0.f, 0.f);
+                    const float2 c = (idx == -1) ? __ldcg(&a.carry_in->sec[G.first + d / 2]) : make_float2(0.f, 0.f);
                     pay[d] = c.x; pay[d + 1] = c.y;
                 }
             } else {
@@ -660,6 +687,9 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 #ifndef ORION_FIR_PACKED
 #define ORION_FIR_PACKED 1
 #endif
+#ifndef ORION_FM_ROLLED
+#define ORION_FM_ROLLED 0     // 1: the FM front of a lane is one rolled loop (small code); 0: unrolled over the lane's items
+#endif
 #ifndef ORION_TAPS_SMEM
 #define ORION_TAPS_SMEM 0
 #endif
@@ -875,7 +905,7 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         }
         if (need_prev) {
             float2 prev = shfl_up2(z[NPT - 1], 1);
-            if (lane == 0) prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+            if (lane == 0) prev = (j0 > 0) ? zhalo : __ldcg(&a.carry_in->prev);
             __syncwarp();
             // carried discriminator state for the next call
             if (a.n_out > 0 && jt <= a.n_out - 1 && a.n_out - 1 < jt + NPT) {
@@ -947,9 +977,9 @@ DEV void end_of_call_duties(const ChainArgs &a, int lane) {
             if (k0 + lane < a.H) a.hist_out[k0 + lane] = load_x(a, a.n_in - a.H + k0 + lane);
     __syncwarp();
     if (lane == 0) {
-        if (!need_prev || a.n_out == 0) a.carry_out->prev = a.carry_in->prev;
+        if (!need_prev || a.n_out == 0) a.carry_out->prev = __ldcg(&a.carry_in->prev);
         for (int s = 0; s < kMaxSections; ++s)
-            if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = a.carry_in->sec[s];
+            if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = __ldcg(&a.carry_in->sec[s]);
     }
 }
 
@@ -1013,7 +1043,7 @@ DEV void fm_front_rolled(const ChainArgs &a, const Lr4Tabs *tabs, long long tile
         zl = make_float2(zl.x * cr - zl.y * ci, zl.x * ci + zl.y * cr);
     }
     float2 prev = shfl_up2(zl, 1);
-    if (lane == 0) prev = (j0 > 0) ? zhalo : a.carry_in->prev;
+    if (lane == 0) prev = (j0 > 0) ? zhalo : __ldcg(&a.carry_in->prev);
     __syncwarp();
     const int last = (int)max(min(a.n_out - 1 - jt, (long long)NPT), -1ll);      // item of this lane that ends the call
 #pragma unroll
@@ -1055,7 +1085,7 @@ DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long t
     const bool want = lane < depth && idx >= -1;
     if (want) {
         if (idx < 0) {                              // the state carried into this call sits "before tile 0"
-            const float2 c0 = a.carry_in->sec[0], c1 = a.carry_in->sec[1];
+            const float2 c0 = __ldcg(&a.carry_in->sec[0]), c1 = __ldcg(&a.carry_in->sec[1]);
             pay[0] = c0.x; pay[1] = c0.y; pay[2] = c1.x; pay[3] = c1.y;
         } else {
             const TileLink *lk = a.links + idx * kMaxGroups;
@@ -1230,6 +1260,35 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     Hot *hot_sh = reinterpret_cast<Hot *>(reinterpret_cast<unsigned char *>(g_sh) + (((size_t)a.Lg * sizeof(float) + 15) & ~(size_t)15));
     // Hot's layout equals ChainArgs::grp followed by ChainArgs::sec (static_assert below)
     const Hot *hot = ORION_HOT_SMEM ? hot_sh : reinterpret_cast<const Hot *>(a.grp);
+    // The ring first: barriers, then the initial fills go out BEFORE the table copies below, so the first tiles
+    // are already in flight from HBM while the CTA sets itself up.
+    if (FRONT == FRONT_STAGED) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&ring.full[s]), 1); ring.gen[s] = -1; }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) ring.cons = 0;
+    __syncthreads();
+    griddep_launch_dependents();
+    // fill k of slot s = the CTA's tile number i = k*NS + s (lane 0): TMA for interior tiles, a plain
+    // arrive for edge tiles (their consumer loads them cooperatively); nothing past the end
+    auto fill_slot = [&](int s, int k) {
+        const long long t = cta + G * ((long long)k * NS + s);
+        const bool pred = lane == 0 && t < a.ntiles;
+        const uint32_t bar = smem_u32(&ring.full[s]);
+        st_shared_volatile_pred(pred, smem_u32(&ring.gen[s]), k);        // before the arrive below (release)
+        if (tile_is_interior(a, t)) {                                     // warp-uniform
+            tma_fill_pred(pred, smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
+                          (int)(t * kThreads - HRc - a.tma_row0), bar, (uint32_t)stage_bytes);
+        } else {
+            mbar_arrive_pred(pred, bar);
+        }
+    };
+
+    if (FRONT == FRONT_STAGED)
+        for (int s = wid; s < NS; s += NW) fill_slot(s, 0);            // initial fill of the ring
+
     // DM_FM_LR4: per-lane scan tables of the one group, behind the section data
     Lr4Tabs *tabs_sh = reinterpret_cast<Lr4Tabs *>(reinterpret_cast<unsigned char *>(hot_sh) + ((sizeof(Hot) + 15) & ~(size_t)15));
     if (DM == DM_FM_LR4) {
@@ -1260,30 +1319,13 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         atomicMin(reinterpret_cast<unsigned long long *>(a.trace + (long long)a.ntiles * 16), gt);
     }
 
-    if (FRONT == FRONT_STAGED) {
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&ring.full[s]), 1); ring.gen[s] = -1; }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    __syncthreads();                                       // tables in shared memory are complete
+    if (cta == (long long)(a.ntiles - 1) % G && wid == NW - 1) {
+        handoff_wait(a, 1, a.carry_target);                // replaces buffers the previous call still reads until its end
+        end_of_call_duties(a, lane);
+        handoff_signal(a, 0, lane);                        // FIR history for the next call is in place
+        handoff_signal(a, 1, lane);                        // ... and this warp's share of the carried state
     }
-    if (threadIdx.x == 0) ring.cons = 0;
-    __syncthreads();
-    if (cta == (long long)(a.ntiles - 1) % G && wid == NW - 1) end_of_call_duties(a, lane);
-
-    // fill k of slot s = the CTA's tile number i = k*NS + s (lane 0): TMA for interior tiles, a plain
-    // arrive for edge tiles (their consumer loads them cooperatively); nothing past the end
-    auto fill_slot = [&](int s, int k) {
-        const long long t = cta + G * ((long long)k * NS + s);
-        const bool pred = lane == 0 && t < a.ntiles;
-        const uint32_t bar = smem_u32(&ring.full[s]);
-        st_shared_volatile_pred(pred, smem_u32(&ring.gen[s]), k);        // before the arrive below (release)
-        if (tile_is_interior(a, t)) {                                     // warp-uniform
-            tma_fill_pred(pred, smem_u32(smem + (size_t)s * stage_stride), &tmap, 0,
-                          (int)(t * kThreads - HRc - a.tma_row0), bar, (uint32_t)stage_bytes);
-        } else {
-            mbar_arrive_pred(pred, bar);
-        }
-    };
 
     float u_pend[NPT];
 #pragma unroll
@@ -1295,14 +1337,16 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         __syncwarp();
     };
 
-    if (FRONT == FRONT_STAGED)
-        for (int s = wid; s < NS; s += NW) fill_slot(s, 0);            // initial fill of the ring
 
     for (;;) {
         unsigned c = atom_add_shared_pred(lane == 0, smem_u32(&ring.cons), 1u);
         c = __shfl_sync(FULLMASK, c, 0);
         const long long tile = cta + G * (long long)c;
         if (tile >= a.ntiles) break;
+        // the first tiles read what the previous call carried over (FIR history, discriminator `prev`, section
+        // states through the look-back), the last one writes what this call carries out
+        const bool handoff_tile = tile < a.pdl_guard || tile == a.ntiles - 1;
+        if (tile == 0) handoff_wait(a, 0, a.hist_target);  // its edge loader reads the history the previous call left
         stamp(tile, 0);
         if ((ORION_TRACE && a.trace) && lane == 0) {
             unsigned long long gt;
@@ -1359,9 +1403,20 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         } else {
             front_direct<NPT>(a, tile, lane, z, u, zhalo);
         }
+        if (handoff_tile) handoff_wait(a, 1, a.carry_target);   // `prev` now, section states in this tile's look-back
         float E4[4] = { 0.f, 0.f, 0.f, 0.f };
-        if (DM == DM_FM_LR4) fm_front_rolled<NPT>(a, tabs_sh, tile, lane, z, u, zhalo, E4);
-        else front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
+        if (DM == DM_FM_LR4 && ORION_FM_ROLLED) fm_front_rolled<NPT>(a, tabs_sh, tile, lane, z, u, zhalo, E4);
+        else {
+            front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
+            if (DM == DM_FM_LR4) {                       // zero-state dot product of the unrolled front
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {
+                    const float4 im = *reinterpret_cast<const float4 *>(tabs_sh->imp[i]);
+                    E4[0] = fmaf(im.x, u[i], E4[0]); E4[1] = fmaf(im.y, u[i], E4[1]);
+                    E4[2] = fmaf(im.z, u[i], E4[2]); E4[3] = fmaf(im.w, u[i], E4[3]);
+                }
+            }
+        }
         if ((ORION_TRACE && a.trace) && lane == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1370,6 +1425,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             a.trace[tile * 16 + 9] = clock64();
             if (!has_sections) a.trace[tile * 16 + 3] = clock64();
         }
+        if (!has_sections && tile == a.ntiles - 1) handoff_signal(a, 1, lane);      // the call's carried state is complete
         if (has_sections) {
             if (DM == DM_FM_LR4) lr4_front_park<NPT>(a, hot, tile, lane, E4, park[slot_pp]);
             else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
@@ -1377,6 +1433,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             if (pend_tile >= 0) {
                 if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
                 else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
                 stamp(pend_tile, 4);
             }
 #pragma unroll
@@ -1388,6 +1445,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     if (pend_tile >= 0) {
         if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
         else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+        if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
     }
     if ((ORION_TRACE && a.trace) && lane == 0) {
         unsigned long long gt;
@@ -1442,10 +1500,19 @@ cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, i
 }
 
 cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
-                                size_t dyn_smem, cudaStream_t stream) {
+                                size_t dyn_smem, cudaStream_t stream, int overlap) {
     // serial debug mode: one warp walks the tiles in order
-    k<<<grid, args.serial ? kThreads : kThreads * warps, dyn_smem, stream>>>(args, tmap);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(args.serial ? kThreads : kThreads * warps);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, args, tmap);
 }
 
 }  // namespace orion

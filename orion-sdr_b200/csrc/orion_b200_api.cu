@@ -23,7 +23,7 @@ typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm);
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm);
 cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
-                                size_t dyn_smem, cudaStream_t stream);
+                                size_t dyn_smem, cudaStream_t stream, int overlap);
 }  // namespace orion
 
 using namespace orion;
@@ -396,7 +396,7 @@ struct orion_b200_block {
     chain_kernel_t kernel = nullptr;
     int ctas_per_sm = 1, sm_count = 1;
     // ---- options ----
-    int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0;
+    int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0, opt_overlap = 0;
     long long *trace = nullptr;           // debug: device buffer of 8 x int64 per tile
     // ---- device ----
     int device = 0;
@@ -404,6 +404,7 @@ struct orion_b200_block {
     float *d_g = nullptr;
     GroupTables *d_gtabs = nullptr;
     std::vector<GroupParam> groups;
+    std::vector<int> group_depth;
     float2 *d_hist[2] = { nullptr, nullptr };
     size_t hist_cap = 0;
     CarryState *d_carry[2] = { nullptr, nullptr };
@@ -416,6 +417,8 @@ struct orion_b200_block {
     int *d_err = nullptr;
     int *h_err = nullptr;                 // pinned
     int *d_err_ext = nullptr;             // a channel bank's shared watchdog word (not owned)
+    unsigned int *d_handoff = nullptr;    // hand-over counters between consecutive calls (chain_kernels.cu)
+    unsigned int calls_since_reset = 0;
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
     // ---- counters ----
@@ -489,12 +492,15 @@ int finalize_plan(orion_b200_block *b) {
     }
     // section groups + scan tables
     b->groups.clear();
+    b->group_depth.clear();
     if (!b->secs.empty()) {
         const std::vector<GroupHost> gh = split_groups(b->secs);
         if (gh.size() > (size_t)kMaxGroups) return fail(b, ORION_B200_ERR_UNSUPPORTED, "too many section groups");
         std::vector<GroupTables> tabs(gh.size());
         b->groups.resize(gh.size());
         for (size_t g = 0; g < gh.size(); ++g) build_group(b->secs.data(), gh[g], npt_of(b), &b->groups[g], &tabs[g]);
+        b->group_depth.clear();
+        for (size_t g = 0; g < gh.size(); ++g) b->group_depth.push_back(tabs[g].depth);
         if (b->d_gtabs) { cudaFree(b->d_gtabs); b->d_gtabs = nullptr; }
         CK(cudaMalloc(&b->d_gtabs, tabs.size() * sizeof(GroupTables)));
         CK(cudaMemcpy(b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables), cudaMemcpyHostToDevice));
@@ -513,6 +519,8 @@ int reset_state(orion_b200_block *b) {
         CK(cudaMemcpy(b->d_carry[i], &cs, sizeof(cs), cudaMemcpyHostToDevice));
         if (b->d_hist[i]) CK(cudaMemset(b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
     }
+    CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    b->calls_since_reset = 0;
     b->k_pre = b->k_post = 0;
     b->pre.reset_phase();
     b->post.reset_phase();
@@ -541,6 +549,8 @@ int init_device_side(orion_b200_block *b) {
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
     CK(cudaMalloc(&b->d_ticket, 2 * sizeof(unsigned long long)));        // {ticket, done}
     CK(cudaMemset(b->d_ticket, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_handoff, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
     CK(cudaMalloc(&b->d_err, sizeof(int)));
     CK(cudaMemset(b->d_err, 0, sizeof(int)));
     CK(cudaMallocHost(&b->h_err, sizeof(int)));
@@ -611,14 +621,15 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         if (b->d_links) cudaFree(b->d_links);
         size_t cap = std::max<size_t>((size_t)ntiles, 4096);
         cap += cap / 4;
-        CK(cudaMalloc(&b->d_links, cap * kMaxGroups * sizeof(TileLink)));
-        CK(cudaMemset(b->d_links, 0, cap * kMaxGroups * sizeof(TileLink)));
+        CK(cudaMalloc(&b->d_links, 2 * cap * kMaxGroups * sizeof(TileLink)));      // two halves, alternating between calls
+        CK(cudaMemset(b->d_links, 0, 2 * cap * kMaxGroups * sizeof(TileLink)));
         b->links_cap = cap;
         b->epoch = 0;
     }
     b->epoch += 1;
     if (b->epoch >= (1u << 30)) {                      // epoch wrap: clear the links once
-        CK(cudaMemsetAsync(b->d_links, 0, b->links_cap * kMaxGroups * sizeof(TileLink), b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        CK(cudaMemsetAsync(b->d_links, 0, 2 * b->links_cap * kMaxGroups * sizeof(TileLink), b->stream));
         b->epoch = 1;
     }
 
@@ -646,9 +657,17 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
-    a.links = b->d_links;
+    a.links = b->d_links ? b->d_links + (size_t)(b->epoch & 1u) * b->links_cap * kMaxGroups : nullptr;   // consecutive calls may overlap
     a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err_ext ? b->d_err_ext : b->d_err;
     a.trace = b->trace;
+    {   // tile t's look-back reaches the carried state iff t < depth of a group; tile 0 also reads history and `prev`
+        int guard = 1;
+        for (size_t g = 0; g < b->groups.size(); ++g) guard = std::max(guard, std::min(b->group_depth[g], 32) + 1);
+        a.pdl_guard = guard;
+    }
+    a.handoff = b->d_handoff;
+    a.hist_target = b->calls_since_reset;                 // every earlier call has written its history ...
+    a.carry_target = 2u * b->calls_since_reset;           // ... and both of its hand-over signals
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
     a.ntaps2 = (int)b->plan.taps2.size();
 
@@ -682,11 +701,26 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         const long long resident = (long long)b->sm_count * b->ctas_per_sm;
         const long long want = (ntiles + b->plan.warps - 1) / b->plan.warps;      // one tile per warp at least
         grid = (int)std::max<long long>(1, std::min<long long>(want, resident));
+        if (const char *e = getenv("ORION_B200_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments
     }
-    cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream);
+    // Overlap with the previous launch on the stream (programmatic dependent launch): only long calls (the link
+    // records and the output of call N are far from what call N+1 touches first), only section groups whose
+    // look-back cannot reach the carried state past the guarded tiles, and only on the block's own stream unless
+    // the caller opted in (ORION_B200_OPT_OVERLAP_LAUNCHES) -- on an attached stream the predecessor may be a
+    // foreign kernel that is still producing this call's input.
+    bool overlap = !b->opt_serial && ntiles >= 1024 && (b->stream == b->own_stream || b->opt_overlap);
+    for (const GroupParam &gp : b->groups) overlap = overlap && gp.agg_only;
+    if (getenv("ORION_B200_NO_OVERLAP")) overlap = false;
+    cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream, overlap ? 1 : 0);
     delete ap;
     if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "chain kernel launch", e);
     b->launches += 1;
+    b->calls_since_reset += 1;
+    if (b->calls_since_reset >= (1u << 30)) {              // counter wrap: drain, start over
+        CK(cudaStreamSynchronize(b->stream));
+        CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
+        b->calls_since_reset = 0;
+    }
     b->pp ^= 1;
     b->k_pre += n_in;
     b->k_post += n_out;
@@ -1044,6 +1078,7 @@ int orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels
                                     cudaMallocHost(&k->h_err, sizeof(int)) != cudaSuccess)) st = ORION_B200_ERR_ALLOC;
         for (size_t c = 0; c < k->ch.size() && st == ORION_B200_OK; ++c) {
             k->ch[c]->d_err_ext = k->d_err;
+            k->ch[c]->opt_overlap = 1;                 // neighbours on a bank stream are different, independent blocks
             st = orion_b200_block_set_stream(k->ch[c], (void *)k->streams[c % ns]);
         }
     }
@@ -1139,7 +1174,7 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     cudaFree(b->d_g); cudaFree(b->d_gtabs);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     cudaFree(b->d_carry[0]); cudaFree(b->d_carry[1]);
-    cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err);
+    cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err); cudaFree(b->d_handoff);
     cudaFree(b->d_in); cudaFree(b->d_out);
     if (b->h_err) cudaFreeHost(b->h_err);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -1256,6 +1291,7 @@ int orion_b200_block_set_option(orion_b200_block *b, int option, double value) {
             break;
         case ORION_B200_OPT_USE_TMA: b->opt_use_tma = v; break;
         case ORION_B200_OPT_SERIAL_TILES: b->opt_serial = v; break;
+        case ORION_B200_OPT_OVERLAP_LAUNCHES: b->opt_overlap = v; break;
         default: return fail(b, ORION_B200_ERR_INVALID, "unknown option");
     }
     if (b->plan_dirty) {

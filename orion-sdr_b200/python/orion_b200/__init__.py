@@ -25,7 +25,7 @@ ITEM_F32, ITEM_C32 = 1, 2
 MIX_NONE, MIX_ROTATE, MIX_NCO = 0, 1, 2
 FIR_NONE, FIR_DECIM, FIR_IQ = 0, 1, 2
 DEMOD_NONE, DEMOD_FM, DEMOD_PM, DEMOD_AM, DEMOD_AM_ABS, DEMOD_SSB, DEMOD_CW, DEMOD_USB = range(8)
-OPT_FIR_GLOBAL, OPT_USE_TMA, OPT_SERIAL_TILES = 1, 2, 3
+OPT_FIR_GLOBAL, OPT_USE_TMA, OPT_SERIAL_TILES, OPT_OVERLAP_LAUNCHES = 1, 2, 3, 4
 
 
 class OrionB200Error(RuntimeError):

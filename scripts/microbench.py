@@ -11,6 +11,7 @@ def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30
     y = torch.empty(out_items * (2 if out_dtype == torch.complex64 else 1), dtype=torch.float32, device="cuda")
     st = torch.cuda.Stream()
     blk.set_stream(st.cuda_stream)
+    blk.set_option(ob.OPT_OVERLAP_LAUNCHES, int(os.environ.get("OVERLAP", "1")))
     t_end = time.perf_counter() + float(os.environ.get("WARM_S", "1.5"))      # sustained load: let the SM clock ramp up
     while time.perf_counter() < t_end:
         for i in range(30):
@@ -25,7 +26,7 @@ def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30
     ms = e0.elapsed_time(e1) / reps
     print(f"{name:34s} {ms*1e3:8.1f} us  {n_in/ms/1e6:8.1f} GS/s  {bytes_per_in*n_in/ms/1e6:8.1f} GB/s", flush=True)
 
-n = 24_000_000
+n = int(os.environ.get("N_SAMPLES", "24000000"))
 taps = ob.fir_lowpass_design(2.4e6, 100e3, 38400.0)
 which = sys.argv[1:] or ["dec", "chain", "fm", "rot", "lp"]
 if "dec" in which:

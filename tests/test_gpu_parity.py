@@ -339,3 +339,39 @@ def test_chain_wrappers_return_input_len_items():
     assert a.size == b.size == 4096
     assert_parity(a[:1024], b[:1024])
     assert not a[1024:].any() and not b[1024:].any()
+
+
+# ---- back-to-back long calls: the launches overlap (programmatic dependent launch), the stream must not notice --
+def test_overlapped_back_to_back_calls_keep_streaming_state():
+    import os
+    import torch
+    fs, m = 2.4e6, 8
+    n_call = 2048 * 256 * m + 8 * 1237            # >= 2048 warp tiles per call: the overlap path is taken
+    calls = 3
+    x = fm_iq(calls * n_call, fs)
+    xd = torch.from_numpy(x).cuda()
+    n_out = n_call // m
+
+    def run(no_overlap):
+        if no_overlap:
+            os.environ["ORION_B200_NO_OVERLAP"] = "1"
+        else:
+            os.environ.pop("ORION_B200_NO_OVERLAP", None)
+        taps = ob.fir_lowpass_design(fs, 100e3, 38400.0)
+        ch = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_FM, fs_demod=fs / m, p0=25e3,
+                      audio_bw_hz=15e3, translate_hz=100e3)
+        yd = torch.zeros(calls * n_out, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        for c in range(calls):                     # enqueued back to back on the block's own stream
+            wr = ch.process_dev(xd.data_ptr() + c * n_call * 8, n_call, yd.data_ptr() + c * n_out * 4, n_out)
+            assert tuple(wr) == (n_call, n_out)
+        ch.synchronize()
+        os.environ.pop("ORION_B200_NO_OVERLAP", None)
+        return yd.cpu().numpy()
+
+    over, plain = run(False), run(True)
+    assert bit_equal(over, plain), "overlapped launches must give exactly the serialised result"
+    dec = oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
+    ref = np.concatenate([fm.run(dec.run(x[c * n_call:(c + 1) * n_call])) for c in range(calls)])
+    assert_parity(over, ref, what="3 overlapped calls vs oracle streaming")
