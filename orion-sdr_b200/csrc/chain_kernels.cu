@@ -42,10 +42,14 @@ template <> struct Geo<1> { static constexpr bool fixed = true; static constexpr
 // Demodulator specialisation.  DM = -1: demodulator kind and section structure are launch arguments;
 // DM = DEMOD_NONE (0): C32 out, no sections; DM = DM_FM_LR4: FM discriminator followed by exactly one group of
 // two biquads (the LR4 of fm.rs:27) and nothing else -- the C1 chain.
-constexpr int DM_FM_LR4 = 100;
+// DM = DM_LR4 + kind: that demodulator kind followed by exactly one group of two biquads and nothing else (the LR4
+// of fm.rs:27 / pm.rs:27, or LpCascade itself when the kind is DEMOD_F32).
+constexpr int DM_LR4 = 100;
+constexpr int DM_FM_LR4 = DM_LR4 + DEMOD_FM;
 template <int DM> struct Dm {
     static constexpr bool fixed = DM >= 0;
-    static DEV int demod(const ChainArgs &a) { return DM < 0 ? a.demod : (DM == DM_FM_LR4 ? (int)DEMOD_FM : DM); }
+    static constexpr bool lr4 = DM >= DM_LR4;
+    static DEV int demod(const ChainArgs &a) { return DM < 0 ? a.demod : (DM >= DM_LR4 ? DM - DM_LR4 : DM); }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -1291,7 +1295,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
 
     // DM_FM_LR4: per-lane scan tables of the one group, behind the section data
     Lr4Tabs *tabs_sh = reinterpret_cast<Lr4Tabs *>(reinterpret_cast<unsigned char *>(hot_sh) + ((sizeof(Hot) + 15) & ~(size_t)15));
-    if (DM == DM_FM_LR4) {
+    if (Dm<DM>::lr4) {
         const float *src_l = &a.gtabs->lane[0][0], *src_b = &a.gtabs->lb[0][0];
         for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
             (&tabs_sh->lane[0][0])[i] = __ldg(src_l + i);
@@ -1408,7 +1412,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         if (DM == DM_FM_LR4 && ORION_FM_ROLLED) fm_front_rolled<NPT>(a, tabs_sh, tile, lane, z, u, zhalo, E4);
         else {
             front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
-            if (DM == DM_FM_LR4) {                       // zero-state dot product of the unrolled front
+            if (Dm<DM>::lr4) {                           // zero-state dot product of the unrolled front
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) {
                     const float4 im = *reinterpret_cast<const float4 *>(tabs_sh->imp[i]);
@@ -1427,11 +1431,11 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         }
         if (!has_sections && tile == a.ntiles - 1) handoff_signal(a, 1, lane);      // the call's carried state is complete
         if (has_sections) {
-            if (DM == DM_FM_LR4) lr4_front_park<NPT>(a, hot, tile, lane, E4, park[slot_pp]);
+            if (Dm<DM>::lr4) lr4_front_park<NPT>(a, hot, tile, lane, E4, park[slot_pp]);
             else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
             stamp(tile, 3);
             if (pend_tile >= 0) {
-                if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
                 else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
                 if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
                 stamp(pend_tile, 4);
@@ -1443,7 +1447,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         }
     }
     if (pend_tile >= 0) {
-        if (DM == DM_FM_LR4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+        if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
         else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
         if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
     }
@@ -1462,13 +1466,22 @@ typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 template <int FRONT, int R, int U, int SP = 0, int DM = -1>
 static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM>; }
 
-// sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, DEMOD_NONE, DM_FM_LR4
+// sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, a DEMOD_* kind, DM_LR4 + kind
 chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
-    if (front == FRONT_DIRECT) return kptr<FRONT_DIRECT, 16, 1>();
+    if (front == FRONT_DIRECT) {                          // rate-1 blocks: 16 items per lane straight from global memory
+        switch (dm) {
+            case DEMOD_NONE: return kptr<FRONT_DIRECT, 16, 1, 0, DEMOD_NONE>();                  // Rotator, NcoMixer
+            case DM_LR4 + DEMOD_FM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_FM>();    // FmQuadratureDemod
+            case DM_LR4 + DEMOD_PM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_PM>();    // PmQuadratureDemod
+            case DM_LR4 + DEMOD_F32: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_F32>();  // LpCascade
+        }
+        return kptr<FRONT_DIRECT, 16, 1>();
+    }
     if (front == FRONT_GLOBAL) return kptr<FRONT_GLOBAL, 8, 1>();
     if (sp == 1 && R == 8 && U == 1) {
         if (dm == DEMOD_NONE) return kptr<FRONT_STAGED, 8, 1, 1, DEMOD_NONE>();
         if (dm == DM_FM_LR4) return kptr<FRONT_STAGED, 8, 1, 1, DM_FM_LR4>();
+        if (dm == DEMOD_AM) return kptr<FRONT_STAGED, 8, 1, 1, DEMOD_AM>();                      // C3: sections stay generic
         return kptr<FRONT_STAGED, 8, 1, 1, -1>();
     }
 #ifndef ORION_ONLY_HOT_SHAPES

@@ -450,13 +450,17 @@ int finalize_plan(orion_b200_block *b) {
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     // shape / demodulator specialisations of the kernel family (chain_kernels.cu, Geo<SP> and Dm<DM>)
     int sp = 0, dm = -1;
+    const bool lr4_only = b->secs.size() == 2 && b->secs[0].type == SEC_BIQUAD && b->secs[1].type == SEC_BIQUAD &&
+                          b->secs[0].post_op == OP_NONE && b->secs[1].post_op == OP_NONE;
     if (b->plan.front == FRONT_STAGED && b->plan.R == 8 && b->plan.U == 1 && b->plan.Mb == 8 && b->plan.HR == 1 &&
         b->plan.P_pad == 8 && b->plan.row_pitch == 528) {
         sp = 1;
         if (b->demod == DEMOD_NONE) dm = DEMOD_NONE;
-        else if (b->demod == DEMOD_FM && b->secs.size() == 2 && b->secs[0].type == SEC_BIQUAD && b->secs[1].type == SEC_BIQUAD &&
-                 b->secs[0].post_op == OP_NONE && b->secs[1].post_op == OP_NONE)
-            dm = 100;                                                   // DM_FM_LR4
+        else if (b->demod == DEMOD_FM && lr4_only) dm = 100 + DEMOD_FM;              // DM_LR4 + kind
+        else if (b->demod == DEMOD_AM) dm = DEMOD_AM;
+    } else if (b->plan.front == FRONT_DIRECT) {
+        if (b->demod == DEMOD_NONE) dm = DEMOD_NONE;
+        else if ((b->demod == DEMOD_FM || b->demod == DEMOD_PM || b->demod == DEMOD_F32) && lr4_only) dm = 100 + b->demod;
     }
     if (getenv("ORION_B200_NO_SPECIALIZE")) { sp = 0; dm = -1; }
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm);
