@@ -243,6 +243,43 @@ DEV float post_apply(const SecParam &P, float y) {
     return y;
 }
 
+// Warp-tile transposing copies for the rate-1 blocks.  A lane owns CHUNKS consecutive 16-byte chunks of the warp
+// tile (its NPT items), but global memory is touched with LANE-consecutive chunks -- one instruction moves 512
+// contiguous bytes -- and the re-layout goes through a per-warp shared-memory scratch whose row pitch is an odd
+// number of chunks, so both directions are bank-conflict free.
+constexpr int kXposeBytes = kThreads * (8 * 16 + 16);          // per warp: 32 rows of 8 chunks + pad
+template <int CHUNKS>
+DEV void warp_tile_load(const void *gsrc, unsigned char *xs, int lane, float4 (&v)[CHUNKS]) {
+    constexpr int PITCH = CHUNKS * 16 + 16;
+    const float4 *g = reinterpret_cast<const float4 *>(gsrc);
+    float4 t[CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) t[k] = __ldg(g + k * kThreads + lane);
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int c = k * kThreads + lane;
+        *reinterpret_cast<float4 *>(xs + (c / CHUNKS) * PITCH + (c % CHUNKS) * 16) = t[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) v[k] = *reinterpret_cast<const float4 *>(xs + lane * PITCH + k * 16);
+    __syncwarp();
+}
+template <int CHUNKS>
+DEV void warp_tile_store(void *gdst, unsigned char *xs, int lane, const float4 (&v)[CHUNKS]) {
+    constexpr int PITCH = CHUNKS * 16 + 16;
+    float4 *g = reinterpret_cast<float4 *>(gdst);
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) *reinterpret_cast<float4 *>(xs + lane * PITCH + k * 16) = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int c = k * kThreads + lane;
+        g[c] = *reinterpret_cast<const float4 *>(xs + (c / CHUNKS) * PITCH + (c % CHUNKS) * 16);
+    }
+    __syncwarp();
+}
+
 // virtual input stream: FIR history for negative indices, zeros past the end of the call
 DEV float2 load_x(const ChainArgs &a, long long s) {
     if (s < 0) {
@@ -876,7 +913,8 @@ DEV float2 fir_staged_one(const ChainArgs &a, const unsigned char *smem, const f
 // DEMOD_NONE, end-of-call duties
 // ----------------------------------------------------------------------------------------------
 template <int NPT, int DM>
-DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo) {
+DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 zhalo,
+                   unsigned char *xs = nullptr) {
     const long long j0 = tile * (long long)(kThreads * NPT);
     const long long jt = j0 + (long long)lane * NPT;
     const int demod = Dm<DM>::demod(a);
@@ -959,7 +997,18 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
     if (demod == DEMOD_NONE) {
         float2 *out = reinterpret_cast<float2 *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
-        if (al16 && full) {
+        bool done = false;
+        if constexpr (NPT == 16) {
+            if (xs && al16 && j0 + kThreads * NPT <= a.n_out) {                 // whole warp tile: coalesced through the scratch
+                float4 v[NPT / 2];
+#pragma unroll
+                for (int i = 0; i < NPT; i += 2) v[i / 2] = make_float4(z[i].x, z[i].y, z[i + 1].x, z[i + 1].y);
+                warp_tile_store<NPT / 2>(out + j0, xs, lane, v);
+                done = true;
+            }
+        }
+        if (done) {
+        } else if (al16 && full) {
 #pragma unroll
             for (int i = 0; i < NPT; i += 2)
                 *reinterpret_cast<float4 *>(out + jt + i) = make_float4(z[i].x, z[i].y, z[i + 1].x, z[i + 1].y);
@@ -989,11 +1038,23 @@ DEV void end_of_call_duties(const ChainArgs &a, int lane) {
 
 // store the f32 outputs of a tile
 template <int NPT>
-DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u)[NPT]) {
-    const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
+DEV void store_f32(const ChainArgs &a, long long tile, int lane, const float (&u)[NPT], unsigned char *xs = nullptr) {
+    const long long j0 = tile * (long long)(kThreads * NPT);
+    const long long jt = j0 + (long long)lane * NPT;
     float *out = reinterpret_cast<float *>(a.out);
     const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 4 == 0);
-    if (al16 && jt + NPT <= a.n_out) {
+    bool done = false;
+    if constexpr (NPT == 16) {
+        if (xs && al16 && j0 + kThreads * NPT <= a.n_out) {                     // whole warp tile: coalesced through the scratch
+            float4 v[NPT / 4];
+#pragma unroll
+            for (int i = 0; i < NPT; i += 4) v[i / 4] = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+            warp_tile_store<NPT / 4>(out + j0, xs, lane, v);
+            done = true;
+        }
+    }
+    if (done) {
+    } else if (al16 && jt + NPT <= a.n_out) {
 #pragma unroll
         for (int i = 0; i < NPT; i += 4)
             *reinterpret_cast<float4 *>(out + jt + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
@@ -1117,7 +1178,7 @@ DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long t
 }
 template <int NPT>
 DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *tabs, long long tile, int lane, float (&u)[NPT],
-                           const float *park) {
+                           const float *park, unsigned char *xs = nullptr) {
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
     const float4 xv = *reinterpret_cast<const float4 *>(park + lane * kMaxGroupDim);
     float sin[4];
@@ -1150,32 +1211,49 @@ DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *ta
             a.carry_out->sec[1] = make_float2(st[2], st[3]);
         }
     }
-    store_f32<NPT>(a, tile, lane, u);
+    store_f32<NPT>(a, tile, lane, u, xs);
 }
 
 // the section phase of a tile whose group-0 front ran one loop iteration earlier (state parked in
 // shared memory): group 0 finish, then the remaining groups front + finish, then the store
 template <int NPT>
-DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&u)[NPT], const float *park) {
+DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&u)[NPT], const float *park,
+                         unsigned char *xs = nullptr) {
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
     const bool full = jt + NPT <= a.n_out;
     if (a.ngroups > 0) {
         group_finish_parked<NPT>(a, hot, 0, tile, lane, u, full, jt, park);
         for (int g = 1; g < a.ngroups; ++g) group_whole<NPT>(a, hot, g, tile, lane, u, full, jt);
     }
-    store_f32<NPT>(a, tile, lane, u);
+    store_f32<NPT>(a, tile, lane, u, xs);
 }
 
 // direct front: items straight from global memory (rate-1 blocks)
 template <int NPT>
-DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 &zhalo) {
+DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 &zhalo,
+                      unsigned char *xs) {
     const long long j0 = tile * (long long)(kThreads * NPT);
     const long long jt = j0 + (long long)lane * NPT;
     const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
+    const bool whole = NPT == 16 && j0 + kThreads * NPT <= a.n_out;             // warp-uniform: the warp tile is full
     if (a.demod != DEMOD_F32) {
         const float2 *in = reinterpret_cast<const float2 *>(a.in);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 2 == 0);
-        if (al16 && jt + NPT <= a.n_out) {
+        bool done = false;
+        if constexpr (NPT == 16) {
+            if (xs && al16 && whole) {
+                float4 v[NPT / 2];
+                warp_tile_load<NPT / 2>(in + j0, xs, lane, v);
+#pragma unroll
+                for (int i = 0; i < NPT; i += 2) {
+                    z[i] = make_float2(v[i / 2].x, v[i / 2].y);
+                    z[i + 1] = make_float2(v[i / 2].z, v[i / 2].w);
+                }
+                done = true;
+            }
+        }
+        if (done) {
+        } else if (al16 && jt + NPT <= a.n_out) {
 #pragma unroll
             for (int i = 0; i < NPT; i += 2) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
@@ -1201,7 +1279,18 @@ DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[
     } else {
         const float *in = reinterpret_cast<const float *>(a.in);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 4 == 0);
-        if (al16 && jt + NPT <= a.n_out) {
+        bool done = false;
+        if constexpr (NPT == 16) {
+            if (xs && al16 && whole) {
+                float4 v[NPT / 4];
+                warp_tile_load<NPT / 4>(in + j0, xs, lane, v);
+#pragma unroll
+                for (int i = 0; i < NPT; i += 4) { u[i] = v[i / 4].x; u[i + 1] = v[i / 4].y; u[i + 2] = v[i / 4].z; u[i + 3] = v[i / 4].w; }
+                done = true;
+            }
+        }
+        if (done) {
+        } else if (al16 && jt + NPT <= a.n_out) {
 #pragma unroll
             for (int i = 0; i < NPT; i += 4) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(in + jt + i));
@@ -1295,6 +1384,8 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
 
     // DM_FM_LR4: per-lane scan tables of the one group, behind the section data
     Lr4Tabs *tabs_sh = reinterpret_cast<Lr4Tabs *>(reinterpret_cast<unsigned char *>(hot_sh) + ((sizeof(Hot) + 15) & ~(size_t)15));
+    // rate-1 blocks: per-warp transposing scratch behind the tables
+    unsigned char *xs = (FRONT == FRONT_DIRECT) ? reinterpret_cast<unsigned char *>(tabs_sh + 1) + (size_t)wid * kXposeBytes : nullptr;
     if (Dm<DM>::lr4) {
         const float *src_l = &a.gtabs->lane[0][0], *src_b = &a.gtabs->lb[0][0];
         for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
@@ -1405,13 +1496,13 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
                 if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
             if (need_prev && j0 > 0 && lane == 0) zhalo = fir_global_one(a, j0 - 1);
         } else {
-            front_direct<NPT>(a, tile, lane, z, u, zhalo);
+            front_direct<NPT>(a, tile, lane, z, u, zhalo, xs);
         }
         if (handoff_tile) handoff_wait(a, 1, a.carry_target);   // `prev` now, section states in this tile's look-back
         float E4[4] = { 0.f, 0.f, 0.f, 0.f };
         if (DM == DM_FM_LR4 && ORION_FM_ROLLED) fm_front_rolled<NPT>(a, tabs_sh, tile, lane, z, u, zhalo, E4);
         else {
-            front_map<NPT, DM>(a, tile, lane, z, u, zhalo);
+            front_map<NPT, DM>(a, tile, lane, z, u, zhalo, xs);
             if (Dm<DM>::lr4) {                           // zero-state dot product of the unrolled front
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) {
@@ -1435,8 +1526,8 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
             stamp(tile, 3);
             if (pend_tile >= 0) {
-                if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
-                else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+                if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
+                else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
                 if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
                 stamp(pend_tile, 4);
             }
@@ -1447,8 +1538,8 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         }
     }
     if (pend_tile >= 0) {
-        if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
-        else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1]);
+        if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
+        else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
         if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
     }
     if ((ORION_TRACE && a.trace) && lane == 0) {

@@ -470,7 +470,8 @@ int finalize_plan(orion_b200_block *b) {
                        b->plan.taps2.size() * sizeof(float2) +                              // + tap table
                        ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +            // + generic taps
                        sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
-                       (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float);                               // + per-lane scan tables (LR4 instance)
+                       (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +                             // + per-lane scan tables (LR4 instance)
+                       (b->plan.front == FRONT_DIRECT ? (size_t)b->plan.warps * 32 * 144 + 16 : 0);  // + transposing scratch (rate-1 blocks)
     CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, b->plan.warps, &b->ctas_per_sm));
     if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
     // FIR taps + history

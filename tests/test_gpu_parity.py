@@ -375,3 +375,9 @@ def test_overlapped_back_to_back_calls_keep_streaming_state():
     fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
     ref = np.concatenate([fm.run(dec.run(x[c * n_call:(c + 1) * n_call])) for c in range(calls)])
     assert_parity(over, ref, what="3 overlapped calls vs oracle streaming")
+    # the host-pointer entry point on the block's own stream takes the same path (copy, overlapping-capable launch, copy)
+    taps = ob.fir_lowpass_design(fs, 100e3, 38400.0)
+    ch = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_FM, fs_demod=fs / m, p0=25e3,
+                  audio_bw_hz=15e3, translate_hz=100e3)
+    host = np.concatenate([ch.run(x[c * n_call:(c + 1) * n_call]) for c in range(calls)])
+    assert bit_equal(host, over)
