@@ -6,8 +6,8 @@ for p in (ROOT, os.path.join(ROOT, "orion-sdr_b200", "python"), os.path.join(ROO
 import numpy as np, torch
 import orion_b200 as ob
 
-def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30):
-    xs = [torch.randn(n_in * (2 if in_dtype == torch.complex64 else 1), device="cuda").view(-1) for _ in range(3)]
+def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30, nbuf=3):
+    xs = [torch.randn(n_in * (2 if in_dtype == torch.complex64 else 1), device="cuda").view(-1) for _ in range(nbuf)]
     y = torch.empty(out_items * (2 if out_dtype == torch.complex64 else 1), dtype=torch.float32, device="cuda")
     st = torch.cuda.Stream()
     blk.set_stream(st.cuda_stream)
@@ -15,12 +15,12 @@ def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30
     t_end = time.perf_counter() + float(os.environ.get("WARM_S", "1.5"))      # sustained load: let the SM clock ramp up
     while time.perf_counter() < t_end:
         for i in range(30):
-            blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
+            blk.process_dev(xs[i % nbuf].data_ptr(), n_in, y.data_ptr(), out_items)
         blk.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(reps):
-        blk.process_dev(xs[i % 3].data_ptr(), n_in, y.data_ptr(), out_items)
+        blk.process_dev(xs[i % nbuf].data_ptr(), n_in, y.data_ptr(), out_items)
     e1.record(st)
     blk.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -41,3 +41,15 @@ if "rot" in which:
     bench("Rotator rate-1 (C32->C32)", ob.Rotator(1e5, 2.4e6), n, torch.complex64, n, torch.complex64, 16.0)
 if "lp" in which:
     bench("LpCascade rate-1 (f32->f32)", ob.LpCascade(48e3, 4.5e3), n, torch.float32, n, torch.float32, 8.0)
+
+# ---- the other BASELINE configs at their full sizes (parity for them: tests/test_gpu_parity.py) -------------
+if "configs" in which:
+    t2 = ob.kaiser_lowpass_taps(201, 0.01, 60.0)
+    bench("C2 rot+FIRiq201/25+SSB, 12 M @1.2 MS/s", ob.Chain(mix=ob.MIX_ROTATE, mix_freq_hz=-250e3, mix_fs=1.2e6, fir=ob.FIR_IQ, taps=t2, decim=25,
+          demod=ob.DEMOD_SSB, fs_demod=48e3, p0=0.0, audio_bw_hz=2800.0), 12_000_000, torch.complex64, 480_000, torch.float32, 8.16)
+    t3 = ob.fir_lowpass_design(384e3, 10e3, 6144.0)
+    extra = np.stack([ob.lp_biquad_design(48e3, 3e3)] * 2)
+    bench("C3 FIR63/8+AM+DC+LR4, 38.4 M @384 kS/s", ob.Chain(fir=ob.FIR_DECIM, taps=t3, decim=8, demod=ob.DEMOD_AM, fs_demod=48e3, audio_bw_hz=5e3,
+          post_sos=extra), 38_400_000, torch.complex64, 4_800_000, torch.float32, 8.5)
+    bench("C4 FirDecimator 1023/32, 100 M @100 MS/s", ob.FirDecimator(100e6, 32, 450e3, 97800.0), 100_000_000, torch.complex64, 3_125_000,
+          torch.complex64, 8.25, reps=10, nbuf=2)
