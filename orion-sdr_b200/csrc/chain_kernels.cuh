@@ -1,4 +1,6 @@
-// chain_kernels.cu -- the sm_100a streaming-chain kernel family.
+#pragma once
+// chain_kernels.cuh -- the sm_100a streaming-chain kernel family (templates; instantiated per translation unit
+// by chain_inst_*.cu so the instances compile in parallel).
 //
 //   [input-rate mixer] -> [FIR, keep every M-th] -> [demod-rate oscillator] -> [demod front map]
 //   -> [recursive sections]                                       one launch, one pass over HBM.
@@ -1549,75 +1551,16 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     }
 }
 
-// ----------------------------------------------------------------------------------------------
-// host-side launcher
-// ----------------------------------------------------------------------------------------------
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 
 template <int FRONT, int R, int U, int SP = 0, int DM = -1>
 static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM>; }
 
-// sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, a DEMOD_* kind, DM_LR4 + kind
-chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
-    if (front == FRONT_DIRECT) {                          // rate-1 blocks: 16 items per lane straight from global memory
-        switch (dm) {
-            case DEMOD_NONE: return kptr<FRONT_DIRECT, 16, 1, 0, DEMOD_NONE>();                  // Rotator, NcoMixer
-            case DM_LR4 + DEMOD_FM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_FM>();    // FmQuadratureDemod
-            case DM_LR4 + DEMOD_PM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_PM>();    // PmQuadratureDemod
-            case DM_LR4 + DEMOD_F32: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_F32>();  // LpCascade
-        }
-        return kptr<FRONT_DIRECT, 16, 1>();
-    }
-    if (front == FRONT_GLOBAL) return kptr<FRONT_GLOBAL, 8, 1>();
-    if (sp == 1 && R == 8 && U == 1) {
-        if (dm == DEMOD_NONE) return kptr<FRONT_STAGED, 8, 1, 1, DEMOD_NONE>();
-        if (dm == DM_FM_LR4) return kptr<FRONT_STAGED, 8, 1, 1, DM_FM_LR4>();
-        if (dm == DEMOD_AM) return kptr<FRONT_STAGED, 8, 1, 1, DEMOD_AM>();                      // C3: sections stay generic
-        return kptr<FRONT_STAGED, 8, 1, 1, -1>();
-    }
-#ifndef ORION_ONLY_HOT_SHAPES
-    if (U == 1) {
-        switch (R) {
-            case 8: return kptr<FRONT_STAGED, 8, 1>();
-            case 4: return kptr<FRONT_STAGED, 4, 1>();
-            case 2: return kptr<FRONT_STAGED, 2, 1>();
-            case 1: return kptr<FRONT_STAGED, 1, 1>();
-        }
-    } else if (U == 2) {
-        switch (R) {
-            case 8: return kptr<FRONT_STAGED, 8, 2>();
-            case 4: return kptr<FRONT_STAGED, 4, 2>();
-            case 2: return kptr<FRONT_STAGED, 2, 2>();
-            case 1: return kptr<FRONT_STAGED, 1, 2>();
-        }
-    }
-#endif
-    return nullptr;
-}
-
-cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads * warps, dyn_smem);
-}
-
-cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
-                                size_t dyn_smem, cudaStream_t stream, int overlap) {
-    // serial debug mode: one warp walks the tiles in order
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(args.serial ? kThreads : kThreads * warps);
-    cfg.dynamicSmemBytes = dyn_smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = overlap ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k, args, tmap);
-}
+// one getter per translation unit (nullptr: no such instance there)
+chain_kernel_t get_kernel_hot(int front, int dm);           // fixed decimate-by-8 geometry (SP = 1) + FRONT_GLOBAL
+chain_kernel_t get_kernel_direct(int dm);                   // rate-1 blocks
+chain_kernel_t get_kernel_staged_u1(int R);                 // generic staged instances, even M
+chain_kernel_t get_kernel_staged_u2(int R);                 // generic staged instances, odd M
 
 }  // namespace orion
 

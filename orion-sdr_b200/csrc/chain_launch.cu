@@ -1,0 +1,50 @@
+// Kernel selection, occupancy set-up and launch of the chain kernel family (instances: chain_inst_*.cu).
+#include "chain_args.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+namespace orion {
+
+typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
+chain_kernel_t get_kernel_hot(int front, int dm);
+chain_kernel_t get_kernel_direct(int dm);
+chain_kernel_t get_kernel_staged_u1(int R);
+chain_kernel_t get_kernel_staged_u2(int R);
+
+// sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, a DEMOD_* kind, DM_LR4 + kind
+chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
+    if (front == FRONT_DIRECT) return get_kernel_direct(dm);
+    if (front == FRONT_GLOBAL) return get_kernel_hot(front, dm);
+    if (sp == 1 && R == 8 && U == 1) return get_kernel_hot(front, dm);
+    if (U == 1) return get_kernel_staged_u1(R);
+    if (U == 2) return get_kernel_staged_u2(R);
+    return nullptr;
+}
+
+cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, kThreads * warps, dyn_smem);
+}
+
+cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
+                                size_t dyn_smem, cudaStream_t stream, int overlap) {
+    // serial debug mode: one warp walks the tiles in order
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(args.serial ? kThreads : kThreads * warps);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, args, tmap);
+}
+
+}  // namespace orion

@@ -2,7 +2,7 @@
 // design-time math restated on the host, launch planning, and the host<->device plumbing.
 //
 // No CPU fallback lives here: every process() call ends in a launch of the sm_100a chain
-// kernel (chain_kernels.cu); without a usable CUDA device the constructors fail.
+// kernel (chain_kernels.cuh); without a usable CUDA device the constructors fail.
 #include "../../include/orion_b200.h"
 #include "chain_args.h"
 
@@ -417,7 +417,7 @@ struct orion_b200_block {
     int *d_err = nullptr;
     int *h_err = nullptr;                 // pinned
     int *d_err_ext = nullptr;             // a channel bank's shared watchdog word (not owned)
-    unsigned int *d_handoff = nullptr;    // hand-over counters between consecutive calls (chain_kernels.cu)
+    unsigned int *d_handoff = nullptr;    // hand-over counters between consecutive calls (chain_kernels.cuh)
     unsigned int calls_since_reset = 0;
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
@@ -448,7 +448,7 @@ int finalize_plan(orion_b200_block *b) {
     CK(cudaSetDevice(b->device));
     if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
-    // shape / demodulator specialisations of the kernel family (chain_kernels.cu, Geo<SP> and Dm<DM>)
+    // shape / demodulator specialisations of the kernel family (chain_kernels.cuh, Geo<SP> and Dm<DM>)
     int sp = 0, dm = -1;
     const bool lr4_only = b->secs.size() == 2 && b->secs[0].type == SEC_BIQUAD && b->secs[1].type == SEC_BIQUAD &&
                           b->secs[0].post_op == OP_NONE && b->secs[1].post_op == OP_NONE;
