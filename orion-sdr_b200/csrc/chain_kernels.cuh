@@ -730,6 +730,10 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 #ifndef ORION_FIR_PACKED
 #define ORION_FIR_PACKED 1
 #endif
+#ifndef ORION_FIR_Q_UNROLL
+#define ORION_FIR_Q_UNROLL 1  // unroll factor of the FIR's loop over sample pairs (4 = full for the decimate-by-8 shape)
+#endif
+constexpr int kFirQUnroll = ORION_FIR_Q_UNROLL;
 #ifndef ORION_FM_ROLLED
 #define ORION_FM_ROLLED 0     // 1: the FM front of a lane is one rolled loop (small code); 0: unrolled over the lane's items
 #endif
@@ -746,7 +750,7 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 #endif
 
 #if ORION_FIR_PACKED
-template <int R, int U, int SP>
+template <int R, int U, int SP, int QU>
 DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
     typedef Geo<SP> GE;
     f32x2 acc[U][R];                                 // (re, im) of every output, one packed register pair each
@@ -760,7 +764,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
     const int blk_bytes = Mb * 8;
     const unsigned char *row_own = smem + (size_t)lane * pitch;
     const int npairs = Mb >> 1;
-#pragma unroll 1
+#pragma unroll QU
     for (int q = 0; q < npairs; ++q) {
         const int off_q = (Mb - 2 - 2 * q) * 8;
         // sliding window of sample pairs (x[s], x[s+1]), each sample a packed (re, im) pair:
@@ -809,7 +813,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
 }
 
 #else
-template <int R, int U, int SP>
+template <int R, int U, int SP, int QU>
 DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
     float2 acc[U][R];
 #pragma unroll
@@ -1486,7 +1490,9 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         if (FRONT == FRONT_STAGED) {
             if (!tile_is_interior(a, tile)) stage_load_generic(a, tile, stage, lane);
             if (a.mix != MIX_NONE) stage_mix(a, tile, stage, lane);
-            fir_staged<R, U, SP>(a, stage, taps_sh, lane, z);
+            // the FIR-only instance affords the fully unrolled pair loop (loads hoisted across pairs); with a post phase
+            // behind it the smaller rolled body wins (instruction cache)
+            fir_staged<R, U, SP, (SP == 1 && DM == DEMOD_NONE) ? 4 : kFirQUnroll>(a, stage, taps_sh, lane, z);
             if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, g_sh, tile * kThreads - HRc, j0 - 1, lane);
             __syncwarp();                               // every lane is done with the slot: refill it
             stamp(tile, 2);
