@@ -41,6 +41,8 @@ namespace orion {
 // loops unroll and every shared-memory offset folds into the instruction.
 template <int SP> struct Geo { static constexpr bool fixed = false; static constexpr int Mb = 0, HR = 0, P_pad = 0, pitch = 0; };
 template <> struct Geo<1> { static constexpr bool fixed = true; static constexpr int Mb = 8, HR = 1, P_pad = 8, pitch = 528; };
+// SP = 2: the decimate-by-32, <= 1024-tap shape (C4: R = 4, Mb = 32, eight halo rows, 32 tap steps, 1040-byte rows)
+template <> struct Geo<2> { static constexpr bool fixed = true; static constexpr int Mb = 32, HR = 8, P_pad = 32, pitch = 1040; };
 // Demodulator specialisation.  DM = -1: demodulator kind and section structure are launch arguments;
 // DM = DEMOD_NONE (0): C32 out, no sections; DM = DM_FM_LR4: FM discriminator followed by exactly one group of
 // two biquads (the LR4 of fm.rs:27) and nothing else -- the C1 chain.
@@ -779,6 +781,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
         const float2 *tp0 = ORION_TAPS + (size_t)q * P_pad;
         const float2 *tp1 = ORION_TAPS + (size_t)(npairs + q) * P_pad;     // U == 2 only
         const unsigned char *rb = row_own + pitch + off_q;
+#pragma unroll (GE::fixed ? 2 : 1)
         for (int rr = 0; rr < HR; ++rr, rb += pitch) {
             // all loads of this row first (R LDS.128 + R*U broadcast LDS.64), then 2*R*R*U packed FMAs
             // in an order that touches every accumulator once per tap: dependent FMAs are R apart
@@ -1563,7 +1566,7 @@ template <int FRONT, int R, int U, int SP = 0, int DM = -1>
 static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM>; }
 
 // one getter per translation unit (nullptr: no such instance there)
-chain_kernel_t get_kernel_hot(int front, int dm);           // fixed decimate-by-8 geometry (SP = 1) + FRONT_GLOBAL
+chain_kernel_t get_kernel_hot(int front, int sp, int dm);   // fixed geometries (SP = 1, 2) + FRONT_GLOBAL
 chain_kernel_t get_kernel_direct(int dm);                   // rate-1 blocks
 chain_kernel_t get_kernel_staged_u1(int R);                 // generic staged instances, even M
 chain_kernel_t get_kernel_staged_u2(int R);                 // generic staged instances, odd M

@@ -8,7 +8,7 @@
 namespace orion {
 
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
-chain_kernel_t get_kernel_hot(int front, int dm);
+chain_kernel_t get_kernel_hot(int front, int sp, int dm);
 chain_kernel_t get_kernel_direct(int dm);
 chain_kernel_t get_kernel_staged_u1(int R);
 chain_kernel_t get_kernel_staged_u2(int R);
@@ -16,8 +16,9 @@ chain_kernel_t get_kernel_staged_u2(int R);
 // sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, a DEMOD_* kind, DM_LR4 + kind
 chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
     if (front == FRONT_DIRECT) return get_kernel_direct(dm);
-    if (front == FRONT_GLOBAL) return get_kernel_hot(front, dm);
-    if (sp == 1 && R == 8 && U == 1) return get_kernel_hot(front, dm);
+    if (front == FRONT_GLOBAL) return get_kernel_hot(front, 0, dm);
+    if (sp == 1 && R == 8 && U == 1) return get_kernel_hot(front, 1, dm);
+    if (sp == 2 && R == 4 && U == 1 && dm == DEMOD_NONE) return get_kernel_hot(front, 2, dm);
     if (U == 1) return get_kernel_staged_u1(R);
     if (U == 2) return get_kernel_staged_u2(R);
     return nullptr;

@@ -458,6 +458,9 @@ int finalize_plan(orion_b200_block *b) {
         if (b->demod == DEMOD_NONE) dm = DEMOD_NONE;
         else if (b->demod == DEMOD_FM && lr4_only) dm = 100 + DEMOD_FM;              // DM_LR4 + kind
         else if (b->demod == DEMOD_AM) dm = DEMOD_AM;
+    } else if (b->plan.front == FRONT_STAGED && b->plan.R == 4 && b->plan.U == 1 && b->plan.Mb == 32 && b->plan.HR == 8 &&
+               b->plan.P_pad == 32 && b->plan.row_pitch == 1040 && b->demod == DEMOD_NONE && b->mix == MIX_NONE) {
+        sp = 2; dm = DEMOD_NONE;                                                     // C4 shape, FIR alone
     } else if (b->plan.front == FRONT_DIRECT) {
         if (b->demod == DEMOD_NONE) dm = DEMOD_NONE;
         else if ((b->demod == DEMOD_FM || b->demod == DEMOD_PM || b->demod == DEMOD_F32) && lr4_only) dm = 100 + b->demod;
