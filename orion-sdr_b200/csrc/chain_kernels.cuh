@@ -363,7 +363,7 @@ DEV bool read_link(const uint4 *src, unsigned epoch, float (&v)[D]) {
 // non-zero in f32: tiles further back contribute exactly nothing, so for fast-decaying groups
 // (the LR4 biquads) the look-back reads a few aggregates -- published one whole tile earlier,
 // because the section phase of a tile runs one loop iteration behind its front -- and never waits
-// for an inclusive value; slow poles (the DC blocker) use the classic chained form.
+// for an inclusive value; slow poles (the DC blocker) chain through one inclusive value per block of tiles.
 template <int D>
 DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&sin)[D]) {
     const GroupParam &G = hot->grp[g];
@@ -376,9 +376,16 @@ DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int
     int dist0 = 0;                                   // predecessor distance of lane 0 in this window
     int window = 0;
     float Mw[D * D];                                 // Ac^(T * 32 * window), only used past the first window
+    // Slow poles (no truncation): a FIXED recipe, so that the sum has the same shape in every run.  Tiles are dealt
+    // round-robin in blocks of gridDim.x; tile t takes the aggregates of its p = t mod gridDim.x predecessors of the
+    // same block and the INCLUSIVE value of the last tile of the previous block (or the state carried into the call),
+    // which was published about one block-time earlier.
+    const int p_blk = (int)(tile % (long long)gridDim.x);
     for (;;) {
         const long long idx = base - lane;
-        const bool beyond = (dist0 + lane) >= depth;      // weight is exactly zero from here on
+        const int delta = dist0 + lane;                   // predecessor distance, 0-based
+        const bool beyond = agg_only ? (delta >= depth)   // weight is exactly zero from here on
+                                     : (delta > p_blk);   // past the designated inclusive predecessor
         const TileLink *lk = a.links + (idx >= 0 ? idx : 0) * kMaxGroups + g;
         float pa[D], pi[D];
 #pragma unroll
@@ -390,9 +397,12 @@ DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int
             if (beyond || idx < 0) {       // virtual terminators: zero weight / the state carried in
                 ready = true;
                 incl = true;
-            } else {
-                incl = agg_only ? false : read_link<D>(lk->incl, a.epoch, pi);
-                ready = incl || read_link<D>(lk->agg, a.epoch, pa);
+            } else if (agg_only || delta < p_blk) {
+                incl = false;
+                ready = read_link<D>(lk->agg, a.epoch, pa);
+            } else {                       // delta == p_blk: the designated inclusive predecessor
+                incl = read_link<D>(lk->incl, a.epoch, pi);
+                ready = incl;
             }
             const unsigned incl_mask = __ballot_sync(FULLMASK, incl);
             const unsigned ready_mask = __ballot_sync(FULLMASK, ready);
