@@ -96,6 +96,8 @@ extern "C" {
     pub fn orion_b200_fir_lowpass_iq_create(num_taps: usize, cutoff_norm: f32, stopband_db: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_fir_lowpass_iq_create_taps(taps: *const f32, ntaps: usize, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_fir_lowpass_iq_filter_aligned(b: *mut orion_b200_block, io: *mut orion_b200_c32, n: usize) -> c_int;
+    pub fn orion_b200_half_cosine_mf_taps(sps: usize, taps: *mut f32, cap: usize) -> usize;
+    pub fn orion_b200_half_cosine_mf_create(sps: usize, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_rotator_create(freq_hz: f32, fs: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_rotator_usb_create(freq_hz: f32, fs: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_nco_mixer_create(freq_hz: f32, fs: f32, out: *mut *mut orion_b200_block) -> c_int;

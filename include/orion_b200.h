@@ -102,6 +102,11 @@ int orion_b200_fir_lowpass_iq_create_taps(const float *taps, size_t ntaps, orion
  * (host pointer), same length, group delay compensated. */
 int orion_b200_fir_lowpass_iq_filter_aligned(orion_b200_block *b, orion_b200_c32 *io, size_t n);
 
+/* HalfCosineMf::new + one push() per input sample, src/dsp/fir.rs:317-376 (PSK31 matched filter).
+ * C32 -> C32, sps taps, unit energy.  `..._taps` is the design alone [host-only]; returns the tap count. */
+size_t orion_b200_half_cosine_mf_taps(size_t sps, float *taps, size_t cap);
+int orion_b200_half_cosine_mf_create(size_t sps, orion_b200_block **out);
+
 /* Rotator::new + rotate_block, src/dsp/rotator.rs:16-24,74-84.  C32 -> C32. */
 int orion_b200_rotator_create(float freq_hz, float fs, orion_b200_block **out);
 /* Rotator + mix_usb_block, src/dsp/rotator.rs:88-94.  C32 -> f32. */

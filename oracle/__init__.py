@@ -104,6 +104,8 @@ def lib():
     sig("oo_cw_demod_new", vp, f, f, f)
     sig("oo_cw_demod_set_gain", None, vp, f)
     sig("oo_get_state", sz, vp, vp, sz)
+    sig("oo_half_cosine_taps", sz, sz, vp, sz)
+    sig("oo_half_cosine_mf_new", vp, sz)
     sig("oo_fm_mod_new", vp, f, f, f)
     sig("oo_pm_mod_new", vp, f, f, f)
     sig("oo_am_mod_new", vp, f, f, f, f)
@@ -397,6 +399,21 @@ class CwEnvelopeDemod(Block):
 
     def set_gain(self, g):
         lib().oo_cw_demod_set_gain(self._h, g)
+
+
+def half_cosine_taps(sps) -> np.ndarray:                # src/dsp/fir.rs:325-346
+    n = lib().oo_half_cosine_taps(int(sps), None, 0)
+    t = np.zeros(n, np.float32)
+    lib().oo_half_cosine_taps(int(sps), _ptr(t), n)
+    return t
+
+
+class HalfCosineMf(Block):                            # src/dsp/fir.rs:317-376 (push per sample)
+    In = np.complex64
+    Out = np.complex64
+
+    def __init__(self, sps):
+        super().__init__(lib().oo_half_cosine_mf_new(int(sps)))
 
 
 # ---- modulators, f32 -> c32 (src/modulate/*.rs; SURVEY.md 8(f) row 1, CPU oracle only) ----

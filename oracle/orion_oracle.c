@@ -169,7 +169,8 @@ float oo_atan2_approx(float y, float x) {
 enum {
     K_FIR_LOWPASS = 1, K_FIR_DECIM, K_FIR_IQ, K_ROTATOR, K_NCO, K_BIQUAD, K_LP_CASCADE,
     K_LP_DC_CASCADE, K_DC_BLOCKER, K_FM, K_PM, K_AM, K_SSB, K_CW,
-    K_MOD_FM, K_MOD_PM, K_MOD_AM, K_MOD_SSB, K_MOD_CW      /* f32 -> c32; SURVEY.md 8(f) row 1 */
+    K_MOD_FM, K_MOD_PM, K_MOD_AM, K_MOD_SSB, K_MOD_CW,     /* f32 -> c32; SURVEY.md 8(f) row 1 */
+    K_HCMF                                                 /* HalfCosineMf, SURVEY.md 8(f) row 2 */
 };
 
 typedef struct { float *taps; float *delay; size_t len, idx; } fir_real;     /* fir.rs:7-12 */
@@ -490,6 +491,32 @@ void oo_cw_demod_set_gain(oo_block *b, float g) { b->gain = g; }
 
 /* ---- reset --------------------------------------------------------------- */
 
+/* ---- HalfCosineMf, src/dsp/fir.rs:317-376: split delay lines, y[n] = sum_t taps[t] x[n-t], unfused, t ascending ---- */
+size_t oo_half_cosine_taps(size_t sps, float *taps, size_t cap) {               /* fir.rs:325-346 */
+    size_t n = sps < 1 ? 1 : sps;
+    if (!taps || cap < n) return n;
+    if (sps <= 1) { taps[0] = 1.0f; }
+    else {
+        float denom = (float)(sps - 1);
+        for (size_t i = 0; i < sps; ++i) taps[i] = 0.5f - 0.5f * cosf(OO_PI * (float)i / denom);
+    }
+    float energy = 0.0f;
+    for (size_t i = 0; i < n; ++i) energy += taps[i] * taps[i];
+    float scale = (energy > 0.0f) ? 1.0f / sqrtf(energy) : 1.0f;
+    for (size_t i = 0; i < n; ++i) taps[i] = taps[i] * scale;
+    return n;
+}
+oo_block *oo_half_cosine_mf_new(size_t sps) {
+    oo_block *b = blk_new(K_HCMF);
+    size_t n = oo_half_cosine_taps(sps, NULL, 0);
+    float *t = (float *)malloc(n * sizeof(float));
+    oo_half_cosine_taps(sps, t, n);
+    fir_real_init(&b->fi, t, n);                 /* delay_re */
+    fir_real_init(&b->fq, t, n);                 /* delay_im; both share idx (kept equal) */
+    free(t);
+    return b;
+}
+
 /* ---- modulators (f32 -> c32): the step before the path in the reference's round-trip tests ---- */
 
 /* mix_with_nco, src/dsp/nco.rs:63-66 (num-complex Mul is unfused) */
@@ -746,6 +773,24 @@ oo_work_report oo_process(oo_block *b, const void *in, size_t n_in, void *out, s
         wr.in_read = n; wr.out_written = n;
         break;
     }
+    case K_HCMF:                                             /* fir.rs:358-371 */
+        for (size_t i = 0; i < n; ++i) {
+            const size_t len = b->fi.len;
+            b->fi.delay[b->fi.idx] = cin[i].re;
+            b->fq.delay[b->fi.idx] = cin[i].im;
+            float re = 0.0f, im = 0.0f;
+            for (size_t t = 0; t < len; ++t) {
+                size_t d = (b->fi.idx + len - t) % len;
+                float w = b->fi.taps[t];
+                re += b->fi.delay[d] * w;
+                im += b->fq.delay[d] * w;
+            }
+            b->fi.idx = (b->fi.idx + 1) % len;
+            cout[i].re = re; cout[i].im = im;
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
     case K_MOD_FM: {                                         /* modulate/fm.rs:45-72 */
         float kf = OO_TAU * b->k / b->fs;
         for (size_t i = 0; i < n; ++i) {

@@ -92,6 +92,10 @@ oo_block *oo_ssb_demod_new(float fs, float bfo_hz, float audio_bw_hz);          
 oo_block *oo_cw_demod_new(float fs, float tone_hz, float env_bw_hz);            /* cw.rs:15-24 */
 void      oo_cw_demod_set_gain(oo_block *b, float g);                           /* cw.rs:25-27 */
 
+/* HalfCosineMf (src/dsp/fir.rs:317-376) as a streaming c32 -> c32 block: one push() per sample */
+size_t    oo_half_cosine_taps(size_t sps, float *taps, size_t cap);
+oo_block *oo_half_cosine_mf_new(size_t sps);
+
 /* modulators, f32 -> c32 (src/modulate/{fm,pm,am,ssb,cw}.rs) -- SURVEY.md 8(f) row 1: the step before the path in the
  * reference's round-trip tests; CPU only */
 oo_block *oo_fm_mod_new(float fs, float deviation_hz, float rf_hz);             /* modulate/fm.rs:22-75 */

@@ -20,7 +20,8 @@ constexpr int kMaxRowSamples = 128; // R * Mb limit of the shared-memory staged 
 enum : int { SEC_BIQUAD = 1, SEC_DC = 2, SEC_ONEPOLE = 3 };
 enum : int { OP_NONE = 0, OP_SQRT = 1, OP_SCALE = 2 };
 enum : int { MIX_NONE = 0, MIX_ROTATE = 1, MIX_NCO = 2 };
-enum : int { FIR_NONE = 0, FIR_DECIM = 1, FIR_IQ = 2 };
+enum : int { FIR_NONE = 0, FIR_DECIM = 1, FIR_IQ = 2,
+             FIR_IQ_UNFUSED = 3 /* FIR_IQ pairing; the bit-faithful front accumulates unfused (HalfCosineMf, fir.rs:358-371) */ };
 enum : int { DEMOD_NONE = 0, DEMOD_FM = 1, DEMOD_PM = 2, DEMOD_AM = 3, DEMOD_AM_ABS = 4,
              DEMOD_SSB = 5, DEMOD_CW = 6, DEMOD_USB = 7, DEMOD_F32 = 8 /* f32 in -> sections only */ };
 enum : int { FRONT_DIRECT = 0,   // no FIR: items are read straight from global memory

@@ -892,6 +892,13 @@ DEV float2 fir_global_one(const ChainArgs &a, long long j) {
         const float t = __ldg(a.g);
         re = re + x.x * t;
         im = im + x.y * t;
+    } else if (a.fir == FIR_IQ_UNFUSED) {
+        for (int k = 0; k < a.Lg; ++k) {
+            const float2 x = load_x_mixed(a, n - k);
+            const float t = __ldg(a.g + k);
+            re = re + x.x * t;
+            im = im + x.y * t;
+        }
     } else {
         for (int k = 0; k < a.Lg; ++k) {
             const float2 x = load_x_mixed(a, n - k);

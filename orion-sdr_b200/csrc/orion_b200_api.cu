@@ -839,6 +839,31 @@ int orion_b200_fir_lowpass_iq_create_taps(const float *taps, size_t ntaps, orion
     b->M = 1;
     return finish_create(b, out);
 }
+// HalfCosineMf::new, fir.rs:325-346: unit-energy half-cosine pulse
+size_t orion_b200_half_cosine_mf_taps(size_t sps, float *taps, size_t cap) {
+    const size_t n = sps < 1 ? 1 : sps;
+    if (!taps || cap < n) return n;
+    if (sps <= 1) taps[0] = 1.0f;
+    else {
+        const float denom = (float)(sps - 1);
+        for (size_t i = 0; i < sps; ++i) taps[i] = 0.5f - 0.5f * cosf(kPi * (float)i / denom);
+    }
+    float energy = 0.0f;
+    for (size_t i = 0; i < n; ++i) energy += taps[i] * taps[i];
+    const float scale = (energy > 0.0f) ? 1.0f / sqrtf(energy) : 1.0f;
+    for (size_t i = 0; i < n; ++i) taps[i] = taps[i] * scale;
+    return n;
+}
+int orion_b200_half_cosine_mf_create(size_t sps, orion_b200_block **out) {
+    const size_t n = orion_b200_half_cosine_mf_taps(sps, nullptr, 0);
+    std::vector<float> t(n);
+    orion_b200_half_cosine_mf_taps(sps, t.data(), n);
+    NEW_BLOCK();
+    b->fir = FIR_IQ_UNFUSED;
+    b->taps = t;
+    b->M = 1;
+    return finish_create(b, out);
+}
 int orion_b200_fir_lowpass_iq_create(size_t num_taps, float cutoff_norm, float stopband_db, orion_b200_block **out) {
     const size_t m = kaiser_len(num_taps);
     std::vector<float> t(m);

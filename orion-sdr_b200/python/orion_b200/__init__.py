@@ -124,6 +124,8 @@ def lib():
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
     sig("orion_b200_debug_set_trace", i, vp, vp)
+    sig("orion_b200_half_cosine_mf_taps", sz, sz, vp, sz)
+    sig("orion_b200_half_cosine_mf_create", i, sz, vp)
     sig("orion_b200_bank_create", i, vp, sz, vp)
     sig("orion_b200_bank_destroy", None, vp)
     sig("orion_b200_bank_reset", i, vp)
@@ -158,6 +160,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_block_process_dev", "orion_b200_block_synchronize", "orion_b200_block_set_stream",
     "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
     "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables", "orion_b200_debug_set_trace",
+    "orion_b200_half_cosine_mf_taps", "orion_b200_half_cosine_mf_create",
     "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
@@ -401,6 +404,18 @@ class FirLowpassIq(Block):                                            # src/dsp/
             raise TypeError("filter_aligned needs a contiguous complex64 vector")
         _check(lib().orion_b200_fir_lowpass_iq_filter_aligned(self._h, io.ctypes.data if io.size else None, io.size),
                self._h)
+
+
+def half_cosine_mf_taps(sps) -> np.ndarray:                           # src/dsp/fir.rs:325-346
+    n = lib().orion_b200_half_cosine_mf_taps(int(sps), None, 0)
+    t = np.zeros(n, np.float32)
+    lib().orion_b200_half_cosine_mf_taps(int(sps), t.ctypes.data, n)
+    return t
+
+
+class HalfCosineMf(Block):                                            # src/dsp/fir.rs:317-376, one push() per sample
+    def __init__(self, sps):
+        super().__init__(_mk("orion_b200_half_cosine_mf_create", int(sps)))
 
 
 class Rotator(Block):                                                 # src/dsp/rotator.rs (rotate_block)

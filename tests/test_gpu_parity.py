@@ -442,3 +442,15 @@ def test_overlapped_calls_other_blocks(kind):
         assert e < 1e-3, f"rotator drift {e:.2e} over {over.size} samples"
     else:
         assert_parity(over, ref, what=f"{kind}: 3 back-to-back calls vs oracle streaming")
+
+
+# ---- HalfCosineMf (src/dsp/fir.rs:317-376) ---------------------------------------------
+@pytest.mark.parametrize("sps,n", [(32, 40_000), (1, 1000), (256, 100_001)])
+def test_half_cosine_mf(sps, n):
+    x = noise_c64(n, seed=sps)
+    a, b = run_pair(ob.HalfCosineMf(sps), oracle.HalfCosineMf(sps), x, np.complex64)
+    assert_parity(a, b, what="staged")
+    g = ob.HalfCosineMf(sps)
+    g.set_option(ob.OPT_FIR_GLOBAL, 1)
+    a2, _ = run_pair(g, oracle.HalfCosineMf(sps), x, np.complex64)
+    assert bit_equal(a2, b), "reference-order (unfused) matched filter must be bit-identical"

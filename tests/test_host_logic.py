@@ -280,3 +280,11 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"\boracle\b|orion_oracle|np_oracle", txt):
                         bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("sps", [0, 1, 2, 32, 255, 1024])
+def test_half_cosine_taps_match_oracle(sps):
+    a, b = ob.half_cosine_mf_taps(sps), oracle.half_cosine_taps(sps)
+    assert a.size == b.size == max(sps, 1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert abs(float(np.sum(a.astype(np.float64) ** 2)) - 1.0) < 1e-5
