@@ -11,7 +11,10 @@ namespace orion {
 
 constexpr int kThreads     = 32;    // lanes per (warp) tile: one tile = 32 * NPT outputs
 constexpr int kWarpsPerCta = 8;     // default warps per CTA; they share a ring of staged-tile slots
-constexpr int kMaxWarpsPerCta = 16;    // __launch_bounds__(512, 1): 128 registers per thread, 16 warps per SM
+#ifndef ORION_MAX_WARPS
+#define ORION_MAX_WARPS 16
+#endif
+constexpr int kMaxWarpsPerCta = ORION_MAX_WARPS;   // __launch_bounds__(32 * this, 1): 16 -> 128 registers per thread
 constexpr int kMaxStages   = 12;    // slots in the ring
 constexpr int kMaxSections = 8;     // recursive sections per chain (LR4 = 2, LpDc = 3, + post sections)
 constexpr int kMaxTapTable = 2560;  // float capacity of the polyphase tap table held in the parameter bank
