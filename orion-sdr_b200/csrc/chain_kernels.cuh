@@ -5,19 +5,21 @@
 //   [input-rate mixer] -> [FIR, keep every M-th] -> [demod-rate oscillator] -> [demod front map]
 //   -> [recursive sections]                                       one launch, one pass over HBM.
 //
-// Work decomposition (DESIGN.md "kernel"): the output stream is cut into WARP TILES of
-// 32*NPT items.  A CTA is one warp (up to 12 resident per SM for the C1 shape); it takes tiles in
-// ticket order (persistent, dynamic), and every lane owns NPT = R*U CONSECUTIVE output items, so
+// Work decomposition: the output stream is cut into WARP TILES of 32*NPT items.
+// One persistent CTA of up to 16 warps per SM; the CTA's tiles (static round-robin over the grid) are taken by
+// its warps in ticket order, and every lane owns NPT = R*U CONSECUTIVE output items, so
 //   * the polyphase FIR slides an R-deep register window over the staged input (each staged
 //     sample is read once per lane and reused R times),
 //   * the discriminator needs one neighbour value per lane (a shuffle),
 //   * every recursive section is a per-lane serial recursion (the reference's exact arithmetic)
 //     stitched together by a warp-level state-space scan and an inter-tile decoupled look-back.
-// There is no block-level barrier anywhere: a warp that waits (TMA, look-back) stalls alone.
-// Input staging: one cp.async.bulk.tensor (TMA) per interior tile into a padded row layout,
-// issued for the NEXT tile as soon as the FIR of the current one has consumed the buffer, so the
-// load overlaps the demodulator / section / store phase; edge tiles (FIR history, ragged tail)
-// use a cooperative loader into the same layout.
+// There is no block-level barrier in the steady state: a warp that waits (TMA, look-back) stalls alone.
+// Input staging: one cp.async.bulk.tensor (TMA) per interior tile into a slot of a ring shared by the CTA's
+// warps (padded row layout); the warp that has run the FIR on a slot refills it at once with the tile NS
+// places ahead; edge tiles (FIR history, ragged tail) use a cooperative loader into the same layout.
+// Rate-1 blocks (FRONT_DIRECT) move whole warp tiles with lane-consecutive 16-byte accesses through a per-warp
+// transposing scratch instead.  Consecutive launches of a block may overlap (programmatic dependent launch);
+// what one call hands to the next is guarded by two counters (handoff_wait / handoff_signal).
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (FMA only where written).
 #include "chain_args.h"
