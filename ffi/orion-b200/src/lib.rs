@@ -77,6 +77,18 @@ impl<In, Out> GpuBlock<In, Out> {
     pub fn take_error(&mut self) -> Option<Error> {
         self.last_error.take()
     }
+    /// The complete streaming state as an opaque blob (what `Clone` gives the CPU blocks).
+    pub fn snapshot(&mut self) -> Result<Vec<u8>, Error> {
+        let n = unsafe { sys::orion_b200_block_snapshot_size(self.h) };
+        let mut buf = vec![0u8; n];
+        let st = unsafe { sys::orion_b200_block_snapshot(self.h, buf.as_mut_ptr() as *mut c_void, n) };
+        if st == sys::ORION_B200_OK { Ok(buf) } else { Err(status_to_error(st, self.h)) }
+    }
+    /// Restore a blob taken from a block built with the same constructor arguments.
+    pub fn restore(&mut self, blob: &[u8]) -> Result<(), Error> {
+        let st = unsafe { sys::orion_b200_block_restore(self.h, blob.as_ptr() as *const c_void, blob.len()) };
+        if st == sys::ORION_B200_OK { Ok(()) } else { Err(status_to_error(st, self.h)) }
+    }
     pub fn raw(&mut self) -> *mut sys::orion_b200_block {
         self.h
     }

@@ -253,6 +253,14 @@ int orion_b200_block_set_option(orion_b200_block *b, int option, double value);
  * modulo 2^24); [4 ..] recursive-section states, 2 per section in section order (8 sections). */
 size_t orion_b200_block_get_state(orion_b200_block *b, float *state, size_t cap);
 
+/* Checkpoint / resume: the complete streaming state of a block (FIR history, oscillator phase and counters,
+ * discriminator `prev`, section states) as an opaque blob.  The reference's blocks are plain data and derive
+ * Clone (fm.rs:10, iir.rs:4,43,89, rotator.rs:7, fir.rs:176): snapshot + restore into a block built with the
+ * same constructor arguments is that clone.  Both calls drain the block's stream first. */
+size_t orion_b200_block_snapshot_size(const orion_b200_block *b);
+int    orion_b200_block_snapshot(orion_b200_block *b, void *buf, size_t cap);
+int    orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size);
+
 /* number of kernels this block has launched since creation (for bench accounting) [host-only] */
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b);
 

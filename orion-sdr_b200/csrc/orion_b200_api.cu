@@ -1349,6 +1349,70 @@ size_t orion_b200_block_get_state(orion_b200_block *b, float *state, size_t cap)
     return n;
 }
 
+// ---- checkpoint / resume: the block's complete streaming state as an opaque blob ----------------------------
+// (the reference's blocks are plain data and derive Clone: fm.rs:10, iir.rs:4,43,89, rotator.rs:7, fir.rs:176)
+namespace {
+struct SnapshotHeader {
+    uint32_t magic, version;
+    uint32_t fir, demod, mix, nsec;
+    uint64_t M, ntaps, hist_len;
+    unsigned long long k_pre, k_post;
+    unsigned long long pre_step, pre_phase0, pre_k0, post_step, post_phase0, post_k0;
+    float pre_w[3], post_w[3];
+    uint32_t pre_on, post_on;
+};
+const uint32_t kSnapMagic = 0x4F423230u;      // "OB20"
+}  // namespace
+
+size_t orion_b200_block_snapshot_size(const orion_b200_block *b) {
+    if (!b) return 0;
+    return sizeof(SnapshotHeader) + sizeof(CarryState) + b->hist_cap * sizeof(float2);
+}
+int orion_b200_block_snapshot(orion_b200_block *b, void *buf, size_t cap) {
+    if (!b || !buf) return ORION_B200_ERR_INVALID;
+    if (cap < orion_b200_block_snapshot_size(b)) return fail(b, ORION_B200_ERR_INVALID, "snapshot buffer too small");
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    SnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = kSnapMagic; h.version = 1;
+    h.fir = (uint32_t)b->fir; h.demod = (uint32_t)b->demod; h.mix = (uint32_t)b->mix; h.nsec = (uint32_t)b->secs.size();
+    h.M = b->M; h.ntaps = b->taps.size(); h.hist_len = b->hist_cap;
+    h.k_pre = b->k_pre; h.k_post = b->k_post;
+    h.pre_step = b->pre.step; h.pre_phase0 = b->pre.phase0; h.pre_k0 = b->pre.k0;
+    h.post_step = b->post.step; h.post_phase0 = b->post.phase0; h.post_k0 = b->post.k0;
+    h.pre_w[0] = b->pre.wre; h.pre_w[1] = b->pre.wim; h.pre_w[2] = b->pre.amp_delta;
+    h.post_w[0] = b->post.wre; h.post_w[1] = b->post.wim; h.post_w[2] = b->post.amp_delta;
+    h.pre_on = b->pre.on; h.post_on = b->post.on;
+    char *p = (char *)buf;
+    memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    CK(cudaMemcpy(p, b->d_carry[b->pp], sizeof(CarryState), cudaMemcpyDeviceToHost)); p += sizeof(CarryState);
+    if (b->hist_cap) CK(cudaMemcpy(p, b->d_hist[b->pp], b->hist_cap * sizeof(float2), cudaMemcpyDeviceToHost));
+    return ORION_B200_OK;
+}
+int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) {
+    if (!b || !buf || size < sizeof(SnapshotHeader)) return ORION_B200_ERR_INVALID;
+    SnapshotHeader h;
+    memcpy(&h, buf, sizeof(h));
+    if (h.magic != kSnapMagic || h.version != 1) return fail(b, ORION_B200_ERR_INVALID, "not a snapshot of this library version");
+    if (h.fir != (uint32_t)b->fir || h.demod != (uint32_t)b->demod || h.mix != (uint32_t)b->mix || h.nsec != b->secs.size() ||
+        h.M != b->M || h.ntaps != b->taps.size() || h.hist_len != b->hist_cap ||
+        size < sizeof(h) + sizeof(CarryState) + h.hist_len * sizeof(float2))
+        return fail(b, ORION_B200_ERR_INVALID, "snapshot was taken from a block of a different shape");
+    int st = reset_state(b);                              // drains the stream, zeroes the hand-over counters
+    if (st != ORION_B200_OK) return st;
+    b->k_pre = h.k_pre; b->k_post = h.k_post;
+    b->pre.step = h.pre_step; b->pre.phase0 = h.pre_phase0; b->pre.k0 = h.pre_k0;
+    b->post.step = h.post_step; b->post.phase0 = h.post_phase0; b->post.k0 = h.post_k0;
+    b->pre.wre = h.pre_w[0]; b->pre.wim = h.pre_w[1]; b->pre.amp_delta = h.pre_w[2];
+    b->post.wre = h.post_w[0]; b->post.wim = h.post_w[1]; b->post.amp_delta = h.post_w[2];
+    b->pre.on = h.pre_on != 0; b->post.on = h.post_on != 0;
+    const char *p = (const char *)buf + sizeof(h);
+    CK(cudaMemcpy(b->d_carry[b->pp], p, sizeof(CarryState), cudaMemcpyHostToDevice)); p += sizeof(CarryState);
+    if (b->hist_cap) CK(cudaMemcpy(b->d_hist[b->pp], p, b->hist_cap * sizeof(float2), cudaMemcpyHostToDevice));
+    return ORION_B200_OK;
+}
+
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b) { return b ? b->launches : 0; }
 
 // debug: per-tile SM clock stamps (8 x int64 per tile, device pointer; NULL disables)

@@ -123,6 +123,9 @@ def lib():
     sig("orion_b200_block_set_option", i, vp, i, d)
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
+    sig("orion_b200_block_snapshot_size", sz, vp)
+    sig("orion_b200_block_snapshot", i, vp, vp, sz)
+    sig("orion_b200_block_restore", i, vp, vp, sz)
     sig("orion_b200_debug_set_trace", i, vp, vp)
     sig("orion_b200_half_cosine_mf_taps", sz, sz, vp, sz)
     sig("orion_b200_half_cosine_mf_create", i, sz, vp)
@@ -161,6 +164,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_block_set_option", "orion_b200_block_get_state", "orion_b200_block_launch_count",
     "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables", "orion_b200_debug_set_trace",
     "orion_b200_half_cosine_mf_taps", "orion_b200_half_cosine_mf_create",
+    "orion_b200_block_snapshot_size", "orion_b200_block_snapshot", "orion_b200_block_restore",
     "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
@@ -344,6 +348,16 @@ class Block:
         s = np.zeros(n, np.float32)
         lib().orion_b200_block_get_state(self._h, s.ctypes.data, n)
         return s
+
+    def snapshot(self) -> bytes:
+        """The block's complete streaming state (the reference's `Clone`)."""
+        n = lib().orion_b200_block_snapshot_size(self._h)
+        buf = C.create_string_buffer(n)
+        _check(lib().orion_b200_block_snapshot(self._h, buf, n), self._h)
+        return buf.raw
+
+    def restore(self, blob: bytes) -> None:
+        _check(lib().orion_b200_block_restore(self._h, blob, len(blob)), self._h)
 
     def set_trace(self, d_ptr: int):
         _check(lib().orion_b200_debug_set_trace(self._h, C.c_void_p(d_ptr)), self._h)

@@ -454,3 +454,33 @@ def test_half_cosine_mf(sps, n):
     g.set_option(ob.OPT_FIR_GLOBAL, 1)
     a2, _ = run_pair(g, oracle.HalfCosineMf(sps), x, np.complex64)
     assert bit_equal(a2, b), "reference-order (unfused) matched filter must be bit-identical"
+
+
+# ---- checkpoint / resume (the reference's blocks are Clone) -------------------------------------------------------
+@pytest.mark.parametrize("kind", ["c1_chain", "ssb", "am", "fir_iq", "rotator"])
+def test_snapshot_restore_continues_the_stream_bit_for_bit(kind):
+    n = 120_000
+    if kind == "c1_chain":
+        taps = ob.fir_lowpass_design(2.4e6, 100e3, 38400.0)
+        mk = lambda: ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=8, demod=ob.DEMOD_FM, fs_demod=3e5, p0=25e3,
+                              audio_bw_hz=15e3, translate_hz=100e3)
+        x = fm_iq(2 * n, 2.4e6)
+    elif kind == "ssb":
+        mk, x = (lambda: ob.SsbProductDemod(48e3, 1.5e3, 2800.0)), ssb_iq(2 * n, 48e3, f_bfo=1.5e3)
+    elif kind == "am":
+        mk, x = (lambda: ob.AmEnvelopeDemod(48e3, 5e3)), am_iq(2 * n, 48e3)
+    elif kind == "fir_iq":
+        mk, x = (lambda: ob.FirLowpassIq(81, 0.1, 60.0)), noise_c64(2 * n, seed=5)
+    else:
+        mk, x = (lambda: ob.Rotator(1.5e3, 48e3)), noise_c64(2 * n, seed=6)
+    a = mk()
+    a.run(x[:n])
+    blob = a.snapshot()
+    tail_a = a.run(x[n:])
+    b = mk()
+    b.run(x[:777])                         # some unrelated history that restore must wipe
+    b.restore(blob)
+    tail_b = b.run(x[n:])
+    assert bit_equal(tail_a, tail_b)
+    with pytest.raises(ob.OrionB200Error):
+        ob.LpCascade(48e3, 4.5e3).restore(blob)          # a block of a different shape refuses the blob
