@@ -77,3 +77,35 @@ def test_fm_pm_am_tone_snr_thresholds():                      # tests/unit/fm.rs
     assert _snr_db_at(y[n:], FS, 1e3) > 24.0
     y = orion_sdr.AmEnvelopeDemod(FS, 5e3, abs_approx=True).process(am_iq(2 * n, FS, tones=(1e3,), sigma=0.0))
     assert _snr_db_at(y[n:], FS, 1e3) > 20.0
+
+
+# ---- the reference's round-trip tests (tests/roundtrip/*.rs, python/tests/test_roundtrip.py:25-123): the reference's own
+# ---- modulators (CPU restatement in the oracle -- the step BEFORE the path) feeding the GPU demodulators of the shim ----
+def _real_tone(fs, f_hz, n, amp):                             # tests/roundtrip/helpers.rs:19-23
+    k = np.arange(n, dtype=np.float32)
+    return (np.float32(amp) * np.sin(np.float32(2 * np.pi) * np.float32(f_hz) * k / np.float32(fs))).astype(np.float32)
+
+
+def test_roundtrips_with_reference_modulators():
+    import oracle
+    n = 32_768
+    iq = oracle.FmPhaseAccumMod(FS, 2_500.0, 0.0).run(_real_tone(FS, 1_000.0, n, 0.5))          # roundtrip/fm.rs:11-27
+    assert _snr_db_at(orion_sdr.FmQuadratureDemod(FS, 2_500.0, 5_000.0).process(iq)[n // 4:], FS, 1_000.0) > 20.0
+    iq = oracle.AmDsbMod(FS, 0.0, 0.8, 0.5).run(_real_tone(FS, 1_000.0, n, 0.5))                  # roundtrip/am.rs:11-27
+    assert _snr_db_at(orion_sdr.AmEnvelopeDemod(FS, 5_000.0).process(iq)[n // 4:], FS, 1_000.0) > 24.0
+    assert _snr_db_at(orion_sdr.AmEnvelopeDemod(FS, 5_000.0, abs_approx=True).process(iq)[n // 4:], FS, 1_000.0) > 20.0
+    iq = oracle.PmDirectPhaseMod(FS, 0.9, 0.0).run(_real_tone(FS, 900.0, n, 0.5))                 # roundtrip/pm.rs:11-27
+    assert _snr_db_at(orion_sdr.PmQuadratureDemod(FS, 0.9, 5_000.0).process(iq)[n // 4:], FS, 900.0) > 18.0
+    iq = oracle.SsbPhasingMod(FS, 2_800.0, 1_500.0, 0.0, True).run(_real_tone(FS, 1_200.0, n, 0.4))   # roundtrip/ssb.rs:10-33
+    assert _snr_db_at(orion_sdr.SsbProductDemod(FS, 1_500.0, 2_800.0).process(iq)[int(0.120 * FS):], FS, 1_200.0) > 18.0
+    nk = 24_000                                                                                   # roundtrip/cw.rs:10-48
+    key = ((np.arange(nk, dtype=np.float32) * np.float32(5.0) / np.float32(FS)) % np.float32(1.0) < 0.5).astype(np.float32)
+    iq = oracle.CwKeyedMod(FS, 700.0, 3.0, 3.0).run(key)
+    audio = orion_sdr.CwEnvelopeDemod(FS, 700.0, 300.0).process(iq)
+    skip = int(0.100 * FS)
+    a, ke = audio[skip:], key[skip:]
+    rms = lambda v: float(np.sqrt(np.mean(np.square(v, dtype=np.float64))))
+    assert 20.0 * np.log10(rms(a[ke > 0.5]) / (rms(a[ke <= 0.5]) + 1e-12)) > 14.0
+    # and every one of them equals the oracle's demodulator on the same IQ within the parity bar
+    from signals import assert_parity
+    assert_parity(audio, oracle.CwEnvelopeDemod(FS, 700.0, 300.0).run(iq), what="cw roundtrip")
