@@ -116,6 +116,10 @@ extern "C" {
     pub fn orion_b200_ssb_demod_create(fs: f32, bfo_hz: f32, audio_bw_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_cw_demod_create(sample_rate: f32, tone_hz: f32, env_bw_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_cw_demod_set_gain(b: *mut orion_b200_block, gain: f32) -> c_int;
+    pub fn orion_b200_am_mod_create(fs: f32, rf_hz: f32, carrier_level: f32, modulation_index: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_am_mod_set_clamp(b: *mut orion_b200_block, on: c_int) -> c_int;
+    pub fn orion_b200_pm_mod_create(fs: f32, kp_rad_per_unit: f32, rf_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_mod_set_gain(b: *mut orion_b200_block, gain: f32) -> c_int;
     pub fn orion_b200_chain_create(spec: *const orion_b200_chain_spec, out: *mut *mut orion_b200_block) -> c_int;
 
     pub fn orion_b200_bank_create(specs: *const orion_b200_chain_spec, n_channels: usize, out: *mut *mut orion_b200_bank) -> c_int;

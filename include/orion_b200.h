@@ -138,6 +138,14 @@ int orion_b200_ssb_demod_create(float fs, float bfo_hz, float audio_bw_hz, orion
 int orion_b200_cw_demod_create(float sample_rate, float tone_hz, float env_bw_hz, orion_b200_block **out); /* cw.rs:15-24 */
 int orion_b200_cw_demod_set_gain(orion_b200_block *b, float gain);                                   /* cw.rs:25-27 */
 
+/* Modulators, f32 audio -> C32 IQ (next-row scope: the step before the path in the reference's round-trip tests).
+ * AmDsbMod (src/modulate/am.rs:10-120) and PmDirectPhaseMod (src/modulate/pm.rs:10-47); the FM / SSB / CW modulators
+ * are not built on the GPU. */
+int orion_b200_am_mod_create(float fs, float rf_hz, float carrier_level, float modulation_index, orion_b200_block **out);
+int orion_b200_am_mod_set_clamp(orion_b200_block *b, int on);                                         /* am.rs:34-36 */
+int orion_b200_pm_mod_create(float fs, float kp_rad_per_unit, float rf_hz, orion_b200_block **out);
+int orion_b200_mod_set_gain(orion_b200_block *b, float gain);
+
 /* ------------------------------------------------------------------------------------
  * Fused chain: [input-rate mixer] -> [FIR, decimate by m] -> [demodulator] -> [extra IIR
  * sections], one streaming kernel.  It is what a user composes today by running the

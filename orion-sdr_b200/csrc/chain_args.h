@@ -26,7 +26,10 @@ enum : int { MIX_NONE = 0, MIX_ROTATE = 1, MIX_NCO = 2 };
 enum : int { FIR_NONE = 0, FIR_DECIM = 1, FIR_IQ = 2,
              FIR_IQ_UNFUSED = 3 /* FIR_IQ pairing; the bit-faithful front accumulates unfused (HalfCosineMf, fir.rs:358-371) */ };
 enum : int { DEMOD_NONE = 0, DEMOD_FM = 1, DEMOD_PM = 2, DEMOD_AM = 3, DEMOD_AM_ABS = 4,
-             DEMOD_SSB = 5, DEMOD_CW = 6, DEMOD_USB = 7, DEMOD_F32 = 8 /* f32 in -> sections only */ };
+             DEMOD_SSB = 5, DEMOD_CW = 6, DEMOD_USB = 7, DEMOD_F32 = 8 /* f32 in -> sections only */,
+             MOD_AM = 9, MOD_PM = 10 /* modulators: f32 in -> C32 out, no sections (modulate/am.rs, pm.rs) */ };
+__host__ __device__ inline bool kind_f32_in(int d) { return d == DEMOD_F32 || d == MOD_AM || d == MOD_PM; }
+__host__ __device__ inline bool kind_c32_out(int d) { return d == DEMOD_NONE || d == MOD_AM || d == MOD_PM; }
 enum : int { FRONT_DIRECT = 0,   // no FIR: items are read straight from global memory
              FRONT_STAGED = 1,   // polyphase FIR on a TMA / cooperatively staged shared-memory tile
              FRONT_GLOBAL = 2 }; // any-shape FIR evaluated from global memory (large M, huge tap sets)
@@ -127,7 +130,8 @@ struct ChainArgs {
     // demodulator
     int   demod;
     int   translate;             // FM: multiply by conj(post phasor) first (fm.rs:34-37)
-    float k, k1, k2;
+    float k, k1, k2;             // FM/PM: k | AM_ABS: k1, k2 | MOD_AM: carrier level, modulation index, gain (k = clamp flag) | MOD_PM: k1 = kp, k2 = gain
+    float k3;
     NcoParam post;               // demod-rate oscillator (FM translate / SSB BFO / USB mix)
     // recursive sections
     int   nsec;

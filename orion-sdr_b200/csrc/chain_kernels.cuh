@@ -946,9 +946,10 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
     const long long j0 = tile * (long long)(kThreads * NPT);
     const long long jt = j0 + (long long)lane * NPT;
     const int demod = Dm<DM>::demod(a);
-    const bool is_c32_in = demod != DEMOD_F32;
+    const bool is_c32_in = !kind_f32_in(demod);
     const bool need_prev = demod == DEMOD_FM || demod == DEMOD_PM;
-    const bool post_osc = (demod == DEMOD_FM && a.translate) || demod == DEMOD_SSB || demod == DEMOD_USB;
+    const bool post_osc = (demod == DEMOD_FM && a.translate) || demod == DEMOD_SSB || demod == DEMOD_USB ||
+                          demod == MOD_AM || demod == MOD_PM;
     const bool full = jt + NPT <= a.n_out;
 
     if (is_c32_in && demod != DEMOD_NONE) {
@@ -1022,7 +1023,29 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         }
     }
 
-    if (demod == DEMOD_NONE) {
+    if (demod == MOD_AM || demod == MOD_PM) {             // modulators: u[] holds the audio, z[] receives the IQ
+        float2 p = make_float2(1.f, 0.f);
+        const float2 w = make_float2(a.post.wre, a.post.wim);
+        const unsigned long long kp0 = a.post.kbase + (unsigned long long)jt + 1ull;
+        p = nco_unit(a.post, kp0);
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const float2 r = scale2(p, nco_amp(a.post, kp0 + i));
+            if (demod == MOD_AM) {                         // modulate/am.rs:61-118: m = (cl + mi*x) [clamped] * g; out = m * rot.next()
+                float m = a.k1 + a.k2 * u[i];
+                if (a.k != 0.f) m = fminf(fmaxf(m, -1.0f), 1.0f);
+                m = m * a.k3;
+                z[i] = make_float2(m * r.x, m * r.y);
+            } else {                                       // modulate/pm.rs:37-47: base = (cos phi, sin phi) * gain; mix_with_nco (unfused)
+                const float phi = a.k1 * u[i];
+                const float br = cosf(phi) * a.k2, bi = sinf(phi) * a.k2;
+                z[i] = make_float2(br * r.x - bi * r.y, br * r.y + bi * r.x);
+            }
+            p = cmul_fma(p, w);
+        }
+    }
+
+    if (kind_c32_out(demod)) {
         float2 *out = reinterpret_cast<float2 *>(a.out);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && (NPT % 2 == 0);
         bool done = false;
@@ -1060,7 +1083,7 @@ DEV void end_of_call_duties(const ChainArgs &a, int lane) {
     if (lane == 0) {
         if (!need_prev || a.n_out == 0) a.carry_out->prev = __ldcg(&a.carry_in->prev);
         for (int s = 0; s < kMaxSections; ++s)
-            if (s >= a.nsec || a.n_out == 0 || a.demod == DEMOD_NONE) a.carry_out->sec[s] = __ldcg(&a.carry_in->sec[s]);
+            if (s >= a.nsec || a.n_out == 0 || kind_c32_out(a.demod)) a.carry_out->sec[s] = __ldcg(&a.carry_in->sec[s]);
     }
 }
 
@@ -1264,7 +1287,7 @@ DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[
     const long long jt = j0 + (long long)lane * NPT;
     const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
     const bool whole = NPT == 16 && j0 + kThreads * NPT <= a.n_out;             // warp-uniform: the warp tile is full
-    if (a.demod != DEMOD_F32) {
+    if (!kind_f32_in(a.demod)) {
         const float2 *in = reinterpret_cast<const float2 *>(a.in);
         const bool al16 = ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0) && (NPT % 2 == 0);
         bool done = false;
@@ -1435,7 +1458,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     }
 
     const bool need_prev = demod == DEMOD_FM || demod == DEMOD_PM;
-    const bool has_sections = demod != DEMOD_NONE;
+    const bool has_sections = !kind_c32_out(demod);
     if ((ORION_TRACE && a.trace) && threadIdx.x == 0) {                  // debug: kernel span in %globaltimer ns
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));

@@ -385,7 +385,7 @@ struct orion_b200_block {
     size_t M = 1;
     int demod = DEMOD_NONE;
     int translate = 0;
-    float k = 0.f, k1 = 0.f, k2 = 0.f;
+    float k = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f;
     float fs_demod = 0.f;
     std::vector<SecParam> secs;
     Osc pre, post;
@@ -570,8 +570,8 @@ int init_device_side(orion_b200_block *b) {
 
 int finish_create(orion_b200_block *b, orion_b200_block **out) {
     if (b->secs.size() > (size_t)kMaxSections) { delete b; return ORION_B200_ERR_UNSUPPORTED; }
-    b->in_item = (b->demod == DEMOD_F32) ? ORION_B200_ITEM_F32 : ORION_B200_ITEM_C32;
-    b->out_item = (b->demod == DEMOD_NONE) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
+    b->in_item = kind_f32_in(b->demod) ? ORION_B200_ITEM_F32 : ORION_B200_ITEM_C32;
+    b->out_item = kind_c32_out(b->demod) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
     int st = init_device_side(b);
     if (st != ORION_B200_OK) {
         // keep the message reachable through a static buffer, then drop the half-built block
@@ -657,7 +657,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.row_shift = -1;
     for (int sh = 0; sh < 20; ++sh) if ((1 << sh) == b->plan.row_samples) a.row_shift = sh;
     a.nstages = b->opt_serial ? std::min(b->plan.nstages, 1) : b->plan.nstages;
-    a.demod = b->demod; a.translate = b->translate; a.k = b->k; a.k1 = b->k1; a.k2 = b->k2;
+    a.demod = b->demod; a.translate = b->translate; a.k = b->k; a.k1 = b->k1; a.k2 = b->k2; a.k3 = b->k3;
     a.post = b->post.param(b->k_post);
     a.nsec = nsec;
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
@@ -1048,6 +1048,34 @@ int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block 
         for (size_t s = 0; s < spec->n_post; ++s) b->secs.push_back(sec_biquad(spec->post_sos + 5 * s));
     }
     return finish_create(b, out);
+}
+
+// ---- modulators (next-row scope): f32 audio -> C32 IQ ------------------------------------
+int orion_b200_am_mod_create(float fs, float rf_hz, float carrier_level, float modulation_index, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // AmDsbMod::new, modulate/am.rs:21-30
+    b->demod = MOD_AM;
+    b->k = 0.f; b->k1 = carrier_level; b->k2 = modulation_index; b->k3 = 1.0f;
+    b->post.set(rf_hz, fs, 0);
+    return finish_create(b, out);
+}
+int orion_b200_am_mod_set_clamp(orion_b200_block *b, int on) {      // modulate/am.rs:34-36
+    if (!b || b->demod != MOD_AM) return b ? fail(b, ORION_B200_ERR_INVALID, "not an AM modulator") : ORION_B200_ERR_INVALID;
+    b->k = on ? 1.0f : 0.0f;
+    return ORION_B200_OK;
+}
+int orion_b200_pm_mod_create(float fs, float kp_rad_per_unit, float rf_hz, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // PmDirectPhaseMod::new, modulate/pm.rs:17-23
+    b->demod = MOD_PM;
+    b->k1 = kp_rad_per_unit; b->k2 = 1.0f;
+    b->post.set(rf_hz, fs, 0);
+    return finish_create(b, out);
+}
+int orion_b200_mod_set_gain(orion_b200_block *b, float gain) {      // set_gain, modulate/am.rs:31-33, pm.rs:24-26
+    if (!b) return ORION_B200_ERR_INVALID;
+    if (b->demod == MOD_AM) b->k3 = gain;
+    else if (b->demod == MOD_PM) b->k2 = gain;
+    else return fail(b, ORION_B200_ERR_INVALID, "not a modulator");
+    return ORION_B200_OK;
 }
 
 // ---- channel bank --------------------------------------------------------------------------------

@@ -129,6 +129,10 @@ def lib():
     sig("orion_b200_debug_set_trace", i, vp, vp)
     sig("orion_b200_half_cosine_mf_taps", sz, sz, vp, sz)
     sig("orion_b200_half_cosine_mf_create", i, sz, vp)
+    sig("orion_b200_am_mod_create", i, f, f, f, f, vp)
+    sig("orion_b200_am_mod_set_clamp", i, vp, i)
+    sig("orion_b200_pm_mod_create", i, f, f, f, vp)
+    sig("orion_b200_mod_set_gain", i, vp, f)
     sig("orion_b200_bank_create", i, vp, sz, vp)
     sig("orion_b200_bank_destroy", None, vp)
     sig("orion_b200_bank_reset", i, vp)
@@ -165,6 +169,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_debug_fir_plan", "orion_b200_debug_group_tables", "orion_b200_debug_set_trace",
     "orion_b200_half_cosine_mf_taps", "orion_b200_half_cosine_mf_create",
     "orion_b200_block_snapshot_size", "orion_b200_block_snapshot", "orion_b200_block_restore",
+    "orion_b200_am_mod_create", "orion_b200_am_mod_set_clamp", "orion_b200_pm_mod_create", "orion_b200_mod_set_gain",
     "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
@@ -529,6 +534,26 @@ class CwEnvelopeDemod(Block):                                         # src/demo
 
     def set_gain(self, g):
         _check(lib().orion_b200_cw_demod_set_gain(self._h, g), self._h)
+
+
+# ---- src/modulate (next-row scope; the FM / SSB / CW modulators are not built on the GPU) ---------------
+class AmDsbMod(Block):                                                # src/modulate/am.rs:10-120
+    def __init__(self, fs, rf_hz, carrier_level, modulation_index):
+        super().__init__(_mk("orion_b200_am_mod_create", fs, rf_hz, carrier_level, modulation_index))
+
+    def set_clamp(self, on):
+        _check(lib().orion_b200_am_mod_set_clamp(self._h, int(bool(on))), self._h)
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_mod_set_gain(self._h, g), self._h)
+
+
+class PmDirectPhaseMod(Block):                                        # src/modulate/pm.rs:10-47
+    def __init__(self, sample_rate, kp_rad_per_unit, rf_hz):
+        super().__init__(_mk("orion_b200_pm_mod_create", sample_rate, kp_rad_per_unit, rf_hz))
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_mod_set_gain(self._h, g), self._h)
 
 
 # ---- fused chain ----------------------------------------------------------------------------------

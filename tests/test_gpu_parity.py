@@ -484,3 +484,33 @@ def test_snapshot_restore_continues_the_stream_bit_for_bit(kind):
     assert bit_equal(tail_a, tail_b)
     with pytest.raises(ob.OrionB200Error):
         ob.LpCascade(48e3, 4.5e3).restore(blob)          # a block of a different shape refuses the blob
+
+
+# ---- modulators on the GPU (next-row scope: AmDsbMod, PmDirectPhaseMod) ---------------------------------------------
+@pytest.mark.parametrize("rf", [0.0, 1.5e3])
+def test_am_pm_modulators(rf):
+    fs, n = 48e3, 65_536
+    audio = (0.5 * np.sin(2 * np.pi * 1e3 * np.arange(n) / fs)).astype(np.float32)
+    a, b = run_pair(ob.AmDsbMod(fs, rf, 0.8, 0.5), oracle.AmDsbMod(fs, rf, 0.8, 0.5), audio, np.complex64)
+    assert_parity(a, b, what="AmDsbMod")
+    g, r = ob.AmDsbMod(fs, rf, 0.8, 0.9), oracle.AmDsbMod(fs, rf, 0.8, 0.9)
+    g.set_clamp(True); r.set_clamp(True); g.set_gain(0.7); r.set_gain(0.7)
+    a, b = run_pair(g, r, (3.0 * audio).astype(np.float32), np.complex64)
+    assert_parity(a, b, what="AmDsbMod clamped")
+    a, b = run_pair(ob.PmDirectPhaseMod(fs, 0.9, rf), oracle.PmDirectPhaseMod(fs, 0.9, rf), audio, np.complex64)
+    assert_parity(a, b, what="PmDirectPhaseMod")
+    # streaming: two calls continue the carrier phase
+    g, r = ob.PmDirectPhaseMod(fs, 0.9, rf), oracle.PmDirectPhaseMod(fs, 0.9, rf)
+    a, b = stream_pair(g, r, audio, np.complex64, [10_001, n - 10_001])
+    assert_parity(a, b, what="PmDirectPhaseMod two calls")
+
+
+def test_gpu_modulator_into_gpu_demodulator_roundtrip():
+    fs, n = 48e3, 32_768
+    k = np.arange(n, dtype=np.float32)
+    audio = (np.float32(0.5) * np.sin(np.float32(2 * np.pi) * np.float32(1e3) * k / np.float32(fs))).astype(np.float32)
+    iq = ob.AmDsbMod(fs, 0.0, 0.8, 0.5).run(audio)
+    y = ob.AmEnvelopeDemod(fs, 5e3).run(iq)[n // 4:]
+    t = np.arange(y.size) / fs
+    p = lambda f: np.abs(np.sum(y * np.exp(-2j * np.pi * f * t))) ** 2
+    assert 10 * np.log10(p(1e3) / max(p(730.0), 1e-30)) > 24.0          # tests/roundtrip/am.rs:26
