@@ -959,20 +959,21 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         if (post_osc) p = nco_unit(a.post, kp0);
         if (demod == DEMOD_FM && a.translate) {
             // z = in * conj(p)   (num-complex Mul, unfused; fm.rs:49)
-#pragma unroll
             // the unit phasor is enough: |p| = 1 + O(1e-5) (rotator.rs renormalises every 1024 steps) scales
-            // both discriminator arguments alike, and atan2_approx only sees their ratio
+            // both discriminator arguments alike, and atan2_approx only sees their ratio.
+            // The phasor of the item before the lane's first one is one step back, p * conj(w): lane 0 needs it for the
+            // item before the tile (every lane computes it -- four flops -- so that the warp stays converged).
+            {
+                const float2 pb = make_float2(fmaf(p.x, w.x, p.y * w.y), fmaf(p.y, w.x, -(p.x * w.y)));
+                const float cr = pb.x, ci = -pb.y;
+                zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
+            }
+#pragma unroll
             for (int i = 0; i < NPT; ++i) {
                 const float cr = p.x, ci = -p.y;
                 z[i] = make_float2(z[i].x * cr - z[i].y * ci, z[i].x * ci + z[i].y * cr);
                 p = cmul_fma(p, w);
             }
-            if (j0 > 0 && lane == 0) {
-                const float2 ph = nco_unit(a.post, a.post.kbase + (unsigned long long)j0);
-                const float cr = ph.x, ci = -ph.y;
-                zhalo = make_float2(zhalo.x * cr - zhalo.y * ci, zhalo.x * ci + zhalo.y * cr);
-            }
-            __syncwarp();
         }
         if (need_prev) {
             float2 prev = shfl_up2(z[NPT - 1], 1);
