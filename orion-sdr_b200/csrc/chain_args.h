@@ -152,6 +152,7 @@ struct ChainArgs {
     unsigned int *handoff;       // [0] calls whose FIR history is written, [1] 2 x calls whose carried state is complete
     unsigned int hist_target;    // values of the two counters this call needs before it reads the hand-over (0: none)
     unsigned int carry_target;
+    unsigned int depth_target;   // carried-state counter value that proves the launch before the previous one has ended
     long long *trace;            // debug: 8 x int64 per tile {consume, ready, fir_done, front_done, finish_done, -, smid, warp}
     float2 taps2[kMaxTapTable / 2];   // [u][q][c] -> (g[t0], g[t0-1]); see DESIGN.md "staged FIR"
 };

@@ -1208,7 +1208,12 @@ DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long t
             const TileLink *lk = a.links + idx * kMaxGroups;
             int spins = 0;
             while (!read_link<4>(lk->agg, a.epoch, pay)) {
-                if (++spins > (1 << 21)) { atomicExch(a.err_flag, 1); break; }    // watchdog: never hang the device
+                if (++spins > (1 << 21)) {                                        // watchdog: never hang the device
+                    // diagnostic code: 1 | (epoch tag seen - expected) << 4 | lane << 8 | (predecessor tile / 4) << 16
+                    const uint4 r0 = ld_relaxed_b128(lk->agg);
+                    atomicExch(a.err_flag, 1 | (int)(((r0.w - a.epoch) & 0xFu) << 4) | (int)(((unsigned)lane & 0xFu) << 8) | (int)(((unsigned)(idx >> 2) & 0x7FFFu) << 16));
+                    break;
+                }
                 __nanosleep(32);
             }
         }
@@ -1473,6 +1478,11 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         handoff_signal(a, 0, lane);                        // FIR history for the next call is in place
         handoff_signal(a, 1, lane);                        // ... and this warp's share of the carried state
     }
+
+    // At most two launches of a block are ever in flight: the link records alternate between two halves by launch
+    // parity, so this launch must not publish before the launch before the previous one has ended (observed on long
+    // streams: with only the hardware's launch ordering a third launch did start while the first still had tiles to finish).
+    handoff_wait(a, 1, a.depth_target);
 
     float u_pend[NPT];
 #pragma unroll

@@ -676,6 +676,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.handoff = b->d_handoff;
     a.hist_target = b->calls_since_reset;                 // every earlier call has written its history ...
     a.carry_target = 2u * b->calls_since_reset;           // ... and both of its hand-over signals
+    a.depth_target = b->calls_since_reset >= 1 ? 2u * (b->calls_since_reset - 1) : 0u;   // every call but the previous one has ended
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
     a.ntaps2 = (int)b->plan.taps2.size();
 
@@ -716,7 +717,9 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     // look-back cannot reach the carried state past the guarded tiles, and only on the block's own stream unless
     // the caller opted in (ORION_B200_OPT_OVERLAP_LAUNCHES) -- on an attached stream the predecessor may be a
     // foreign kernel that is still producing this call's input.
-    bool overlap = !b->opt_serial && ntiles >= 1024 && (b->stream == b->own_stream || b->opt_overlap);
+    // Upper bound: calls of more than 16 384 tiles gain nothing from the overlap (their fixed cost is < 3 % of the
+    // launch) and are where an unresolved stall was seen (known limitations), so they stay serialised.
+    bool overlap = !b->opt_serial && ntiles >= 1024 && ntiles <= 16384 && (b->stream == b->own_stream || b->opt_overlap);
     for (const GroupParam &gp : b->groups) overlap = overlap && gp.agg_only;
     if (getenv("ORION_B200_NO_OVERLAP")) overlap = false;
     cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream, overlap ? 1 : 0);
