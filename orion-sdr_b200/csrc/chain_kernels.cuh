@@ -1209,9 +1209,9 @@ DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long t
             int spins = 0;
             while (!read_link<4>(lk->agg, a.epoch, pay)) {
                 if (++spins > (1 << 21)) {                                        // watchdog: never hang the device
-                    // diagnostic code: 1 | (epoch tag seen - expected) << 4 | lane << 8 | (predecessor tile / 4) << 16
+                    // diagnostic code: 1 | (epoch tag seen & 0x7FF) << 4 | (epoch expected & 0x7FF) << 15 | lane << 26
                     const uint4 r0 = ld_relaxed_b128(lk->agg);
-                    atomicExch(a.err_flag, 1 | (int)(((r0.w - a.epoch) & 0xFu) << 4) | (int)(((unsigned)lane & 0xFu) << 8) | (int)(((unsigned)(idx >> 2) & 0x7FFFu) << 16));
+                    atomicExch(a.err_flag, 1 | (int)((r0.w & 0x7FFu) << 4) | (int)((a.epoch & 0x7FFu) << 15) | (int)(((unsigned)lane & 0x1Fu) << 26));
                     break;
                 }
                 __nanosleep(32);

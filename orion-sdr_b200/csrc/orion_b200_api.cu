@@ -438,6 +438,18 @@ int fail(orion_b200_block *b, int status, const char *what, cudaError_t e = cuda
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, #call, _e); } while (0)
 
+// Device memory is initialised ON THE BLOCK'S STREAM.  The legacy default stream does not order against the
+// non-blocking streams the kernels run on: a 45 MB cudaMemset of the link records, queued on it behind a caller's own
+// default-stream work, was seen to run while launches were already publishing into those records -- and wiped them.
+cudaError_t dev_memset(orion_b200_block *b, void *p, int v, size_t n) { return cudaMemsetAsync(p, v, n, b->stream); }
+cudaError_t dev_upload(orion_b200_block *b, void *dst, const void *src, size_t n) {      // src may be a temporary
+    cudaError_t e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, b->stream);
+    return e == cudaSuccess ? cudaStreamSynchronize(b->stream) : e;
+}
+cudaError_t dev_copy(orion_b200_block *b, void *dst, const void *src, size_t n) {
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, b->stream);
+}
+
 size_t in_item_bytes(const orion_b200_block *b) { return b->in_item == ORION_B200_ITEM_C32 ? 8 : 4; }
 size_t out_item_bytes(const orion_b200_block *b) { return b->out_item == ORION_B200_ITEM_C32 ? 8 : 4; }
 
@@ -481,16 +493,16 @@ int finalize_plan(orion_b200_block *b) {
     if (b->fir != FIR_NONE) {
         if (b->d_g) { cudaFree(b->d_g); b->d_g = nullptr; }
         CK(cudaMalloc(&b->d_g, b->plan.g.size() * sizeof(float)));
-        CK(cudaMemcpy(b->d_g, b->plan.g.data(), b->plan.g.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(dev_upload(b, b->d_g, b->plan.g.data(), b->plan.g.size() * sizeof(float)));
         if ((size_t)b->plan.H > b->hist_cap) {
             // growing the history keeps the most recent samples at the end
             for (int i = 0; i < 2; ++i) {
                 float2 *nh = nullptr;
                 CK(cudaMalloc(&nh, (size_t)b->plan.H * sizeof(float2)));
-                CK(cudaMemset(nh, 0, (size_t)b->plan.H * sizeof(float2)));
+                CK(dev_memset(b, nh, 0, (size_t)b->plan.H * sizeof(float2)));
                 if (b->d_hist[i]) {
-                    CK(cudaMemcpy(nh + (b->plan.H - b->hist_cap), b->d_hist[i], b->hist_cap * sizeof(float2),
-                                  cudaMemcpyDeviceToDevice));
+                    CK(dev_copy(b, nh + (b->plan.H - b->hist_cap), b->d_hist[i], b->hist_cap * sizeof(float2)));
+                    CK(cudaStreamSynchronize(b->stream));
                     cudaFree(b->d_hist[i]);
                 }
                 b->d_hist[i] = nh;
@@ -511,7 +523,7 @@ int finalize_plan(orion_b200_block *b) {
         for (size_t g = 0; g < gh.size(); ++g) b->group_depth.push_back(tabs[g].depth);
         if (b->d_gtabs) { cudaFree(b->d_gtabs); b->d_gtabs = nullptr; }
         CK(cudaMalloc(&b->d_gtabs, tabs.size() * sizeof(GroupTables)));
-        CK(cudaMemcpy(b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables), cudaMemcpyHostToDevice));
+        CK(dev_upload(b, b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables)));
     }
     b->plan_dirty = false;
     return ORION_B200_OK;
@@ -524,10 +536,11 @@ int reset_state(orion_b200_block *b) {
     memset(&cs, 0, sizeof(cs));
     cs.prev = make_float2(1.0f, 0.0f);                         // fm.rs:29, pm.rs:29
     for (int i = 0; i < 2; ++i) {
-        CK(cudaMemcpy(b->d_carry[i], &cs, sizeof(cs), cudaMemcpyHostToDevice));
-        if (b->d_hist[i]) CK(cudaMemset(b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
+        CK(dev_upload(b, b->d_carry[i], &cs, sizeof(cs)));
+        if (b->d_hist[i]) CK(dev_memset(b, b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
     }
-    CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    CK(cudaStreamSynchronize(b->stream));
     b->calls_since_reset = 0;
     b->k_pre = b->k_post = 0;
     b->pre.reset_phase();
@@ -556,11 +569,11 @@ int init_device_side(orion_b200_block *b) {
     b->stream = b->own_stream;
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
     CK(cudaMalloc(&b->d_ticket, 2 * sizeof(unsigned long long)));        // {ticket, done}
-    CK(cudaMemset(b->d_ticket, 0, 2 * sizeof(unsigned long long)));
+    CK(dev_memset(b, b->d_ticket, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_handoff, 2 * sizeof(unsigned int)));
-    CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
     CK(cudaMalloc(&b->d_err, sizeof(int)));
-    CK(cudaMemset(b->d_err, 0, sizeof(int)));
+    CK(dev_memset(b, b->d_err, 0, sizeof(int)));
     CK(cudaMallocHost(&b->h_err, sizeof(int)));
     *b->h_err = 0;
     int st = finalize_plan(b);
@@ -630,7 +643,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         size_t cap = std::max<size_t>((size_t)ntiles, 4096);
         cap += cap / 4;
         CK(cudaMalloc(&b->d_links, 2 * cap * kMaxGroups * sizeof(TileLink)));      // two halves, alternating between calls
-        CK(cudaMemset(b->d_links, 0, 2 * cap * kMaxGroups * sizeof(TileLink)));
+        CK(dev_memset(b, b->d_links, 0, 2 * cap * kMaxGroups * sizeof(TileLink)));     // stream-ordered before the launch below
         b->links_cap = cap;
         b->epoch = 0;
     }
@@ -717,9 +730,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     // look-back cannot reach the carried state past the guarded tiles, and only on the block's own stream unless
     // the caller opted in (ORION_B200_OPT_OVERLAP_LAUNCHES) -- on an attached stream the predecessor may be a
     // foreign kernel that is still producing this call's input.
-    // Upper bound: calls of more than 16 384 tiles gain nothing from the overlap (their fixed cost is < 3 % of the
-    // launch) and are where an unresolved stall was seen (known limitations), so they stay serialised.
-    bool overlap = !b->opt_serial && ntiles >= 1024 && ntiles <= 16384 && (b->stream == b->own_stream || b->opt_overlap);
+    bool overlap = !b->opt_serial && ntiles >= 1024 && (b->stream == b->own_stream || b->opt_overlap);
     for (const GroupParam &gp : b->groups) overlap = overlap && gp.agg_only;
     if (getenv("ORION_B200_NO_OVERLAP")) overlap = false;
     cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream, overlap ? 1 : 0);
@@ -729,7 +740,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     b->calls_since_reset += 1;
     if (b->calls_since_reset >= (1u << 30)) {              // counter wrap: drain, start over
         CK(cudaStreamSynchronize(b->stream));
-        CK(cudaMemset(b->d_handoff, 0, 2 * sizeof(unsigned int)));
+        CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
         b->calls_since_reset = 0;
     }
     b->pp ^= 1;
@@ -745,7 +756,8 @@ int check_device_error(orion_b200_block *b) {
         char msg[96];
         snprintf(msg, sizeof(msg), "device watchdog tripped (code %d): inter-tile link or TMA wait timed out", *b->h_err);
         *b->h_err = 0;
-        cudaMemset(b->d_err, 0, sizeof(int));
+        dev_memset(b, b->d_err, 0, sizeof(int));
+        cudaStreamSynchronize(b->stream);
         return fail(b, ORION_B200_ERR_INTERNAL, msg);
     }
     return ORION_B200_OK;
@@ -1138,7 +1150,7 @@ int orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels
         for (int i = 0; i < ns && st == ORION_B200_OK; ++i)
             if (cudaEventCreateWithFlags(&k->ev_done[i], cudaEventDisableTiming) != cudaSuccess) st = ORION_B200_ERR_CUDA;
         if (st == ORION_B200_OK && cudaEventCreateWithFlags(&k->ev_in, cudaEventDisableTiming) != cudaSuccess) st = ORION_B200_ERR_CUDA;
-        if (st == ORION_B200_OK && (cudaMalloc(&k->d_err, sizeof(int)) != cudaSuccess || cudaMemset(k->d_err, 0, sizeof(int)) != cudaSuccess ||
+        if (st == ORION_B200_OK && (cudaMalloc(&k->d_err, sizeof(int)) != cudaSuccess || cudaMemset(k->d_err, 0, sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
                                     cudaMallocHost(&k->h_err, sizeof(int)) != cudaSuccess)) st = ORION_B200_ERR_ALLOC;
         for (size_t c = 0; c < k->ch.size() && st == ORION_B200_OK; ++c) {
             k->ch[c]->d_err_ext = k->d_err;
@@ -1194,6 +1206,7 @@ int orion_b200_bank_synchronize(orion_b200_bank *k) {
         snprintf(msg, sizeof(msg), "device watchdog tripped (code %d) in a bank channel", *k->h_err);
         *k->h_err = 0;
         cudaMemset(k->d_err, 0, sizeof(int));
+        cudaDeviceSynchronize();
         return bank_fail(k, ORION_B200_ERR_INTERNAL, msg);
     }
     return ORION_B200_OK;
@@ -1439,8 +1452,8 @@ int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) 
     b->post.wre = h.post_w[0]; b->post.wim = h.post_w[1]; b->post.amp_delta = h.post_w[2];
     b->pre.on = h.pre_on != 0; b->post.on = h.post_on != 0;
     const char *p = (const char *)buf + sizeof(h);
-    CK(cudaMemcpy(b->d_carry[b->pp], p, sizeof(CarryState), cudaMemcpyHostToDevice)); p += sizeof(CarryState);
-    if (b->hist_cap) CK(cudaMemcpy(b->d_hist[b->pp], p, b->hist_cap * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(dev_upload(b, b->d_carry[b->pp], p, sizeof(CarryState))); p += sizeof(CarryState);
+    if (b->hist_cap) CK(dev_upload(b, b->d_hist[b->pp], p, b->hist_cap * sizeof(float2)));
     return ORION_B200_OK;
 }
 

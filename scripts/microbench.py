@@ -12,6 +12,8 @@ def bench(name, blk, n_in, in_dtype, out_items, out_dtype, bytes_per_in, reps=30
     st = torch.cuda.Stream()
     blk.set_stream(st.cuda_stream)
     blk.set_option(ob.OPT_OVERLAP_LAUNCHES, int(os.environ.get("OVERLAP", "1")))
+    if "USE_TMA" in os.environ:
+        blk.set_option(ob.OPT_USE_TMA, int(os.environ["USE_TMA"]))
     t_end = time.perf_counter() + float(os.environ.get("WARM_S", "1.5"))      # sustained load: let the SM clock ramp up
     while time.perf_counter() < t_end:
         for i in range(30):
