@@ -514,3 +514,25 @@ def test_gpu_modulator_into_gpu_demodulator_roundtrip():
     t = np.arange(y.size) / fs
     p = lambda f: np.abs(np.sum(y * np.exp(-2j * np.pi * f * t))) ** 2
     assert 10 * np.log10(p(1e3) / max(p(730.0), 1e-30)) > 24.0          # tests/roundtrip/am.rs:26
+
+
+def test_first_long_launch_is_ordered_after_the_blocks_own_initialisation():
+    """Regression: the link records of a long call are cleared on the block's stream.  A plain cudaMemset (legacy default
+    stream) queued behind a caller's default-stream work once ran while the first launches were already publishing."""
+    import torch
+    fs, m, n = 2.4e6, 8, 40_000_000                       # 19 532 tiles: a 19 MB link array to clear at the first launch
+    x = torch.from_numpy(fm_iq(4_000_000, fs)).cuda().repeat(10)
+    taps = ob.fir_lowpass_design(fs, 100e3, 38400.0)
+    ch = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_FM, fs_demod=fs / m, p0=25e3,
+                  audio_bw_hz=15e3, translate_hz=100e3)
+    y = torch.zeros(3 * (n // m), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    junk = [torch.randn(200_000_000, device="cuda") for _ in range(6)]        # several ms of default-stream work in the queue
+    for c in range(3):
+        ch.process_dev(x.data_ptr(), n, y.data_ptr() + c * (n // m) * 4, n // m)
+    ch.synchronize()                                       # raises if a device watchdog tripped
+    del junk
+    head = y[:25_000].cpu().numpy()
+    dec = oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
+    assert_parity(head, fm.run(dec.run(x[:200_000].cpu().numpy())), what="head of the first long call")
