@@ -288,3 +288,19 @@ def test_half_cosine_taps_match_oracle(sps):
     assert a.size == b.size == max(sps, 1)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert abs(float(np.sum(a.astype(np.float64) ** 2)) - 1.0) < 1e-5
+
+
+def test_plain_c_client_compiles_links_and_runs(tmp_path):
+    """include/orion_b200.h is usable from C99 and the shared library links from a C program (tests/c_abi/host_only.c)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "host_only")
+    libdir = os.path.dirname(ob.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "host_only.c"), "-o", exe,
+                           "-L", libdir, "-lorion_b200", "-lm", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ok" in out.stdout
