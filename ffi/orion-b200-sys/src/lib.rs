@@ -150,6 +150,8 @@ extern "C" {
     pub fn orion_b200_block_set_option(b: *mut orion_b200_block, option: c_int, value: f64) -> c_int;
     pub fn orion_b200_block_get_state(b: *mut orion_b200_block, state: *mut f32, cap: usize) -> usize;
     pub fn orion_b200_block_launch_count(b: *const orion_b200_block) -> u64;
+    pub fn orion_b200_block_exact_host_ms(b: *const orion_b200_block) -> f64;
+    pub fn orion_b200_last_create_error() -> *const c_char;
     pub fn orion_b200_block_snapshot_size(b: *const orion_b200_block) -> usize;
     pub fn orion_b200_block_snapshot(b: *mut orion_b200_block, buf: *mut c_void, cap: usize) -> c_int;
     pub fn orion_b200_block_restore(b: *mut orion_b200_block, buf: *const c_void, size: usize) -> c_int;

@@ -23,6 +23,13 @@
  * H2D/D2H staging inside), `orion_b200_block_process_dev` takes DEVICE pointers
  * (16-byte aligned) and only enqueues work on the block's stream -- call
  * `orion_b200_block_synchronize` (or sync the stream you attached) before reading.
+ *
+ * Stream contract of `_process_dev`: work is enqueued on the block's stream (its own non-blocking stream, or the one
+ * attached with `orion_b200_block_set_stream`).  The block's own stream has NO ordering with the stream that produced
+ * `d_in` or will read `d_out` (the legacy default stream included): the input must be complete when the call is
+ * enqueued, and the caller synchronises before reading.  Attach your stream to get stream ordering instead.
+ * Consecutive calls on one block may overlap on the device (long calls; see ORION_B200_OPT_OVERLAP_LAUNCHES): do not
+ * hand two un-synchronised consecutive calls the same output buffer unless overwriting it in any order is acceptable.
  */
 #ifndef ORION_B200_H
 #define ORION_B200_H
@@ -60,6 +67,7 @@ typedef struct orion_b200_work_report { size_t in_read, out_written; } orion_b20
  * Library-level
  * ---------------------------------------------------------------------------------- */
 int         orion_b200_abi_version(void);                       /* [host-only] */
+const char *orion_b200_last_create_error(void);                 /* [host-only] why the last constructor on this thread failed */
 const char *orion_b200_build_info(void);                        /* [host-only] arch, flags */
 int         orion_b200_device_count(void);                      /* 0 if no driver/GPU */
 int         orion_b200_set_device(int ordinal);                 /* device for blocks created afterwards (per thread) */
@@ -254,7 +262,18 @@ int orion_b200_block_set_stream(orion_b200_block *b, void *cuda_stream);
                                            calls is still waited for).  The caller promises that the input of a call is complete
                                            when the call is enqueued (not produced by the kernel enqueued just before it).  On the
                                            block's own stream this overlap is always on: nothing foreign can be enqueued there. */
+#define ORION_B200_OPT_EXACT_NCO     5  /* oscillator arithmetic.  -1 (default): by block kind -- the reference's f32 phasor recurrence
+                                           (renormalised every 1024 steps, rotator.rs:44-61) is replayed bit for bit wherever the
+                                           ABSOLUTE phase reaches the output (Rotator, NcoMixer, mix_usb_block, SsbProductDemod,
+                                           the modulators, mixer -> FIR -> C32 / SSB chains); a closed-form 64-bit phase is used
+                                           where only phase differences or magnitudes matter (FM translate, mixer -> FIR -> FM / PM /
+                                           AM / CW).  1: replay everywhere it applies; 0: closed form everywhere (drifts from the
+                                           reference by its rounding: ~5e-2 rad after 24 M samples).  The replay is a sequential walk
+                                           on the host (~3 ns per item, orion_b200_block_exact_host_ms) plus a parallel expansion
+                                           kernel.  Select it before the first call after a reset. */
 int orion_b200_block_set_option(orion_b200_block *b, int option, double value);
+/* host milliseconds this block has spent walking the oscillator recurrence (exact mode) since creation [host-only] */
+double orion_b200_block_exact_host_ms(const orion_b200_block *b);
 
 /* Streaming-state snapshot for the parity harness.  Layout (20 floats):
  * [0..1] discriminator prev (re,im); [2..3] oscillator call counters (input-rate, demod-rate,
@@ -272,8 +291,10 @@ int    orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t siz
 /* number of kernels this block has launched since creation (for bench accounting) [host-only] */
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b);
 
-/* Debug: per-tile SM-clock stamps of the kernel's phases, 8 x int64 per tile {consume, slot ready, FIR done,
- * front done, section phase done, -, smid, warp}; d_trace is a device pointer (NULL disables). */
+/* Debug (only in a -DORION_TRACE=1 build): per-tile SM-clock stamps of the kernel's phases, 16 x int64 per tile
+ * {consume, slot ready, FIR done, front done, section phase done, globaltimer, smid, warp, refill, front end, look-back
+ * done, scan start, scan end, publish end, active mask lane 0, active mask lane 31} plus 2 trailing words {kernel start,
+ * kernel end in globaltimer ns}: size the buffer (16 * ntiles + 2) * 8 bytes.  d_trace is a device pointer (NULL disables). */
 int orion_b200_debug_set_trace(orion_b200_block *b, void *d_trace);
 
 /* Plan introspection for the host-logic tests [host-only].  info[12] = {front, R, U, Mb, O, P,

@@ -76,6 +76,8 @@ def lib():
     sig("oo_fir_lowpass_from_taps", vp, vp, sz)
     sig("oo_fir_decimator_new", vp, f, sz, f, f)
     sig("oo_fir_decimator_from_taps", vp, vp, sz, sz)
+    sig("oo_fir_decim_kept", None, vp, sz, sz, vp, sz, vp, sz, sz)
+    sig("oo_fir_iq_kept", None, vp, sz, sz, vp, sz, vp, sz, sz)
     sig("oo_fir_iq_design", vp, sz, f, f)
     sig("oo_fir_iq_from_taps", vp, vp, sz)
     sig("oo_fir_iq_group_delay", sz, vp)
@@ -255,6 +257,37 @@ class FirDecimator(Block):
         out = np.zeros(-(-x.size // self.m), self.Out)
         wr = self.process(x, out)
         return out[: wr.out_written]
+
+
+def _kept(fn_name, taps, m, x, threads=None):
+    """Outputs y[j*m] of a FRESH decimating FIR over x, evaluated directly (oo_fir_*_kept; bit-identical to the
+    loop-for-loop block).  Output ranges are spread over host threads (ctypes drops the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    t = _as(taps, np.float32)
+    x = _as(x, np.complex64)
+    m = max(int(m), 1)
+    n_out = -(-x.size // m)
+    out = np.zeros(n_out, np.complex64)
+    threads = threads or min(os.cpu_count() or 1, 16)
+    fn = getattr(lib(), fn_name)
+    step = max(-(-n_out // (threads * 4)), 1)
+
+    def work(j0):
+        j1 = min(n_out, j0 + step)
+        fn(_ptr(t), t.size, m, _ptr(x), x.size, out[j0:j1].ctypes.data, j0, j1)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(0, n_out, step)))
+    return out
+
+
+def fir_decim_kept(taps, m, x, threads=None) -> np.ndarray:
+    """== FirDecimator(taps=taps, m=m).run(x) on a fresh block, m times cheaper."""
+    return _kept("oo_fir_decim_kept", taps, m, x, threads)
+
+
+def fir_iq_kept(taps, m, x, threads=None) -> np.ndarray:
+    """== FirLowpassIq(taps=taps).run(x)[::m] on a fresh block, m times cheaper."""
+    return _kept("oo_fir_iq_kept", taps, m, x, threads)
 
 
 class FirLowpassIq(Block):

@@ -620,6 +620,49 @@ void oo_fir_iq_filter_aligned(oo_block *b, oo_c32 *io, size_t n) {
     }
 }
 
+/* ---- test accelerators: only the outputs a decimating caller keeps -------------------------
+ * FirDecimator::process (decim.rs:44-76) runs both FirLowpass filters at the INPUT rate and then keeps
+ * yi[j*m], yq[j*m]; every filter output is an independent dot product, so the kept ones can be evaluated
+ * alone, in the same accumulation order and rounding as fir_real_step above (t ascending; taps[t] pairs
+ * with x[n-1-t], taps[L-1] with x[n]; samples before the start of a FRESH block are the zeros of its delay
+ * line).  Bit-identical to the loop-for-loop path (tests/test_oracle_crosscheck.py pins that); m times
+ * cheaper, which is what lets the full-size BASELINE configurations be checked in seconds.
+ * Outputs [j0, j1) of a fresh block fed x[0, n). */
+void oo_fir_decim_kept(const float *taps, size_t L, size_t m, const oo_c32 *x, size_t n,
+                       oo_c32 *out, size_t j0, size_t j1) {
+    for (size_t j = j0; j < j1; ++j) {
+        const size_t p = j * m;                      /* index of the newest sample */
+        if (p >= n) { out[j - j0].re = 0.0f; out[j - j0].im = 0.0f; continue; }
+        float ar = 0.0f, ai = 0.0f;
+        for (size_t t = 0; t + 1 < L; ++t) {
+            if (t + 1 > p) { ar += 0.0f * taps[t]; ai += 0.0f * taps[t]; continue; }
+            const oo_c32 d = x[p - 1 - t];
+            ar += d.re * taps[t];
+            ai += d.im * taps[t];
+        }
+        ar += x[p].re * taps[L - 1];
+        ai += x[p].im * taps[L - 1];
+        out[j - j0].re = ar; out[j - j0].im = ai;
+    }
+}
+/* The same for FirLowpassIq::push (fir.rs:229-247: y[n] = sum_j taps[j] x[n-j], fused, j ascending) followed
+ * by a keep-every-m-th pick: outputs y[j*m], j in [j0, j1), of a fresh block. */
+void oo_fir_iq_kept(const float *taps, size_t L, size_t m, const oo_c32 *x, size_t n,
+                    oo_c32 *out, size_t j0, size_t j1) {
+    for (size_t j = j0; j < j1; ++j) {
+        const size_t p = j * m;
+        if (p >= n) { out[j - j0].re = 0.0f; out[j - j0].im = 0.0f; continue; }
+        float re = 0.0f, im = 0.0f;
+        for (size_t k = 0; k < L; ++k) {
+            oo_c32 d = { 0.0f, 0.0f };
+            if (k <= p) d = x[p - k];
+            re = fmaf(d.re, taps[k], re);
+            im = fmaf(d.im, taps[k], im);
+        }
+        out[j - j0].re = re; out[j - j0].im = im;
+    }
+}
+
 /* ---- Block::process ------------------------------------------------------ */
 oo_work_report oo_process(oo_block *b, const void *in, size_t n_in, void *out, size_t out_cap) {
     oo_work_report wr = { 0, 0 };

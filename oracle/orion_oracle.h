@@ -106,6 +106,13 @@ oo_block *oo_ssb_mod_new(float fs, float audio_bw_hz, float audio_if_hz, float r
 oo_block *oo_cw_mod_new(float fs, float tone_hz, float rise_ms, float fall_ms); /* modulate/cw.rs:21-102 */
 void      oo_mod_set_gain(oo_block *b, float g);
 
+/* test accelerators (see the .c): the outputs [j0, j1) a keep-every-m-th caller retains from a FRESH
+ * FirDecimator / FirLowpassIq fed x[0, n) -- bit-identical to running the block loop-for-loop */
+void oo_fir_decim_kept(const float *taps, size_t L, size_t m, const oo_c32 *x, size_t n,
+                       oo_c32 *out, size_t j0, size_t j1);
+void oo_fir_iq_kept(const float *taps, size_t L, size_t m, const oo_c32 *x, size_t n,
+                    oo_c32 *out, size_t j0, size_t j1);
+
 /* streaming-state snapshot for tests (floats; layout documented per block in the .c) */
 size_t oo_get_state(const oo_block *b, float *state, size_t cap);
 

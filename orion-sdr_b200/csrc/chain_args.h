@@ -82,8 +82,19 @@ struct NcoParam {
     unsigned long long kbase;   // k of item 0 of this call, minus 1  (k = kbase + idx + 1)
     float wre, wim;             // unit (cos, sin) of the step angle, for short in-thread recurrences
     float amp_delta;            // ln|w_f32|: |z_k| = 1 + (k mod 1024) * amp_delta (renormalised every 1024)
-    float pad;
+    int   exact;                // 1: replay the reference's f32 recurrence from the checkpoint tables below (bit-exact phasors)
+    // exact-replay mode (rotator.rs:44-61 restated; DESIGN.md "exact oscillator").  Z(c) = the phasor returned by the c-th
+    // next() since the last reset; item i of this call sees Z(kbase + i + 1).
+    const float2 *xfine;        // xfine[e] = Z(kbase + 1 + 16 e): one checkpoint per 16 items of this call (expanded on the device)
+    const float2 *xhist;        // xhist[xhist_len + i] = the phasor that was applied to item i < 0 (FIR history re-mix)
+    int   xhist_len;
+    int   xfine_len;
+    float xwre, xwim;           // the reference's own f32 step w = (cosf(phi), sinf(phi))
 };
+
+// exact-replay oscillator: one anchor per 1024 items of a call, produced by the host's sequential walk of the
+// reference recurrence; osc_expand_kernel replays from it (chain_kernels.cuh "exact-replay oscillator")
+struct OscAnchor { unsigned long long ctr; float2 z; float2 w; unsigned nsteps; unsigned pad; };
 
 struct CarryState {              // streaming state carried between process() calls (device memory)
     float2 prev;                 // discriminator previous sample (fm.rs:16, pm.rs:16)
@@ -149,10 +160,12 @@ struct ChainArgs {
     int   serial;                // debug: tiles run one after another (grid = 1)
     int  *err_flag;
     int   pdl_guard;             // tiles below this index read state handed over by the previous call (prev, look-back)
-    unsigned int *handoff;       // [0] calls whose FIR history is written, [1] 2 x calls whose carried state is complete
+    unsigned int *handoff;       // [0] calls whose FIR history is written, [1] 2 x calls whose carried state is complete,
+                                 // [2] CTAs (of all calls so far) that have run to their end
     unsigned int hist_target;    // values of the two counters this call needs before it reads the hand-over (0: none)
     unsigned int carry_target;
-    unsigned int depth_target;   // carried-state counter value that proves the launch before the previous one has ended
+    unsigned int depth_target;   // value of the CTA-done counter that proves every launch before the previous one has ended
+                                 // (all of its tiles: nobody reads its buffers or its half of the link records any more)
     long long *trace;            // debug: 8 x int64 per tile {consume, ready, fir_done, front_done, finish_done, -, smid, warp}
     float2 taps2[kMaxTapTable / 2];   // [u][q][c] -> (g[t0], g[t0-1]); see DESIGN.md "staged FIR"
 };

@@ -222,6 +222,56 @@ DEV float2 cmul_fma(float2 z, float2 w) {   // phasor advance, reference form (r
     return make_float2(fmaf(z.x, w.x, -(z.y * w.y)), fmaf(z.y, w.x, z.x * w.y));
 }
 
+// ---- exact-replay oscillator -----------------------------------------------------------------------------------
+// The reference phasor is the f32 recurrence z <- z*w with a renormalisation every 1024 steps (rotator.rs:44-61,
+// nco.rs:42-58).  Its rounding makes it drift away from any closed form (5e-2 rad after 24 M steps), which matters
+// wherever the ABSOLUTE phase reaches the output (Rotator, NcoMixer, mix_usb_block, SsbProductDemod, the modulators).
+// The sequence does not depend on the data, so the host walks the recurrence once (one checkpoint per 1024 steps,
+// orion_b200_api.cu ExactOsc), a small kernel expands the checkpoints to one per 16 items (osc_expand_kernel below),
+// and every lane replays the reference's own arithmetic from the nearest one: phasors are bit-identical.
+DEV void nco_step_exact(float2 &z, const float2 w, unsigned &ctr) {
+    z = cmul_fma(z, w);                                            // rotator.rs:46-48
+    ctr += 1u;
+    if ((ctr & 0x3FFu) == 0u) {                                    // rotator.rs:51-59: r2.sqrt().recip()
+        const float r2 = z.x * z.x + z.y * z.y;
+        const float inv = 1.0f / sqrtf(r2);
+        z.x *= inv;
+        z.y *= inv;
+    }
+}
+// Z(kbase + 1 + idx), idx >= 0: the phasor item idx of this call sees; ctr is left at kbase + 1 + idx.
+// `steps` (>= idx & 15) is the replay trip count: pass the warp maximum where the warp must stay converged.
+DEV float2 nco_exact_at(const NcoParam &p, long long idx, unsigned &ctr, int steps) {
+    long long e = idx >> 4;
+    int r = (int)(idx & 15);
+    if (e >= p.xfine_len) { e = p.xfine_len - 1; r = 0; }         // past the end of the call: the item is zero padding
+    float2 z = __ldg(p.xfine + e);
+    ctr = (unsigned)(p.kbase + 1ull + ((unsigned long long)e << 4));
+    const float2 w = make_float2(p.xwre, p.xwim);
+    for (int i = 0; i < steps; ++i) {
+        float2 zn = z;
+        unsigned cn = ctr;
+        nco_step_exact(zn, w, cn);
+        if (i < r) { z = zn; ctr = cn; }
+    }
+    return z;
+}
+DEV int warp_max_replay(long long idx) {                           // whole warp: max over lanes of idx & 15
+    return (int)__reduce_max_sync(FULLMASK, (unsigned)(idx & 15));
+}
+// the phasor that was applied to item idx < 0 when it was first consumed (FIR history re-mix)
+DEV float2 nco_exact_hist(const NcoParam &p, long long idx) {
+    const long long h = idx + p.xhist_len;
+    return h >= 0 ? __ldcg(p.xhist + h) : make_float2(1.f, 0.f);
+}
+DEV float2 nco_exact_any(const NcoParam &p, long long idx) {      // any lane, any context (slow paths)
+    unsigned ctr;
+    return idx < 0 ? nco_exact_hist(p, idx) : nco_exact_at(p, idx, ctr, (int)(idx & 15));
+}
+
+// checkpoint expansion: thread t replays up to `nsteps` steps from anchor t and writes Z(c0 + 16 e) for every e it passes
+__global__ void osc_expand_kernel(const OscAnchor *an, int n_an, float2 *fine, unsigned long long c0, long long fine_len);
+
 // input-rate mixers
 DEV float2 mix_apply(int mix, float2 x, float2 p) {
     if (mix == MIX_ROTATE)                                         // rotator.rs:74-84
@@ -297,7 +347,8 @@ DEV float2 load_x(const ChainArgs &a, long long s) {
 }
 DEV float2 load_x_mixed(const ChainArgs &a, long long s) {
     float2 x = load_x(a, s);
-    if (a.mix != MIX_NONE) x = mix_apply(a.mix, x, nco_phasor(a.pre, a.pre.kbase + (unsigned long long)s + 1ull));
+    if (a.mix != MIX_NONE)
+        x = mix_apply(a.mix, x, a.pre.exact ? nco_exact_any(a.pre, s) : nco_phasor(a.pre, a.pre.kbase + (unsigned long long)s + 1ull));
     return x;
 }
 
@@ -659,7 +710,7 @@ DEV bool tile_is_interior(const ChainArgs &a, long long tile) {
 // cooperative (whole warp) load of an edge tile -- FIR history / ragged tail -- into the staged layout.
 // Loads are issued in batches of 16 independent chunks per lane: an edge tile sits in the same ring
 // as the TMA-staged ones, so a latency-serialised loader would stall the whole CTA behind its slot.
-DEV void stage_load_generic(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
+static __device__ __noinline__ void stage_load_generic(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
     constexpr int B = 16;
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
@@ -699,7 +750,7 @@ DEV void stage_load_generic(const ChainArgs &a, long long tile, unsigned char *s
 }
 
 // in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
-DEV void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
+static __device__ __noinline__ void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
     const int cpr = a.row_samples >> 1;
@@ -710,6 +761,25 @@ DEV void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int 
         const long long s0 = row_start_sample(a, G0 + rho);
         unsigned char *rp = smem + (size_t)rho * a.row_pitch;
         float2 p = make_float2(1.f, 0.f);
+        if (a.pre.exact) {                                     // the reference recurrence itself, replayed from a checkpoint
+            const float2 wx = make_float2(a.pre.xwre, a.pre.xwim);
+            unsigned ctr = 0;
+            bool walking = false;
+            for (int cc = 0; cc < cpr; ++cc) {
+                float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
+                float2 y[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long s = s0 + 2 * cc + h;
+                    if (s < 0) p = nco_exact_hist(a.pre, s);
+                    else if (!walking) { p = nco_exact_at(a.pre, s, ctr, (int)(s & 15)); walking = true; }
+                    else nco_step_exact(p, wx, ctr);
+                    y[h] = mix_apply(a.mix, h == 0 ? make_float2(v.x, v.y) : make_float2(v.z, v.w), p);
+                }
+                *reinterpret_cast<float4 *>(rp + cc * 16) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+            }
+            continue;
+        }
         for (int cc = 0; cc < cpr; ++cc) {
             const unsigned long long k = a.pre.kbase + (unsigned long long)(s0 + 2 * cc) + 1ull;
             if ((cc & 7) == 0) p = nco_unit(a.pre, k);
@@ -956,7 +1026,7 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         float2 p = make_float2(1.f, 0.f);
         const float2 w = make_float2(a.post.wre, a.post.wim);
         const unsigned long long kp0 = a.post.kbase + (unsigned long long)jt + 1ull;
-        if (post_osc) p = nco_unit(a.post, kp0);
+        if (post_osc && !(a.post.exact && demod != DEMOD_FM)) p = nco_unit(a.post, kp0);
         if (demod == DEMOD_FM && a.translate) {
             // z = in * conj(p)   (num-complex Mul, unfused; fm.rs:49)
             // the unit phasor is enough: |p| = 1 + O(1e-5) (rotator.rs renormalises every 1024 steps) scales
@@ -1011,6 +1081,15 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         } else if (demod == DEMOD_AM_ABS) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) u[i] = fmaf(a.k1, fabsf(z[i].x), a.k2 * fabsf(z[i].y)); // am.rs:86
+        } else if ((demod == DEMOD_SSB || demod == DEMOD_USB) && a.post.exact) {
+            unsigned ctr;
+            float2 px = nco_exact_at(a.post, jt, ctr, warp_max_replay(jt));
+            const float2 wx = make_float2(a.post.xwre, a.post.xwim);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {                                                      // ssb.rs:36-37
+                u[i] = fmaf(z[i].x, px.x, z[i].y * px.y);
+                nco_step_exact(px, wx, ctr);
+            }
         } else if (demod == DEMOD_SSB || demod == DEMOD_USB) {
 #pragma unroll
             for (int i = 0; i < NPT; ++i) {                                                      // ssb.rs:36-37
@@ -1028,10 +1107,14 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
         float2 p = make_float2(1.f, 0.f);
         const float2 w = make_float2(a.post.wre, a.post.wim);
         const unsigned long long kp0 = a.post.kbase + (unsigned long long)jt + 1ull;
-        p = nco_unit(a.post, kp0);
+        unsigned ctr = 0;
+        const bool ex = a.post.exact != 0;
+        const float2 wx = make_float2(a.post.xwre, a.post.xwim);
+        if (ex) p = nco_exact_at(a.post, jt, ctr, warp_max_replay(jt));
+        else p = nco_unit(a.post, kp0);
 #pragma unroll
         for (int i = 0; i < NPT; ++i) {
-            const float2 r = scale2(p, nco_amp(a.post, kp0 + i));
+            const float2 r = ex ? p : scale2(p, nco_amp(a.post, kp0 + i));
             if (demod == MOD_AM) {                         // modulate/am.rs:61-118: m = (cl + mi*x) [clamped] * g; out = m * rot.next()
                 float m = a.k1 + a.k2 * u[i];
                 if (a.k != 0.f) m = fminf(fmaxf(m, -1.0f), 1.0f);
@@ -1042,7 +1125,8 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
                 const float br = cosf(phi) * a.k2, bi = sinf(phi) * a.k2;
                 z[i] = make_float2(br * r.x - bi * r.y, br * r.y + bi * r.x);
             }
-            p = cmul_fma(p, w);
+            if (ex) nco_step_exact(p, wx, ctr);
+            else p = cmul_fma(p, w);
         }
     }
 
@@ -1075,7 +1159,7 @@ DEV void front_map(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT
 
 // end-of-call duties that depend on the input only: the FIR history for the next call and the carried
 // state no stage of this call touches.  Run by one warp at the START of the kernel (off the tail).
-DEV void end_of_call_duties(const ChainArgs &a, int lane) {
+static __device__ __noinline__ void end_of_call_duties(const ChainArgs &a, int lane) {
     const bool need_prev = a.demod == DEMOD_FM || a.demod == DEMOD_PM;
     if (a.H > 0)
         for (int k0 = 0; k0 < a.H; k0 += kThreads)
@@ -1322,7 +1406,16 @@ DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[
             for (int i = 0; i < NPT; ++i)
                 if (jt + i < a.n_out) z[i] = __ldg(in + jt + i);
         }
-        if (a.mix != MIX_NONE) {
+        if (a.mix != MIX_NONE && a.pre.exact) {
+            unsigned ctr;
+            float2 p = nco_exact_at(a.pre, jt, ctr, warp_max_replay(jt));
+            const float2 w = make_float2(a.pre.xwre, a.pre.xwim);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {
+                z[i] = mix_apply(a.mix, z[i], p);
+                nco_step_exact(p, w, ctr);
+            }
+        } else if (a.mix != MIX_NONE) {
             const unsigned long long k0 = a.pre.kbase + (unsigned long long)jt + 1ull;
             float2 p = nco_unit(a.pre, k0);
             const float2 w = make_float2(a.pre.wre, a.pre.wim);
@@ -1366,7 +1459,7 @@ struct __align__(16) RingCtl {
     unsigned long long full[kMaxStages];     // mbarrier per slot: "the tile of this fill has landed"
     int gen[kMaxStages];                     // index of the slot's latest fill (use k may only look at fill k)
     unsigned int cons;                       // consume counter of the CTA
-    unsigned int pad;
+    unsigned int done;                       // warps of the CTA that have run out of tiles
 };
 
 // The kernel.  Tiles are assigned statically and round-robin: CTA b owns tiles b, b+G, b+2G, ...
@@ -1418,7 +1511,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
-    if (threadIdx.x == 0) ring.cons = 0;
+    if (threadIdx.x == 0) { ring.cons = 0; ring.done = 0; }
     __syncthreads();
     griddep_launch_dependents();
     // fill k of slot s = the CTA's tile number i = k*NS + s (lane 0): TMA for interior tiles, a plain
@@ -1472,17 +1565,18 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
     }
 
     __syncthreads();                                       // tables in shared memory are complete
+    // At most two launches of a block are ever in flight.  The link records alternate between two halves by launch
+    // parity and the history / carried-state buffers rotate through three, so what this launch WRITES was last READ by
+    // the launch before the previous one: nothing is published or handed over before every CTA of that launch has run
+    // to its end (handoff[2] counts them; observed on long streams: with only the hardware's launch ordering a third
+    // launch did start while the first still had tiles to finish).
+    handoff_wait(a, 2, a.depth_target);
     if (cta == (long long)(a.ntiles - 1) % G && wid == NW - 1) {
-        handoff_wait(a, 1, a.carry_target);                // replaces buffers the previous call still reads until its end
+        handoff_wait(a, 1, a.carry_target);                // copies what the previous call writes up to its very end
         end_of_call_duties(a, lane);
         handoff_signal(a, 0, lane);                        // FIR history for the next call is in place
         handoff_signal(a, 1, lane);                        // ... and this warp's share of the carried state
     }
-
-    // At most two launches of a block are ever in flight: the link records alternate between two halves by launch
-    // parity, so this launch must not publish before the launch before the previous one has ended (observed on long
-    // streams: with only the hardware's launch ordering a third launch did start while the first still had tiles to finish).
-    handoff_wait(a, 1, a.depth_target);
 
     float u_pend[NPT];
 #pragma unroll
@@ -1611,6 +1705,10 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(reinterpret_cast<unsigned long long *>(a.trace + (long long)a.ntiles * 16 + 1), gt);
     }
+    // this warp reads nothing of the call any more; the last warp of the CTA reports the CTA as done
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&ring.done, 1u) == (unsigned)NW - 1u) atomicAdd(a.handoff + 2, 1u);
 }
 
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);

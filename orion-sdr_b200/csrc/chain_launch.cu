@@ -1,5 +1,5 @@
 // Kernel selection, occupancy set-up and launch of the chain kernel family (instances: chain_inst_*.cu).
-#include "chain_args.h"
+#include "chain_kernels.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,6 +22,32 @@ chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
     if (U == 1) return get_kernel_staged_u1(R);
     if (U == 2) return get_kernel_staged_u2(R);
     return nullptr;
+}
+
+// Checkpoint expansion of the exact-replay oscillator: thread t starts at anchor t = (ctr, Z(ctr), w), replays the
+// reference recurrence (renormalisation included) and writes fine[e] = Z(c0 + 16 e) for every such counter value in
+// (ctr, ctr + nsteps].
+__global__ void osc_expand_kernel(const OscAnchor *an, int n_an, float2 *fine, unsigned long long c0, long long fine_len) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_an) return;
+    const OscAnchor A = an[t];
+    float2 z = A.z;
+    unsigned ctr = (unsigned)A.ctr;
+    unsigned long long c = A.ctr;
+    for (unsigned s = 0; s < A.nsteps; ++s) {
+        nco_step_exact(z, A.w, ctr);
+        c += 1ull;
+        if (c >= c0 && ((c - c0) & 15ull) == 0ull) {
+            const long long e = (long long)((c - c0) >> 4);
+            if (e < fine_len) fine[e] = z;
+        }
+    }
+}
+cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, unsigned long long c0, long long fine_len,
+                              cudaStream_t stream) {
+    if (n_an <= 0) return cudaSuccess;
+    osc_expand_kernel<<<(n_an + 63) / 64, 64, 0, stream>>>(d_an, n_an, d_fine, c0, fine_len);
+    return cudaGetLastError();
 }
 
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm) {

@@ -24,6 +24,8 @@ chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm);
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm);
 cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
                                 size_t dyn_smem, cudaStream_t stream, int overlap);
+cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, unsigned long long c0, long long fine_len,
+                              cudaStream_t stream);
 }  // namespace orion
 
 using namespace orion;
@@ -240,12 +242,60 @@ void build_group(const SecParam *secs, const GroupHost &gh, int npt, GroupParam 
     gp->agg_only = depth <= 32 ? 1 : 0;
 }
 
+// ---- exact-replay oscillator: the reference recurrence walked on the host --------------------------------------
+// rotator.rs:44-61 / nco.rs:42-58 restated: z <- (fma(zr, wr, -(zi*wi)), fma(zi, wr, zr*wi)); every 1024 steps
+// z *= 1 / sqrt(|z|^2).  The walk is inherently sequential (each step rounds), ~3 ns per step on a host core; it leaves
+// one anchor per 1024 items of a call, from which the device replays in parallel (chain_kernels.cuh).
+struct ExactOsc {
+    bool enabled = false;
+    float wre = 1.f, wim = 0.f;               // the reference's f32 step (cosf(phi), sinf(phi))
+    unsigned long long ctr = 0;               // next() calls since the last reset
+    float zr = 1.f, zi = 0.f;                 // Z(ctr)
+    std::vector<float2> recent;               // the phasors applied to the most recent items (oldest first), for the FIR history
+    size_t keep = 0;                          // how many of them to keep
+    // device side
+    OscAnchor *h_an = nullptr;                // pinned staging
+    OscAnchor *d_an = nullptr;
+    size_t an_cap = 0;
+    float2 *d_fine = nullptr, *d_hist = nullptr;
+    size_t fine_cap = 0, hist_cap = 0;
+    float2 *h_hist = nullptr;
+    cudaEvent_t staged = nullptr;             // the last upload from the pinned staging buffers has completed
+
+    void set_freq(float freq_hz, float fs) {  // rotator.rs:16-18,35-38
+        const float phi = kTau * freq_hz / fs;
+        wre = cosf(phi); wim = sinf(phi);
+    }
+    void reset_phase() { zr = 1.f; zi = 0.f; ctr = 0; }     // rotator.rs:28-31; the FIR history keeps what it was mixed with
+    inline void step() {
+        const float nr = fmaf(zr, wre, -(zi * wim));
+        const float ni = fmaf(zi, wre, zr * wim);
+        zr = nr; zi = ni;
+        ctr += 1;
+        if ((ctr & 0x3FFull) == 0) {
+            const float r2 = zr * zr + zi * zi;
+            const float inv = 1.0f / sqrtf(r2);
+            zr *= inv; zi *= inv;
+        }
+    }
+    void free_device() {
+        if (h_an) cudaFreeHost(h_an);
+        if (h_hist) cudaFreeHost(h_hist);
+        cudaFree(d_an); cudaFree(d_fine); cudaFree(d_hist);
+        if (staged) cudaEventDestroy(staged);
+        h_an = nullptr; h_hist = nullptr; d_an = nullptr; d_fine = nullptr; d_hist = nullptr; staged = nullptr;
+        an_cap = fine_cap = hist_cap = 0;
+    }
+};
+
 // ---- oscillator ------------------------------------------------------------------------------
 struct Osc {
     bool on = false;
     unsigned long long step = 0, phase0 = 0, k0 = 0;
     float wre = 1.f, wim = 0.f, amp_delta = 0.f;
+    ExactOsc x;                                                // the exact-replay twin (same frequency, same resets)
     void set(float freq_hz, float fs, unsigned long long k_now) {
+        x.set_freq(freq_hz, fs);
         // keep the phase reached so far (rotator.rs:35-39), then change the step
         phase0 = phase0 + step * (k_now - k0);
         k0 = k_now;
@@ -260,11 +310,13 @@ struct Osc {
         wim = (float)sin(th);
         on = true;
     }
-    void reset_phase() { phase0 = 0; k0 = 0; }
+    void reset_phase() { phase0 = 0; k0 = 0; x.reset_phase(); }
     NcoParam param(unsigned long long kbase) const {
         NcoParam p;
+        memset(&p, 0, sizeof(p));
         p.step = step; p.phase0 = phase0; p.k0 = k0; p.kbase = kbase; p.wre = wre; p.wim = wim;
-        p.amp_delta = amp_delta; p.pad = 0.f;
+        p.amp_delta = amp_delta;
+        p.xwre = x.wre; p.xwim = x.wim;
         return p;
     }
 };
@@ -370,6 +422,7 @@ encode_tiled_t get_encode_tiled() {
 }
 
 thread_local int t_device = 0;
+thread_local std::string t_create_error;       // why the last constructor on this thread failed
 
 }  // namespace
 
@@ -389,6 +442,8 @@ struct orion_b200_block {
     float fs_demod = 0.f;
     std::vector<SecParam> secs;
     Osc pre, post;
+    int opt_exact = -1;                   // -1 auto (by block kind), 0 closed form everywhere, 1 exact everywhere
+    double exact_host_ms = 0.0;           // host time spent walking the recurrence (reported separately from kernel time)
     int cw_gain_sec = -1;
     // ---- plan ----
     FirPlan plan;
@@ -405,10 +460,13 @@ struct orion_b200_block {
     GroupTables *d_gtabs = nullptr;
     std::vector<GroupParam> groups;
     std::vector<int> group_depth;
-    float2 *d_hist[2] = { nullptr, nullptr };
+    // FIR history and carried state rotate through THREE buffers: call N reads [pp] and writes [pp+1]; the overlapped
+    // call N+1 writes [pp+2], which nobody has read since call N-1 (over before N+1 writes: ChainArgs::depth_target)
+    float2 *d_hist[3] = { nullptr, nullptr, nullptr };
     size_t hist_cap = 0;
-    CarryState *d_carry[2] = { nullptr, nullptr };
+    CarryState *d_carry[3] = { nullptr, nullptr, nullptr };
     int pp = 0;
+    unsigned int ctas_launched = 0, ctas_before_prev = 0;   // CTA-done counter targets (handoff[2])
     TileLink *d_links = nullptr;
     size_t links_cap = 0;
     unsigned long long *d_ticket = nullptr;
@@ -496,7 +554,7 @@ int finalize_plan(orion_b200_block *b) {
         CK(dev_upload(b, b->d_g, b->plan.g.data(), b->plan.g.size() * sizeof(float)));
         if ((size_t)b->plan.H > b->hist_cap) {
             // growing the history keeps the most recent samples at the end
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 3; ++i) {
                 float2 *nh = nullptr;
                 CK(cudaMalloc(&nh, (size_t)b->plan.H * sizeof(float2)));
                 CK(dev_memset(b, nh, 0, (size_t)b->plan.H * sizeof(float2)));
@@ -535,16 +593,19 @@ int reset_state(orion_b200_block *b) {
     CarryState cs;
     memset(&cs, 0, sizeof(cs));
     cs.prev = make_float2(1.0f, 0.0f);                         // fm.rs:29, pm.rs:29
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         CK(dev_upload(b, b->d_carry[i], &cs, sizeof(cs)));
         if (b->d_hist[i]) CK(dev_memset(b, b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
     }
-    CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
     CK(cudaStreamSynchronize(b->stream));
     b->calls_since_reset = 0;
+    b->ctas_launched = b->ctas_before_prev = 0;
     b->k_pre = b->k_post = 0;
     b->pre.reset_phase();
     b->post.reset_phase();
+    b->pre.x.recent.clear();
+    b->post.x.recent.clear();
     return ORION_B200_OK;
 }
 
@@ -567,11 +628,11 @@ int init_device_side(orion_b200_block *b) {
     b->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
     b->stream = b->own_stream;
-    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
+    for (int i = 0; i < 3; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
     CK(cudaMalloc(&b->d_ticket, 2 * sizeof(unsigned long long)));        // {ticket, done}
     CK(dev_memset(b, b->d_ticket, 0, 2 * sizeof(unsigned long long)));
-    CK(cudaMalloc(&b->d_handoff, 2 * sizeof(unsigned int)));
-    CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc(&b->d_handoff, 4 * sizeof(unsigned int)));
+    CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
     CK(cudaMalloc(&b->d_err, sizeof(int)));
     CK(dev_memset(b, b->d_err, 0, sizeof(int)));
     CK(cudaMallocHost(&b->h_err, sizeof(int)));
@@ -587,9 +648,7 @@ int finish_create(orion_b200_block *b, orion_b200_block **out) {
     b->out_item = kind_c32_out(b->demod) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
     int st = init_device_side(b);
     if (st != ORION_B200_OK) {
-        // keep the message reachable through a static buffer, then drop the half-built block
-        static thread_local std::string last;
-        last = b->err;
+        t_create_error = b->err;                 // orion_b200_last_create_error()
         orion_b200_block_destroy(b);
         return st;
     }
@@ -616,7 +675,7 @@ void add_lr4(orion_b200_block *b, float fs, float fc) {
 }
 
 void length_rules(const orion_b200_block *b, size_t n_in, size_t out_cap, size_t *consume, size_t *produce) {
-    if (b->fir != FIR_NONE && b->M > 1) {              // decim.rs:45,66-75: all input read, ceil(n/m) capped
+    if (b->fir == FIR_DECIM || (b->fir != FIR_NONE && b->M > 1)) {   // decim.rs:45,66-75 (any m, m = 1 included): all input read, ceil(n/m) capped
         *consume = n_in;
         const size_t n_out = (n_in + b->M - 1) / b->M;
         *produce = std::min(n_out, out_cap);
@@ -625,6 +684,105 @@ void length_rules(const orion_b200_block *b, size_t n_in, size_t out_cap, size_t
         *consume = n;
         *produce = n;
     }
+}
+
+// Where the absolute oscillator phase reaches the output the reference's own recurrence is replayed (bit-exact
+// phasors); where only phase differences or magnitudes matter (FM / PM / AM / CW behind the mixer, FM translate) the
+// closed form is kept: a slowly drifting common rotation cancels there (DESIGN.md "oscillator").
+bool want_exact_pre(const orion_b200_block *b) {
+    if (b->mix == MIX_NONE) return false;
+    if (b->opt_exact >= 0) return b->opt_exact != 0;
+    return b->demod == DEMOD_NONE || b->demod == DEMOD_SSB || b->demod == DEMOD_USB;
+}
+bool want_exact_post(const orion_b200_block *b) {
+    if (!(b->demod == DEMOD_SSB || b->demod == DEMOD_USB || b->demod == MOD_AM || b->demod == MOD_PM)) return false;
+    return b->opt_exact < 0 || b->opt_exact != 0;
+}
+
+// Walk the reference recurrence over the n_items of this call (host, sequential), leave one anchor per 1024 items and
+// the phasors of the previous hist_len items, and enqueue the expansion kernel.  Fills the exact-mode fields of *np.
+int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t n_items, size_t hist_len, NcoParam *np) {
+    ExactOsc &x = o.x;
+    if (x.ctr != kbase)
+        return fail(b, ORION_B200_ERR_INVALID, "exact oscillator mode must be selected before the first call after a reset");
+    if (n_items == 0) return ORION_B200_OK;
+    const size_t n_an = (n_items + 1023) / 1024;
+    const long long fine_len = (long long)((n_items - 1) >> 4) + 1;
+    if (!x.staged) CK(cudaEventCreateWithFlags(&x.staged, cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(x.staged));               // the pinned staging buffers are free again
+    if (n_an > x.an_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        if (x.h_an) cudaFreeHost(x.h_an);
+        cudaFree(x.d_an);
+        x.h_an = nullptr; x.d_an = nullptr;
+        const size_t cap = n_an + n_an / 4 + 16;
+        CK(cudaMallocHost(&x.h_an, cap * sizeof(OscAnchor)));
+        CK(cudaMalloc(&x.d_an, cap * sizeof(OscAnchor)));
+        x.an_cap = cap;
+    }
+    if ((size_t)fine_len > x.fine_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(x.d_fine); x.d_fine = nullptr;
+        const size_t cap = (size_t)fine_len + (size_t)fine_len / 4 + 64;
+        CK(cudaMalloc(&x.d_fine, cap * sizeof(float2)));
+        x.fine_cap = cap;
+    }
+    if (hist_len > x.hist_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        if (x.h_hist) cudaFreeHost(x.h_hist);
+        cudaFree(x.d_hist);
+        x.h_hist = nullptr; x.d_hist = nullptr;
+        CK(cudaMallocHost(&x.h_hist, hist_len * sizeof(float2)));
+        CK(cudaMalloc(&x.d_hist, hist_len * sizeof(float2)));
+        x.hist_cap = hist_len;
+    }
+    // phasors of the items before this call (newest last)
+    const size_t nh = std::min(x.recent.size(), hist_len);
+    for (size_t i = 0; i < nh; ++i) x.h_hist[i] = x.recent[x.recent.size() - nh + i];
+    // the walk
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const unsigned long long ctr0 = x.ctr;
+    const unsigned long long c_last = ctr0 + 1ull + 16ull * (unsigned long long)(fine_len - 1);
+    std::vector<float2> tail;
+    const size_t n_tail = std::min(n_items, hist_len);
+    tail.reserve(n_tail);
+    size_t done = 0;
+    for (size_t a = 0; a < n_an; ++a) {
+        OscAnchor &A = x.h_an[a];
+        A.ctr = x.ctr; A.z = make_float2(x.zr, x.zi); A.w = make_float2(x.wre, x.wim);
+        A.nsteps = (unsigned)std::min<unsigned long long>(1024ull, c_last - x.ctr);
+        A.pad = 0;
+        const size_t m = std::min<size_t>(1024, n_items - done);
+        if (done + m + n_tail > n_items) {                 // the last hist_len phasors of the call feed the next call's history
+            for (size_t i = 0; i < m; ++i) {
+                x.step();
+                if (done + i + n_tail >= n_items) tail.push_back(make_float2(x.zr, x.zi));
+            }
+        } else {
+            for (size_t i = 0; i < m; ++i) x.step();
+        }
+        done += m;
+    }
+    if (hist_len) {
+        if (n_tail >= hist_len) x.recent.swap(tail);
+        else {
+            x.recent.insert(x.recent.end(), tail.begin(), tail.end());
+            if (x.recent.size() > hist_len) x.recent.erase(x.recent.begin(), x.recent.end() - (long)hist_len);
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    b->exact_host_ms += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    CK(cudaMemcpyAsync(x.d_an, x.h_an, n_an * sizeof(OscAnchor), cudaMemcpyHostToDevice, b->stream));
+    if (nh) CK(cudaMemcpyAsync(x.d_hist, x.h_hist, nh * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaEventRecord(x.staged, b->stream));
+    CK(osc_expand_launch(x.d_an, (int)n_an, x.d_fine, ctr0 + 1ull, fine_len, b->stream));
+    b->launches += 1;
+    np->exact = 1;
+    np->xfine = x.d_fine; np->xfine_len = (int)fine_len;
+    np->xhist = x.d_hist; np->xhist_len = (int)nh;
+    np->xwre = x.wre; np->xwim = x.wim;
+    return ORION_B200_OK;
 }
 
 int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out) {
@@ -660,7 +818,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     memset(&a, 0, sizeof(a));
     a.in = d_in; a.out = d_out;
     a.n_in = (long long)n_in; a.n_out = (long long)n_out;
-    a.hist_in = b->d_hist[b->pp]; a.hist_out = b->d_hist[b->pp ^ 1];
+    a.hist_in = b->d_hist[b->pp]; a.hist_out = b->d_hist[(b->pp + 1) % 3];
     a.H = (b->fir != FIR_NONE) ? b->plan.H : 0;
     a.mix = b->mix;
     a.pre = b->pre.param(b->k_pre);
@@ -672,12 +830,23 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.nstages = b->opt_serial ? std::min(b->plan.nstages, 1) : b->plan.nstages;
     a.demod = b->demod; a.translate = b->translate; a.k = b->k; a.k1 = b->k1; a.k2 = b->k2; a.k3 = b->k3;
     a.post = b->post.param(b->k_post);
+    bool exact_used = false;
+    if (want_exact_pre(b)) {
+        const int st = prepare_exact(b, b->pre, b->k_pre, n_in, (b->fir != FIR_NONE) ? (size_t)b->plan.H : 0, &a.pre);
+        if (st != ORION_B200_OK) { delete ap; return st; }
+        exact_used = true;
+    }
+    if (want_exact_post(b)) {
+        const int st = prepare_exact(b, b->post, b->k_post, n_out, 0, &a.post);
+        if (st != ORION_B200_OK) { delete ap; return st; }
+        exact_used = true;
+    }
     a.nsec = nsec;
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
     a.ngroups = (int)b->groups.size();
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;
-    a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[b->pp ^ 1];
+    a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
     a.links = b->d_links ? b->d_links + (size_t)(b->epoch & 1u) * b->links_cap * kMaxGroups : nullptr;   // consecutive calls may overlap
     a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err_ext ? b->d_err_ext : b->d_err;
     a.trace = b->trace;
@@ -689,7 +858,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.handoff = b->d_handoff;
     a.hist_target = b->calls_since_reset;                 // every earlier call has written its history ...
     a.carry_target = 2u * b->calls_since_reset;           // ... and both of its hand-over signals
-    a.depth_target = b->calls_since_reset >= 1 ? 2u * (b->calls_since_reset - 1) : 0u;   // every call but the previous one has ended
+    a.depth_target = b->ctas_before_prev;                 // every CTA of every call but the previous one has run to its end
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
     a.ntaps2 = (int)b->plan.taps2.size();
 
@@ -732,18 +901,22 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     // foreign kernel that is still producing this call's input.
     bool overlap = !b->opt_serial && ntiles >= 1024 && (b->stream == b->own_stream || b->opt_overlap);
     for (const GroupParam &gp : b->groups) overlap = overlap && gp.agg_only;
+    if (exact_used) overlap = false;                       // the expansion kernel just enqueued must have finished
     if (getenv("ORION_B200_NO_OVERLAP")) overlap = false;
     cudaError_t e = chain_kernel_launch(b->kernel, a, tmap, grid, b->plan.warps, b->plan.dyn_smem, b->stream, overlap ? 1 : 0);
     delete ap;
     if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "chain kernel launch", e);
     b->launches += 1;
     b->calls_since_reset += 1;
-    if (b->calls_since_reset >= (1u << 30)) {              // counter wrap: drain, start over
+    b->ctas_before_prev = b->ctas_launched;
+    b->ctas_launched += (unsigned)grid;
+    if (b->calls_since_reset >= (1u << 30) || b->ctas_launched >= (1u << 30)) {   // counter wrap: drain, start over
         CK(cudaStreamSynchronize(b->stream));
-        CK(dev_memset(b, b->d_handoff, 0, 2 * sizeof(unsigned int)));
+        CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
         b->calls_since_reset = 0;
+        b->ctas_launched = b->ctas_before_prev = 0;
     }
-    b->pp ^= 1;
+    b->pp = (b->pp + 1) % 3;
     b->k_pre += n_in;
     b->k_post += n_out;
     return ORION_B200_OK;
@@ -771,6 +944,7 @@ int check_device_error(orion_b200_block *b) {
 extern "C" {
 
 int orion_b200_abi_version(void) { return ORION_B200_ABI_VERSION; }
+const char *orion_b200_last_create_error(void) { return t_create_error.c_str(); }
 const char *orion_b200_build_info(void) {
     return "orion_b200 sm_100a (compute_100a) -fmad=false; kernels: chain_kernel<front,R,U>; no CPU fallback";
 }
@@ -1022,6 +1196,7 @@ int orion_b200_am_demod_with_abs_approx(orion_b200_block *b, float k1, float k2)
     b->demod = DEMOD_AM_ABS;
     b->k1 = k1; b->k2 = k2;
     for (auto &s : b->secs) if (s.post_op == OP_SQRT) s.post_op = OP_NONE;
+    b->plan_dirty = true;            // the demodulator kind and the section groups changed: reselect the kernel instance
     return ORION_B200_OK;
 }
 int orion_b200_ssb_demod_create(float fs, float bfo_hz, float audio_bw_hz, orion_b200_block **out) {
@@ -1249,8 +1424,8 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_g); cudaFree(b->d_gtabs);
-    cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
-    cudaFree(b->d_carry[0]); cudaFree(b->d_carry[1]);
+    for (int i = 0; i < 3; ++i) { cudaFree(b->d_hist[i]); cudaFree(b->d_carry[i]); }
+    b->pre.x.free_device(); b->post.x.free_device();
     cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err); cudaFree(b->d_handoff);
     cudaFree(b->d_in); cudaFree(b->d_out);
     if (b->h_err) cudaFreeHost(b->h_err);
@@ -1369,6 +1544,7 @@ int orion_b200_block_set_option(orion_b200_block *b, int option, double value) {
         case ORION_B200_OPT_USE_TMA: b->opt_use_tma = v; break;
         case ORION_B200_OPT_SERIAL_TILES: b->opt_serial = v; break;
         case ORION_B200_OPT_OVERLAP_LAUNCHES: b->opt_overlap = v; break;
+        case ORION_B200_OPT_EXACT_NCO: b->opt_exact = value < 0.0 ? -1 : v; break;
         default: return fail(b, ORION_B200_ERR_INVALID, "unknown option");
     }
     if (b->plan_dirty) {
@@ -1405,12 +1581,18 @@ struct SnapshotHeader {
     float pre_w[3], post_w[3];
     uint32_t pre_on, post_on;
 };
+struct SnapshotExact {                         // the exact-replay twin of one oscillator (ExactOsc)
+    unsigned long long ctr, nrecent;
+    float zr, zi, wre, wim;
+};
 const uint32_t kSnapMagic = 0x4F423230u;      // "OB20"
+const uint32_t kSnapVersion = 2;
 }  // namespace
 
 size_t orion_b200_block_snapshot_size(const orion_b200_block *b) {
     if (!b) return 0;
-    return sizeof(SnapshotHeader) + sizeof(CarryState) + b->hist_cap * sizeof(float2);
+    return sizeof(SnapshotHeader) + sizeof(CarryState) + b->hist_cap * sizeof(float2) +
+           2 * sizeof(SnapshotExact) + b->hist_cap * sizeof(float2);
 }
 int orion_b200_block_snapshot(orion_b200_block *b, void *buf, size_t cap) {
     if (!b || !buf) return ORION_B200_ERR_INVALID;
@@ -1419,7 +1601,7 @@ int orion_b200_block_snapshot(orion_b200_block *b, void *buf, size_t cap) {
     CK(cudaStreamSynchronize(b->stream));
     SnapshotHeader h;
     memset(&h, 0, sizeof(h));
-    h.magic = kSnapMagic; h.version = 1;
+    h.magic = kSnapMagic; h.version = kSnapVersion;
     h.fir = (uint32_t)b->fir; h.demod = (uint32_t)b->demod; h.mix = (uint32_t)b->mix; h.nsec = (uint32_t)b->secs.size();
     h.M = b->M; h.ntaps = b->taps.size(); h.hist_len = b->hist_cap;
     h.k_pre = b->k_pre; h.k_post = b->k_post;
@@ -1432,16 +1614,29 @@ int orion_b200_block_snapshot(orion_b200_block *b, void *buf, size_t cap) {
     memcpy(p, &h, sizeof(h)); p += sizeof(h);
     CK(cudaMemcpy(p, b->d_carry[b->pp], sizeof(CarryState), cudaMemcpyDeviceToHost)); p += sizeof(CarryState);
     if (b->hist_cap) CK(cudaMemcpy(p, b->d_hist[b->pp], b->hist_cap * sizeof(float2), cudaMemcpyDeviceToHost));
+    p += b->hist_cap * sizeof(float2);
+    for (const Osc *o : { &b->pre, &b->post }) {
+        SnapshotExact xs;
+        memset(&xs, 0, sizeof(xs));
+        xs.ctr = o->x.ctr; xs.zr = o->x.zr; xs.zi = o->x.zi; xs.wre = o->x.wre; xs.wim = o->x.wim;
+        xs.nrecent = (o == &b->pre) ? std::min(o->x.recent.size(), b->hist_cap) : 0;
+        memcpy(p, &xs, sizeof(xs)); p += sizeof(xs);
+        if (o == &b->pre) {
+            memset(p, 0, b->hist_cap * sizeof(float2));
+            if (xs.nrecent) memcpy(p, o->x.recent.data() + (o->x.recent.size() - xs.nrecent), xs.nrecent * sizeof(float2));
+            p += b->hist_cap * sizeof(float2);
+        }
+    }
     return ORION_B200_OK;
 }
 int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) {
     if (!b || !buf || size < sizeof(SnapshotHeader)) return ORION_B200_ERR_INVALID;
     SnapshotHeader h;
     memcpy(&h, buf, sizeof(h));
-    if (h.magic != kSnapMagic || h.version != 1) return fail(b, ORION_B200_ERR_INVALID, "not a snapshot of this library version");
+    if (h.magic != kSnapMagic || h.version != kSnapVersion) return fail(b, ORION_B200_ERR_INVALID, "not a snapshot of this library version");
     if (h.fir != (uint32_t)b->fir || h.demod != (uint32_t)b->demod || h.mix != (uint32_t)b->mix || h.nsec != b->secs.size() ||
         h.M != b->M || h.ntaps != b->taps.size() || h.hist_len != b->hist_cap ||
-        size < sizeof(h) + sizeof(CarryState) + h.hist_len * sizeof(float2))
+        size < sizeof(h) + sizeof(CarryState) + 2 * h.hist_len * sizeof(float2) + 2 * sizeof(SnapshotExact))
         return fail(b, ORION_B200_ERR_INVALID, "snapshot was taken from a block of a different shape");
     int st = reset_state(b);                              // drains the stream, zeroes the hand-over counters
     if (st != ORION_B200_OK) return st;
@@ -1454,10 +1649,23 @@ int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) 
     const char *p = (const char *)buf + sizeof(h);
     CK(dev_upload(b, b->d_carry[b->pp], p, sizeof(CarryState))); p += sizeof(CarryState);
     if (b->hist_cap) CK(dev_upload(b, b->d_hist[b->pp], p, b->hist_cap * sizeof(float2)));
+    p += b->hist_cap * sizeof(float2);
+    for (Osc *o : { &b->pre, &b->post }) {
+        SnapshotExact xs;
+        memcpy(&xs, p, sizeof(xs)); p += sizeof(xs);
+        o->x.ctr = xs.ctr; o->x.zr = xs.zr; o->x.zi = xs.zi; o->x.wre = xs.wre; o->x.wim = xs.wim;
+        o->x.recent.clear();
+        if (o == &b->pre) {
+            const float2 *r = reinterpret_cast<const float2 *>(p);
+            if (xs.nrecent <= b->hist_cap) o->x.recent.assign(r, r + xs.nrecent);
+            p += b->hist_cap * sizeof(float2);
+        }
+    }
     return ORION_B200_OK;
 }
 
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b) { return b ? b->launches : 0; }
+double orion_b200_block_exact_host_ms(const orion_b200_block *b) { return b ? b->exact_host_ms : 0.0; }
 
 // debug: per-tile SM clock stamps (8 x int64 per tile, device pointer; NULL disables)
 int orion_b200_debug_set_trace(orion_b200_block *b, void *d_trace) {

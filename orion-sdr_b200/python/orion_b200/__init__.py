@@ -25,7 +25,7 @@ ITEM_F32, ITEM_C32 = 1, 2
 MIX_NONE, MIX_ROTATE, MIX_NCO = 0, 1, 2
 FIR_NONE, FIR_DECIM, FIR_IQ = 0, 1, 2
 DEMOD_NONE, DEMOD_FM, DEMOD_PM, DEMOD_AM, DEMOD_AM_ABS, DEMOD_SSB, DEMOD_CW, DEMOD_USB = range(8)
-OPT_FIR_GLOBAL, OPT_USE_TMA, OPT_SERIAL_TILES, OPT_OVERLAP_LAUNCHES = 1, 2, 3, 4
+OPT_FIR_GLOBAL, OPT_USE_TMA, OPT_SERIAL_TILES, OPT_OVERLAP_LAUNCHES, OPT_EXACT_NCO = 1, 2, 3, 4, 5
 
 
 class OrionB200Error(RuntimeError):
@@ -123,6 +123,8 @@ def lib():
     sig("orion_b200_block_set_option", i, vp, i, d)
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
+    sig("orion_b200_block_exact_host_ms", d, vp)
+    sig("orion_b200_last_create_error", C.c_char_p)
     sig("orion_b200_block_snapshot_size", sz, vp)
     sig("orion_b200_block_snapshot", i, vp, vp, sz)
     sig("orion_b200_block_restore", i, vp, vp, sz)
@@ -173,6 +175,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
+    "orion_b200_block_exact_host_ms", "orion_b200_last_create_error",
 ]
 
 
@@ -375,11 +378,26 @@ class Block:
     def launch_count(self) -> int:
         return int(lib().orion_b200_block_launch_count(self._h))
 
+    @property
+    def exact_host_ms(self) -> float:
+        """Host time spent walking the oscillator recurrence (exact-replay mode), reported apart from kernel time."""
+        return float(lib().orion_b200_block_exact_host_ms(self._h))
+
+
+def _check_create(status):
+    if status != OK:
+        L = lib()
+        msg = L.orion_b200_status_string(status).decode()
+        extra = L.orion_b200_last_create_error()
+        if extra:
+            msg += " -- " + extra.decode()
+        raise OrionB200Error(status, msg)
+
 
 def _mk(fn_name, *args) -> int:
     h = C.c_void_p(0)
     st = getattr(lib(), fn_name)(*args, C.byref(h))
-    _check(st)
+    _check_create(st)
     return h.value
 
 
@@ -577,7 +595,7 @@ class Chain(Block):
         sp.post_sos = self._sos.ctypes.data_as(C.POINTER(C.c_float)) if self._sos.size else None
         sp.n_post = self._sos.shape[0]
         h = C.c_void_p(0)
-        _check(lib().orion_b200_chain_create(C.byref(sp), C.byref(h)))
+        _check_create(lib().orion_b200_chain_create(C.byref(sp), C.byref(h)))
         super().__init__(h.value)
 
 

@@ -138,3 +138,17 @@ def test_streaming_state_is_chunk_invariant():
     assert a.size == 251 and b2.size == 774                              # ceil(n/m) each call
     dfull = O.FirDecimator(96e3, 1, 10800.0, 2400.0).run(x)              # same taps, m=1
     same(b2, dfull[1001::4])                                             # phase restarted at sample 1001
+
+
+@pytest.mark.parametrize("L,m,n", [(63, 8, 20_001), (17, 1, 300), (201, 25, 30_000), (1023, 32, 40_000), (513, 128, 70_001)])
+def test_kept_output_accelerators_equal_the_loop_for_loop_blocks(L, m, n):
+    """oo_fir_decim_kept / oo_fir_iq_kept (what the full-size GPU parity tests use as the reference FIR) are
+    bit-identical to FirDecimator::process / FirLowpassIq::push + stride pick run loop for loop."""
+    r = np.random.default_rng(L * 7 + m)
+    taps = r.standard_normal(L).astype(np.float32) / L         # non-zero end taps: both pairing rules exercised
+    x = iq(n, 40 + m)
+    same(O.fir_decim_kept(taps, m, x, threads=3), O.FirDecimator(taps=taps, m=m).run(x))
+    same(O.fir_iq_kept(taps, m, x, threads=3), O.FirLowpassIq(taps=taps).run(x)[::m])
+    # negative zero and denormal inputs go through the same adds
+    x2 = x.copy(); x2[::7] = np.complex64(complex(-0.0, 1e-42))
+    same(O.fir_decim_kept(taps, m, x2), O.FirDecimator(taps=taps, m=m).run(x2))
