@@ -166,6 +166,12 @@ struct ChainArgs {
     unsigned int carry_target;
     unsigned int depth_target;   // value of the CTA-done counter that proves every launch before the previous one has ended
                                  // (all of its tiles: nobody reads its buffers or its half of the link records any more)
+    // batched launch (channel bank): blockIdx.y = member; member m works on channel batch_chan[m]
+    int   batch;                 // members (1: plain launch)
+    const int *batch_chan;       // [batch] channel index of every member (row of the strided input / output)
+    long long batch_in_stride;   // bytes between the inputs of two channels
+    long long batch_out_stride;  // bytes between the outputs of two channels
+    long long batch_links_stride;// TileLink records between two members; carry_in / carry_out are arrays indexed by member
     long long *trace;            // debug: 8 x int64 per tile {consume, ready, fir_done, front_done, finish_done, -, smid, warp}
     float2 taps2[kMaxTapTable / 2];   // [u][q][c] -> (g[t0], g[t0-1]); see DESIGN.md "staged FIR"
 };

@@ -10,4 +10,11 @@ chain_kernel_t get_kernel_direct(int dm) {
     }
     return kptr<FRONT_DIRECT, 16, 1>();
 }
+chain_kernel_t get_kernel_direct_batch(int dm) {
+    switch (dm) {
+        case DM_LR4 + DEMOD_FM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_FM, 1>();
+        case DM_LR4 + DEMOD_PM: return kptr<FRONT_DIRECT, 16, 1, 0, DM_LR4 + DEMOD_PM, 1>();
+    }
+    return kptr<FRONT_DIRECT, 16, 1, 0, -1, 1>();
+}
 }  // namespace orion

@@ -1477,10 +1477,32 @@ struct __align__(16) RingCtl {
 //   * no deadlock by construction: the oldest unfinished tile of the stream is either in a warp's
 //     hands, and that warp never waits on a younger tile, or next in line at its CTA, whose warps
 //     all hold older tiles that wait on still older, finished ones.
-template <int FRONT, int R, int U, int SP, int DM>
+// BATCH = 1: blockIdx.y selects one of ChainArgs::batch independent, equally long streams (the channels of a bank after
+// the shared front end, bank_kernels.cu).  The launch arguments are copied to shared memory once per CTA and the
+// per-stream pointers patched there; everything below reads them through the same reference.
+template <int FRONT, int R, int U, int SP, int DM, int BATCH = 0>
 __global__ void __launch_bounds__(kThreads * kMaxWarpsPerCta, 1)
-chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
+chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ CUtensorMap tmap) {
     constexpr int NPT = R * U;
+    __shared__ __align__(16) unsigned char args_sh[BATCH ? offsetof(ChainArgs, taps2) : 16];
+    if (BATCH) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&a_param);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(args_sh);
+        for (int i = threadIdx.x; i < (int)(offsetof(ChainArgs, taps2) / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ChainArgs *as = reinterpret_cast<ChainArgs *>(args_sh);
+            const long long m = blockIdx.y;
+            const long long ch = a_param.batch_chan ? a_param.batch_chan[m] : m;
+            as->in = reinterpret_cast<const unsigned char *>(a_param.in) + ch * a_param.batch_in_stride;
+            as->out = reinterpret_cast<unsigned char *>(a_param.out) + ch * a_param.batch_out_stride;
+            as->carry_in = a_param.carry_in + m;
+            as->carry_out = a_param.carry_out + m;
+            as->links = a_param.links ? a_param.links + m * a_param.batch_links_stride : nullptr;
+        }
+        __syncthreads();
+    }
+    const ChainArgs &a = BATCH ? *reinterpret_cast<const ChainArgs *>(args_sh) : a_param;
     typedef Geo<SP> GE;
     const int HRc = GE::fixed ? GE::HR : a.HR;
     const int demod = Dm<DM>::demod(a);
@@ -1713,12 +1735,13 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUtens
 
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 
-template <int FRONT, int R, int U, int SP = 0, int DM = -1>
-static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM>; }
+template <int FRONT, int R, int U, int SP = 0, int DM = -1, int BATCH = 0>
+static chain_kernel_t kptr() { return chain_kernel<FRONT, R, U, SP, DM, BATCH>; }
 
 // one getter per translation unit (nullptr: no such instance there)
 chain_kernel_t get_kernel_hot(int front, int sp, int dm);   // fixed geometries (SP = 1, 2) + FRONT_GLOBAL
 chain_kernel_t get_kernel_direct(int dm);                   // rate-1 blocks
+chain_kernel_t get_kernel_direct_batch(int dm);             // rate-1 blocks, batched over blockIdx.y (channel bank)
 chain_kernel_t get_kernel_staged_u1(int R);                 // generic staged instances, even M
 chain_kernel_t get_kernel_staged_u2(int R);                 // generic staged instances, odd M
 

@@ -10,11 +10,13 @@ namespace orion {
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
 chain_kernel_t get_kernel_hot(int front, int sp, int dm);
 chain_kernel_t get_kernel_direct(int dm);
+chain_kernel_t get_kernel_direct_batch(int dm);
 chain_kernel_t get_kernel_staged_u1(int R);
 chain_kernel_t get_kernel_staged_u2(int R);
 
 // sp: 1 = the staged geometry is the fixed decimate-by-8 shape (Geo<1>); dm: -1 generic, a DEMOD_* kind, DM_LR4 + kind
-chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm) {
+chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm, int batch) {
+    if (batch) return front == FRONT_DIRECT ? get_kernel_direct_batch(dm) : nullptr;
     if (front == FRONT_DIRECT) return get_kernel_direct(dm);
     if (front == FRONT_GLOBAL) return get_kernel_hot(front, 0, dm);
     if (sp == 1 && R == 8 && U == 1) return get_kernel_hot(front, 1, dm);
@@ -62,7 +64,7 @@ cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const C
                                 size_t dyn_smem, cudaStream_t stream, int overlap) {
     // serial debug mode: one warp walks the tiles in order
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(grid, args.batch > 1 ? args.batch : 1);
     cfg.blockDim = dim3(args.serial ? kThreads : kThreads * warps);
     cfg.dynamicSmemBytes = dyn_smem;
     cfg.stream = stream;

@@ -20,10 +20,22 @@
 
 namespace orion {
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
-chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm);
+chain_kernel_t select_kernel(int front, int R, int U, int sp, int dm, int batch);
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm);
 cudaError_t chain_kernel_launch(chain_kernel_t k, const ChainArgs &args, const CUtensorMap &tmap, int grid, int warps,
                                 size_t dyn_smem, cudaStream_t stream, int overlap);
+struct BankFirArgs {             // bank_kernels.cu
+    const float2 *in; long long n_in, n_out;
+    const float2 *hist_in; float2 *hist_out; int H;
+    int mix; const NcoParam *osc; unsigned long long kbase;
+    int M, Lg, PM, BT, NS;
+    const float *gt; float g0;
+    float2 *z; long long z_stride; int nch;
+    long long tiles_total; int tiles_per_range;
+    int *err_flag;
+};
+size_t bank_fir_smem_bytes(const BankFirArgs &a);
+cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, cudaStream_t stream);
 cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, unsigned long long c0, long long fine_len,
                               cudaStream_t stream);
 }  // namespace orion
@@ -442,6 +454,8 @@ struct orion_b200_block {
     float fs_demod = 0.f;
     std::vector<SecParam> secs;
     Osc pre, post;
+    int nbatch = 1;                       // > 1: this block runs nbatch independent, equally long streams per call (a bank's
+    int *d_batch_chan = nullptr;          //      demodulator group); member m reads / writes row d_batch_chan[m] of strided buffers
     int opt_exact = -1;                   // -1 auto (by block kind), 0 closed form everywhere, 1 exact everywhere
     double exact_host_ms = 0.0;           // host time spent walking the recurrence (reported separately from kernel time)
     int cw_gain_sec = -1;
@@ -536,7 +550,8 @@ int finalize_plan(orion_b200_block *b) {
         else if ((b->demod == DEMOD_FM || b->demod == DEMOD_PM || b->demod == DEMOD_F32) && lr4_only) dm = 100 + b->demod;
     }
     if (getenv("ORION_B200_NO_SPECIALIZE")) { sp = 0; dm = -1; }
-    b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm);
+    if (b->nbatch > 1) b->plan.warps = 4;          // one small CTA per member; many of them per SM
+    b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm, b->nbatch > 1);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
     b->plan.dyn_smem = b->plan.stage_bytes * b->plan.nstages +
                        (size_t)b->plan.warps * 2 * 33 * kMaxGroupDim * sizeof(float) +     // stage ring + park area
@@ -593,8 +608,9 @@ int reset_state(orion_b200_block *b) {
     CarryState cs;
     memset(&cs, 0, sizeof(cs));
     cs.prev = make_float2(1.0f, 0.0f);                         // fm.rs:29, pm.rs:29
+    std::vector<CarryState> csv((size_t)b->nbatch, cs);
     for (int i = 0; i < 3; ++i) {
-        CK(dev_upload(b, b->d_carry[i], &cs, sizeof(cs)));
+        CK(dev_upload(b, b->d_carry[i], csv.data(), csv.size() * sizeof(CarryState)));
         if (b->d_hist[i]) CK(dev_memset(b, b->d_hist[i], 0, b->hist_cap * sizeof(float2)));
     }
     CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
@@ -628,7 +644,7 @@ int init_device_side(orion_b200_block *b) {
     b->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
     b->stream = b->own_stream;
-    for (int i = 0; i < 3; ++i) CK(cudaMalloc(&b->d_carry[i], sizeof(CarryState)));
+    for (int i = 0; i < 3; ++i) CK(cudaMalloc(&b->d_carry[i], (size_t)b->nbatch * sizeof(CarryState)));
     CK(cudaMalloc(&b->d_ticket, 2 * sizeof(unsigned long long)));        // {ticket, done}
     CK(dev_memset(b, b->d_ticket, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_handoff, 4 * sizeof(unsigned int)));
@@ -785,7 +801,8 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     return ORION_B200_OK;
 }
 
-int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out) {
+int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+           long long batch_in_stride = 0, long long batch_out_stride = 0) {
     if (b->plan_dirty) { int st = finalize_plan(b); if (st) return st; }
     if (n_in == 0) return ORION_B200_OK;
     CK(cudaSetDevice(b->device));
@@ -800,15 +817,15 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         if (b->d_links) cudaFree(b->d_links);
         size_t cap = std::max<size_t>((size_t)ntiles, 4096);
         cap += cap / 4;
-        CK(cudaMalloc(&b->d_links, 2 * cap * kMaxGroups * sizeof(TileLink)));      // two halves, alternating between calls
-        CK(dev_memset(b, b->d_links, 0, 2 * cap * kMaxGroups * sizeof(TileLink)));     // stream-ordered before the launch below
+        CK(cudaMalloc(&b->d_links, 2 * cap * b->nbatch * kMaxGroups * sizeof(TileLink)));      // two halves, alternating between calls
+        CK(dev_memset(b, b->d_links, 0, 2 * cap * b->nbatch * kMaxGroups * sizeof(TileLink)));     // stream-ordered before the launch below
         b->links_cap = cap;
         b->epoch = 0;
     }
     b->epoch += 1;
     if (b->epoch >= (1u << 30)) {                      // epoch wrap: clear the links once
         CK(cudaStreamSynchronize(b->stream));
-        CK(cudaMemsetAsync(b->d_links, 0, 2 * b->links_cap * kMaxGroups * sizeof(TileLink), b->stream));
+        CK(cudaMemsetAsync(b->d_links, 0, 2 * b->links_cap * b->nbatch * kMaxGroups * sizeof(TileLink), b->stream));
         b->epoch = 1;
     }
 
@@ -847,7 +864,11 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
-    a.links = b->d_links ? b->d_links + (size_t)(b->epoch & 1u) * b->links_cap * kMaxGroups : nullptr;   // consecutive calls may overlap
+    a.links = b->d_links ? b->d_links + (size_t)(b->epoch & 1u) * b->links_cap * b->nbatch * kMaxGroups : nullptr;   // consecutive calls may overlap
+    a.batch = b->nbatch;
+    a.batch_chan = b->d_batch_chan;
+    a.batch_in_stride = batch_in_stride; a.batch_out_stride = batch_out_stride;
+    a.batch_links_stride = (long long)b->links_cap * kMaxGroups;
     a.epoch = b->epoch; a.ntiles = (int)ntiles; a.serial = b->opt_serial; a.err_flag = b->d_err_ext ? b->d_err_ext : b->d_err;
     a.trace = b->trace;
     {   // tile t's look-back reaches the carried state iff t < depth of a group; tile 0 also reads history and `prev`
@@ -893,13 +914,14 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
         const long long want = (ntiles + b->plan.warps - 1) / b->plan.warps;      // one tile per warp at least
         grid = (int)std::max<long long>(1, std::min<long long>(want, resident));
         if (const char *e = getenv("ORION_B200_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments
+        if (b->nbatch > 1) grid = 1;      // one CTA per member: its tiles only ever wait for tiles of the same CTA
     }
     // Overlap with the previous launch on the stream (programmatic dependent launch): only long calls (the link
     // records and the output of call N are far from what call N+1 touches first), only section groups whose
     // look-back cannot reach the carried state past the guarded tiles, and only on the block's own stream unless
     // the caller opted in (ORION_B200_OPT_OVERLAP_LAUNCHES) -- on an attached stream the predecessor may be a
     // foreign kernel that is still producing this call's input.
-    bool overlap = !b->opt_serial && ntiles >= 1024 && (b->stream == b->own_stream || b->opt_overlap);
+    bool overlap = !b->opt_serial && ntiles >= 1024 && b->nbatch == 1 && (b->stream == b->own_stream || b->opt_overlap);
     for (const GroupParam &gp : b->groups) overlap = overlap && gp.agg_only;
     if (exact_used) overlap = false;                       // the expansion kernel just enqueued must have finished
     if (getenv("ORION_B200_NO_OVERLAP")) overlap = false;
@@ -909,7 +931,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     b->launches += 1;
     b->calls_since_reset += 1;
     b->ctas_before_prev = b->ctas_launched;
-    b->ctas_launched += (unsigned)grid;
+    b->ctas_launched += (unsigned)grid * (unsigned)b->nbatch;
     if (b->calls_since_reset >= (1u << 30) || b->ctas_launched >= (1u << 30)) {   // counter wrap: drain, start over
         CK(cudaStreamSynchronize(b->stream));
         CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
@@ -1269,7 +1291,31 @@ int orion_b200_mod_set_gain(orion_b200_block *b, float gain) {      // set_gain,
 }
 
 // ---- channel bank --------------------------------------------------------------------------------
+struct BankGroup {                       // channels that share one demodulator configuration: one batched launch
+    orion_b200_block *proto = nullptr;   // rate-1 block with nbatch members (kernel instance, section tables, per-member state)
+    std::vector<int> chans;              // bank channel indices of the members
+};
 struct orion_b200_bank {
+    // ---- fast path (K5): one shared front-end kernel + one batched demodulator launch per group ----
+    bool fast = false;
+    size_t nch = 0;
+    int in_item = ORION_B200_ITEM_C32, out_item = ORION_B200_ITEM_F32;
+    int mix = MIX_NONE, fir = FIR_NONE;
+    size_t M = 1;
+    std::vector<float> g;                // generic causal taps
+    std::vector<Osc> osc;                // per channel
+    NcoParam *d_osc = nullptr;
+    float *d_gt = nullptr;
+    int PM = 0, H = 0;
+    float2 *d_hist[2] = { nullptr, nullptr };
+    int pp = 0;
+    unsigned long long k_pre = 0;
+    float2 *d_z = nullptr;
+    size_t z_cap = 0;
+    std::vector<BankGroup> groups;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // ---- general path: one block per channel ----
     std::vector<orion_b200_block *> ch;
     std::vector<cudaStream_t> streams;
     cudaEvent_t ev_in = nullptr;
@@ -1283,8 +1329,154 @@ struct orion_b200_bank {
 namespace {
 const int kBankStreams = 8;
 int bank_fail(orion_b200_bank *k, int st, const std::string &what) { if (k) k->err = what; return st; }
+
+// ---- K5 fast path ------------------------------------------------------------------------------------------------
+// Eligible when every channel is  [Rotator | Nco mixer] -> FIR with the SAME taps and even decimation -> FM / PM / AM / CW
+// (demodulators that only see phase differences or magnitudes, so the closed-form oscillator is exact enough; see
+// want_exact_pre).  Anything else keeps the general one-block-per-channel path.
+bool bank_fast_eligible(const orion_b200_chain_spec *specs, size_t n) {
+    const orion_b200_chain_spec &s0 = specs[0];
+    if (getenv("ORION_B200_BANK_GENERAL")) return false;
+    if (s0.fir == FIR_NONE || !s0.taps || s0.ntaps == 0 || s0.decim < 2 || (s0.decim & 1)) return false;
+    if (s0.ntaps - 1 > 8 * s0.decim || s0.decim > 4096) return false;
+    for (size_t c = 0; c < n; ++c) {
+        const orion_b200_chain_spec &s = specs[c];
+        if (s.struct_size != sizeof(orion_b200_chain_spec)) return false;
+        if (s.mix != s0.mix || s.fir != s0.fir || s.decim != s0.decim || s.ntaps != s0.ntaps) return false;
+        if (memcmp(s.taps, s0.taps, s0.ntaps * sizeof(float)) != 0) return false;
+        if (!(s.demod == DEMOD_FM || s.demod == DEMOD_PM || s.demod == DEMOD_AM || s.demod == DEMOD_AM_ABS || s.demod == DEMOD_CW)) return false;
+        if (s.n_post && !s.post_sos) return false;
+    }
+    return true;
+}
+std::string bank_group_key(const orion_b200_chain_spec &s) {
+    std::string k;
+    auto put = [&k](const void *p, size_t n) { k.append((const char *)p, n); };
+    put(&s.demod, sizeof(s.demod)); put(&s.fs_demod, 4); put(&s.p0, 4); put(&s.p1, 4); put(&s.audio_bw_hz, 4);
+    put(&s.translate, sizeof(s.translate));
+    if (s.translate) put(&s.translate_hz, 4);
+    put(&s.n_post, sizeof(s.n_post));
+    if (s.n_post) put(s.post_sos, s.n_post * 5 * sizeof(float));
+    return k;
+}
+int bank_fast_create(orion_b200_bank *k, const orion_b200_chain_spec *specs, size_t n) {
+    const orion_b200_chain_spec &s0 = specs[0];
+    if (cudaSetDevice(k->device) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    k->fast = true;
+    k->nch = n;
+    k->mix = s0.mix; k->fir = s0.fir; k->M = s0.decim;
+    k->in_item = ORION_B200_ITEM_C32; k->out_item = ORION_B200_ITEM_F32;
+    FirPlan pl;
+    plan_fir(s0.fir, std::vector<float>(s0.taps, s0.taps + s0.ntaps), s0.decim, true, &pl);   // only the generic taps g[] are used
+    k->g = pl.g;
+    const int Lg = (int)k->g.size(), M = (int)k->M;
+    k->PM = std::max(1, (Lg - 1 + M - 1) / M);
+    k->H = ((Lg + 1) & ~1);
+    // polyphase table gt[i][p-1] = g[M*p - i]
+    std::vector<float> gt((size_t)M * k->PM, 0.f);
+    for (int i = 0; i < M; ++i)
+        for (int p = 1; p <= k->PM; ++p) {
+            const long long t = (long long)M * p - i;
+            if (t >= 1 && t < Lg) gt[(size_t)i * k->PM + (p - 1)] = k->g[t];
+        }
+    k->osc.resize(n);
+    std::vector<NcoParam> op(n);
+    for (size_t c = 0; c < n; ++c) {
+        if (k->mix != MIX_NONE) k->osc[c].set(specs[c].mix_freq_hz, specs[c].mix_fs, 0);
+        op[c] = k->osc[c].param(0);
+    }
+    if (cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    if (cudaMalloc(&k->d_osc, n * sizeof(NcoParam)) != cudaSuccess || cudaMalloc(&k->d_gt, gt.size() * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&k->d_hist[0], k->H * sizeof(float2)) != cudaSuccess || cudaMalloc(&k->d_hist[1], k->H * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc(&k->d_err, sizeof(int)) != cudaSuccess || cudaMallocHost(&k->h_err, sizeof(int)) != cudaSuccess)
+        return ORION_B200_ERR_ALLOC;
+    *k->h_err = 0;
+    cudaMemcpyAsync(k->d_osc, op.data(), n * sizeof(NcoParam), cudaMemcpyHostToDevice, k->stream);
+    cudaMemcpyAsync(k->d_gt, gt.data(), gt.size() * sizeof(float), cudaMemcpyHostToDevice, k->stream);
+    cudaMemsetAsync(k->d_hist[0], 0, k->H * sizeof(float2), k->stream);
+    cudaMemsetAsync(k->d_hist[1], 0, k->H * sizeof(float2), k->stream);
+    cudaMemsetAsync(k->d_err, 0, sizeof(int), k->stream);
+    if (cudaStreamSynchronize(k->stream) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    // demodulator groups
+    std::vector<std::string> keys;
+    for (size_t c = 0; c < n; ++c) {
+        const std::string key = bank_group_key(specs[c]);
+        size_t gi = 0;
+        while (gi < keys.size() && keys[gi] != key) ++gi;
+        if (gi == keys.size()) { keys.push_back(key); k->groups.push_back(BankGroup()); }
+        k->groups[gi].chans.push_back((int)c);
+    }
+    for (BankGroup &g : k->groups) {
+        const orion_b200_chain_spec &s = specs[g.chans[0]];
+        orion_b200_block *b = nullptr;
+        int st = new_block(&g.proto, &b);
+        if (st != ORION_B200_OK) return st;
+        g.proto = nullptr;
+        b->nbatch = (int)g.chans.size();
+        demod_setup(b, s.demod, s.fs_demod, s.p0, s.p1, s.audio_bw_hz);
+        if (s.demod == DEMOD_FM && s.translate) { b->translate = 1; b->post.set(s.translate_hz, s.fs_demod, 0); }
+        for (size_t q = 0; q < s.n_post; ++q) b->secs.push_back(sec_biquad(s.post_sos + 5 * q));
+        orion_b200_block *made = nullptr;
+        st = finish_create(b, &made);
+        if (st != ORION_B200_OK) return st;
+        g.proto = made;
+        made->d_err_ext = k->d_err;
+        if (cudaMalloc(&made->d_batch_chan, g.chans.size() * sizeof(int)) != cudaSuccess) return ORION_B200_ERR_ALLOC;
+        if (cudaMemcpy(made->d_batch_chan, g.chans.data(), g.chans.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return ORION_B200_ERR_CUDA;
+        st = orion_b200_block_set_stream(made, (void *)k->stream);
+        if (st != ORION_B200_OK) return st;
+    }
+    return ORION_B200_OK;
+}
+int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
+                     size_t *in_read, size_t *out_written) {
+    const size_t M = k->M;
+    const size_t n_out_all = (n_in + M - 1) / M;
+    const size_t n_out = std::min(n_out_all, out_stride);              // decim.rs:66-75: capped by the output slice
+    if (in_read) *in_read = n_in;
+    if (out_written) *out_written = n_out;
+    if (n_in == 0) return ORION_B200_OK;
+    if (n_out_all * k->nch > k->z_cap) {
+        cudaStreamSynchronize(k->stream);
+        cudaFree(k->d_z); k->d_z = nullptr; k->z_cap = 0;
+        const size_t cap = n_out_all * k->nch + 1024;
+        if (cudaMalloc(&k->d_z, cap * sizeof(float2)) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_ALLOC, "bank scratch");
+        k->z_cap = cap;
+    }
+    BankFirArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = (const float2 *)d_in; a.n_in = (long long)n_in; a.n_out = (long long)n_out_all;
+    a.hist_in = k->d_hist[k->pp]; a.hist_out = k->d_hist[k->pp ^ 1]; a.H = k->H;
+    a.mix = k->mix; a.osc = k->d_osc; a.kbase = k->k_pre;
+    a.M = (int)M; a.Lg = (int)k->g.size(); a.PM = k->PM;
+    a.BT = std::max(k->PM, std::max(1, 2048 / (int)M));               // 16 KB tiles (16 blocks of 128 samples)
+    a.NS = 4;
+    a.gt = k->d_gt; a.g0 = k->g[0];
+    a.z = k->d_z; a.z_stride = (long long)n_out_all; a.nch = (int)k->nch;
+    a.tiles_total = ((long long)n_out_all + a.BT - 1) / a.BT;
+    a.err_flag = k->d_err;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, k->device);
+    const int ngroups = (int)((k->nch + 255) / 256);
+    long long want = std::max<long long>(1, (2LL * sms + ngroups - 1) / ngroups);    // two CTAs per SM
+    if (const char *e = getenv("ORION_B200_BANK_RANGES")) want = std::max(1, atoi(e));
+    a.tiles_per_range = (int)std::max<long long>(1, (a.tiles_total + want - 1) / want);
+    const int nranges = (int)((a.tiles_total + a.tiles_per_range - 1) / a.tiles_per_range);
+    cudaError_t e = bank_fir_launch(a, nranges, k->stream);
+    if (e != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, std::string("bank front-end launch: ") + cudaGetErrorString(e));
+    k->launches += 1;
+    k->pp ^= 1;
+    k->k_pre += n_in;
+    const size_t ob = 4;
+    for (BankGroup &g : k->groups) {
+        const int st = launch(g.proto, k->d_z, n_out, d_out, n_out, (long long)(n_out_all * sizeof(float2)), (long long)(out_stride * ob));
+        if (st != ORION_B200_OK) return bank_fail(k, st, "bank demodulator group: " + g.proto->err);
+    }
+    return ORION_B200_OK;
+}
 int bank_launch_all(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
                     size_t *in_read, size_t *out_written) {
+    if (k->fast) return bank_fast_launch(k, d_in, n_in, d_out, out_stride, in_read, out_written);
     const size_t ob = out_item_bytes(k->ch[0]);
     size_t r = 0, w = 0;
     for (size_t c = 0; c < k->ch.size(); ++c) {
@@ -1305,6 +1497,15 @@ int orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels
     if (!k) return ORION_B200_ERR_ALLOC;
     k->device = t_device;
     int st = ORION_B200_OK;
+    if (bank_fast_eligible(specs, n_channels)) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); delete k; return ORION_B200_ERR_NO_DEVICE; }
+        st = bank_fast_create(k, specs, n_channels);
+        if (st != ORION_B200_OK) { orion_b200_bank_destroy(k); return st; }
+        k->streams.assign(1, k->stream);
+        *out = k;
+        return ORION_B200_OK;
+    }
     for (size_t c = 0; c < n_channels && st == ORION_B200_OK; ++c) {
         orion_b200_block *b = nullptr;
         st = orion_b200_chain_create(&specs[c], &b);
@@ -1340,6 +1541,17 @@ int orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels
 void orion_b200_bank_destroy(orion_b200_bank *k) {
     if (!k) return;
     cudaSetDevice(k->device);
+    if (k->fast) {
+        if (k->stream) cudaStreamSynchronize(k->stream);
+        for (BankGroup &g : k->groups) if (g.proto) { g.proto->stream = g.proto->own_stream; orion_b200_block_destroy(g.proto); }
+        cudaFree(k->d_osc); cudaFree(k->d_gt); cudaFree(k->d_hist[0]); cudaFree(k->d_hist[1]); cudaFree(k->d_z);
+        cudaFree(k->d_in); cudaFree(k->d_out); cudaFree(k->d_err);
+        if (k->h_err) cudaFreeHost(k->h_err);
+        if (k->stream) cudaStreamDestroy(k->stream);
+        cudaGetLastError();
+        delete k;
+        return;
+    }
     for (cudaStream_t s : k->streams) if (s) cudaStreamSynchronize(s);
     for (orion_b200_block *b : k->ch) { if (b) { b->stream = b->own_stream; orion_b200_block_destroy(b); } }
     for (cudaStream_t s : k->streams) if (s) cudaStreamDestroy(s);
@@ -1352,14 +1564,26 @@ void orion_b200_bank_destroy(orion_b200_bank *k) {
 }
 int orion_b200_bank_reset(orion_b200_bank *k) {
     if (!k) return ORION_B200_ERR_INVALID;
+    if (k->fast) {
+        if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
+        cudaStreamSynchronize(k->stream);
+        cudaMemsetAsync(k->d_hist[0], 0, k->H * sizeof(float2), k->stream);
+        cudaMemsetAsync(k->d_hist[1], 0, k->H * sizeof(float2), k->stream);
+        cudaStreamSynchronize(k->stream);
+        k->k_pre = 0;
+        for (Osc &o : k->osc) o.reset_phase();
+        for (BankGroup &g : k->groups) { const int st = reset_state(g.proto); if (st) return bank_fail(k, st, g.proto->err); }
+        return ORION_B200_OK;
+    }
     for (orion_b200_block *b : k->ch) { const int st = reset_state(b); if (st) return bank_fail(k, st, b->err); }
     return ORION_B200_OK;
 }
-size_t orion_b200_bank_channels(const orion_b200_bank *k) { return k ? k->ch.size() : 0; }
+size_t orion_b200_bank_channels(const orion_b200_bank *k) { return k ? (k->fast ? k->nch : k->ch.size()) : 0; }
 const char *orion_b200_bank_last_error(const orion_b200_bank *k) { return k ? k->err.c_str() : "null bank"; }
 uint64_t orion_b200_bank_launch_count(const orion_b200_bank *k) {
     uint64_t n = 0;
     if (k) for (const orion_b200_block *b : k->ch) n += b->launches;
+    if (k && k->fast) { n = k->launches; for (const BankGroup &g : k->groups) n += g.proto->launches; }
     return n;
 }
 int orion_b200_bank_process_dev(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
@@ -1393,8 +1617,8 @@ int orion_b200_bank_process(orion_b200_bank *k, const void *in, size_t n_in, voi
     if (!k || (n_in && !in) || (out_stride && !out)) return k ? bank_fail(k, ORION_B200_ERR_INVALID, "null buffer") : ORION_B200_ERR_INVALID;
     if (n_in == 0) return ORION_B200_OK;
     if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
-    const size_t ib = n_in * in_item_bytes(k->ch[0]);
-    const size_t ob = k->ch.size() * out_stride * out_item_bytes(k->ch[0]);
+    const size_t ib = n_in * (k->fast ? 8 : in_item_bytes(k->ch[0]));
+    const size_t ob = (k->fast ? k->nch * out_stride * 4 : k->ch.size() * out_stride * out_item_bytes(k->ch[0]));
     if (ib > k->d_in_cap) {
         for (cudaStream_t s : k->streams) cudaStreamSynchronize(s);
         cudaFree(k->d_in); k->d_in = nullptr; k->d_in_cap = 0;
@@ -1409,7 +1633,7 @@ int orion_b200_bank_process(orion_b200_bank *k, const void *in, size_t n_in, voi
     }
     // the wideband slice goes up once on stream 0; every other stream waits for it
     if (cudaMemcpyAsync(k->d_in, in, ib, cudaMemcpyHostToDevice, k->streams[0]) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "H2D");
-    cudaEventRecord(k->ev_in, k->streams[0]);
+    if (k->ev_in) cudaEventRecord(k->ev_in, k->streams[0]);
     for (size_t i = 1; i < k->streams.size(); ++i) cudaStreamWaitEvent(k->streams[i], k->ev_in, 0);
     int st = bank_launch_all(k, k->d_in, n_in, k->d_out, out_stride, in_read, out_written);
     if (st != ORION_B200_OK) return st;
@@ -1427,7 +1651,7 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     for (int i = 0; i < 3; ++i) { cudaFree(b->d_hist[i]); cudaFree(b->d_carry[i]); }
     b->pre.x.free_device(); b->post.x.free_device();
     cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err); cudaFree(b->d_handoff);
-    cudaFree(b->d_in); cudaFree(b->d_out);
+    cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_batch_chan);
     if (b->h_err) cudaFreeHost(b->h_err);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     cudaGetLastError();

@@ -81,7 +81,7 @@ def test_bank_matches_block_by_block_composition():
     assert out.shape == (CFG["n_channels"], n // CFG["m"]) and out.dtype == np.float32
     for c in range(CFG["n_channels"]):
         assert_parity(out[c], c5_oracle_channel(oracle, x, c, **CFG), what=f"channel {c}")
-    assert bank.launch_count == CFG["n_channels"]
+    assert bank.launch_count == 3                # one shared front-end kernel + one batched launch per demodulator kind
     # streaming: a second call continues every channel's state
     x2 = c5_wideband(2 * n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
     bank.reset()
@@ -89,6 +89,40 @@ def test_bank_matches_block_by_block_composition():
     b = ob.ChannelBank(specs).process(x2)
     for c in range(CFG["n_channels"]):
         assert_parity(a[c], b[c], what=f"channel {c} two calls vs one")
+
+
+@pytest.mark.gpu
+def test_bank_general_path_agrees_with_the_batched_path(monkeypatch):
+    """Banks the batched kernels do not cover (here: forced) run one block per channel; both paths meet the oracle."""
+    n = 40_000
+    x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    specs = c5_specs(ob, **CFG)
+    fast = ob.ChannelBank(specs).process(x)
+    monkeypatch.setenv("ORION_B200_BANK_GENERAL", "1")
+    general_bank = ob.ChannelBank(specs)
+    general = general_bank.process(x)
+    assert general_bank.launch_count == CFG["n_channels"]
+    for c in range(CFG["n_channels"]):
+        ref = c5_oracle_channel(oracle, x, c, **CFG)
+        assert_parity(fast[c], ref, what=f"batched, channel {c}")
+        assert_parity(general[c], ref, what=f"general, channel {c}")
+
+
+@pytest.mark.gpu
+def test_bank_short_output_and_ragged_lengths():
+    """decim.rs:66-75 per channel: all input consumed, min(ceil(n/m), out_stride) outputs written; odd call lengths."""
+    import ctypes as C
+    specs = c5_specs(ob, **CFG)
+    bank = ob.ChannelBank(specs)
+    x = c5_wideband(30_011, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    a = np.concatenate([bank.process(x[:10_007]), bank.process(x[10_007:10_008]), bank.process(x[10_008:])], axis=1)
+    for c in (0, 5, 11):
+        xs = [x[:10_007], x[10_007:10_008], x[10_008:]]
+        rot = oracle.Rotator(-(c - 6) * CFG["spacing_hz"], CFG["fs"])
+        dec = oracle.FirDecimator(CFG["fs"], CFG["m"], CFG["cutoff_hz"], CFG["trans_hz"])
+        dem = oracle.FmQuadratureDemod(CFG["fs"] / CFG["m"], 2.5e3, 3e3) if c % 2 == 0 else oracle.AmEnvelopeDemod(CFG["fs"] / CFG["m"], 3e3)
+        ref = np.concatenate([dem.run(dec.run(rot.rotate_block(seg))) for seg in xs])
+        assert_parity(a[c], ref, what=f"ragged calls, channel {c}")
 
 
 @pytest.mark.gpu
