@@ -105,6 +105,9 @@ extern "C" {
     pub fn orion_b200_oscillator_reset_phase(b: *mut orion_b200_block) -> c_int;
     pub fn orion_b200_biquad_create(b0: f32, b1: f32, b2: f32, a1: f32, a2: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_lp_cascade_create(fs: f32, fc: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_agc_rms_create(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_agc_rms_iq_create(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_agc_env(b: *mut orion_b200_block) -> f32;
     pub fn orion_b200_lp_dc_cascade_create(fs: f32, lp_fc: f32, dc_cut_hz: f32, map_sqrt: c_int, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_dc_blocker_create(fs: f32, cut_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_iir_cascade_create(sos: *const f32, nsections: usize, out: *mut *mut orion_b200_block) -> c_int;
@@ -151,6 +154,7 @@ extern "C" {
     pub fn orion_b200_block_get_state(b: *mut orion_b200_block, state: *mut f32, cap: usize) -> usize;
     pub fn orion_b200_block_launch_count(b: *const orion_b200_block) -> u64;
     pub fn orion_b200_block_exact_host_ms(b: *const orion_b200_block) -> f64;
+    pub fn orion_b200_block_prepare_oscillator(b: *mut orion_b200_block, n_in_per_call: usize, n_calls: usize) -> c_int;
     pub fn orion_b200_last_create_error() -> *const c_char;
     pub fn orion_b200_block_snapshot_size(b: *const orion_b200_block) -> usize;
     pub fn orion_b200_block_snapshot(b: *mut orion_b200_block, buf: *mut c_void, cap: usize) -> c_int;

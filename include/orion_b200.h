@@ -203,6 +203,17 @@ typedef struct orion_b200_chain_spec {
 int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block **out);
 
 /* ------------------------------------------------------------------------------------
+ * AGC (next-row scope): AgcRms (f32 -> f32, src/dsp/agc.rs:8-75) and AgcRmsIq (C32 -> C32, agc.rs:81-150).
+ * attack_ms / release_ms in milliseconds, target_rms the desired RMS amplitude; gain limits 0.05 .. 20 as in the
+ * reference.  The envelope is seeded from the first sample of a call while it is exactly 0 (agc.rs:58-61).
+ * The tracker is a data-dependent recurrence; the GPU evaluates it in chunks with a warm-up long enough that the
+ * envelope agrees with the reference's to 2^-26 relative (exact for the first chunk of every call).
+ * ---------------------------------------------------------------------------------- */
+int   orion_b200_agc_rms_create(float fs, float attack_ms, float release_ms, float target_rms, orion_b200_block **out);
+int   orion_b200_agc_rms_iq_create(float fs, float attack_ms, float release_ms, float target_rms, orion_b200_block **out);
+float orion_b200_agc_env(orion_b200_block *b);      /* the tracked power `env` after the last call (synchronises) */
+
+/* ------------------------------------------------------------------------------------
  * Channel bank: C independent narrowband chains fed by ONE wideband input (BASELINE config 5).
  * Channel c is exactly the block `orion_b200_chain_create(&specs[c])` would build -- typically
  * Rotator(-f_c).rotate_block -> FirDecimator -> FM/AM demod -- with its own streaming state, i.e. what the
@@ -274,6 +285,12 @@ int orion_b200_block_set_stream(orion_b200_block *b, void *cuda_stream);
 int orion_b200_block_set_option(orion_b200_block *b, int option, double value);
 /* host milliseconds this block has spent walking the oscillator recurrence (exact mode) since creation [host-only] */
 double orion_b200_block_exact_host_ms(const orion_b200_block *b);
+/* Walk the exact-mode oscillator(s) of the block AHEAD of the stream: enough for the next `n_calls` process() calls of
+ * `n_in_per_call` input items each (the phasor sequence of rotator.rs:44-61 does not depend on the data, so it can be
+ * produced before the samples arrive -- e.g. while the previous buffer is still being captured).  process() then only
+ * copies the anchors it needs; without this call it walks its own n_in items inline.  Host time goes to
+ * orion_b200_block_exact_host_ms.  No-op for blocks that use the closed-form phase.  [host-only] */
+int orion_b200_block_prepare_oscillator(orion_b200_block *b, size_t n_in_per_call, size_t n_calls);
 
 /* Streaming-state snapshot for the parity harness.  Layout (20 floats):
  * [0..1] discriminator prev (re,im); [2..3] oscillator call counters (input-rate, demod-rate,

@@ -115,6 +115,9 @@ def lib():
     sig("oo_ssb_mod_new", vp, f, f, f, f, i)
     sig("oo_cw_mod_new", vp, f, f, f, f)
     sig("oo_mod_set_gain", None, vp, f)
+    sig("oo_agc_rms_new", vp, f, f, f, f)
+    sig("oo_agc_rms_iq_new", vp, f, f, f, f)
+    sig("oo_agc_env", f, vp)
     _lib = L
     return L
 
@@ -485,6 +488,30 @@ class SsbPhasingMod(_Mod):                            # src/modulate/ssb.rs:11-1
 class CwKeyedMod(_Mod):                               # src/modulate/cw.rs:10-102
     def __init__(self, sample_rate, tone_hz, rise_ms, fall_ms):
         super().__init__(lib().oo_cw_mod_new(sample_rate, tone_hz, rise_ms, fall_ms))
+
+
+class AgcRms(Block):                                  # src/dsp/agc.rs:8-75
+    In = np.float32
+    Out = np.float32
+
+    def __init__(self, fs, attack_ms, release_ms, target_rms):
+        super().__init__(lib().oo_agc_rms_new(fs, attack_ms, release_ms, target_rms))
+
+    @property
+    def env(self):
+        return float(lib().oo_agc_env(self._h))
+
+
+class AgcRmsIq(Block):                                # src/dsp/agc.rs:81-150
+    In = np.complex64
+    Out = np.complex64
+
+    def __init__(self, fs, attack_ms, release_ms, target_rms):
+        super().__init__(lib().oo_agc_rms_iq_new(fs, attack_ms, release_ms, target_rms))
+
+    @property
+    def env(self):
+        return float(lib().oo_agc_env(self._h))
 
 
 # ---- chain wrappers (src/core.rs:25-109): single-block, return input.len() items ----

@@ -356,3 +356,35 @@ def cw_demod(fs, env_bw, x, gain=1.0):
         y = f32(f32(a * y) + f32(oma * mag[i]))
         out[i] = f32(y * f32(gain))
     return out
+
+
+def agc_rms(fs, attack_ms, release_ms, target_rms, x, env0=0.0, iq=False):
+    """AgcRms / AgcRmsIq (src/dsp/agc.rs:20-74, :93-149), numpy-f32 restatement; returns (out, env)."""
+    fs = f32(fs)
+    a_att = expf(f32(-1.0) / f32(fs * f32(max(f32(attack_ms), f32(1e-3)) / f32(1000.0))))
+    a_rel = expf(f32(-1.0) / f32(fs * f32(max(f32(release_ms), f32(1e-3)) / f32(1000.0))))
+    target = max(f32(target_rms), f32(1e-6))
+    if iq:
+        x = np.asarray(x, np.complex64)
+        re = x.real.astype(f32); im = x.imag.astype(f32)
+        x2 = ((re * re).astype(f32) + (im * im).astype(f32)).astype(f32)
+        out = np.zeros(x.size, np.complex64)
+    else:
+        x = np.asarray(x, f32)
+        x2 = (x * x).astype(f32)
+        out = np.zeros(x.size, f32)
+    env = f32(env0)
+    if x.size and env == f32(0.0):
+        env = max(x2[0], f32(1e-12))
+    one = f32(1.0)
+    for i in range(x.size):
+        a = a_att if x2[i] > env else a_rel
+        env = f32(f32(a * env) + f32(f32(one - a) * x2[i]))
+        rms = max(f32(np.sqrt(env)), f32(1e-6))
+        g = f32(target / rms)
+        g = min(max(g, f32(0.05)), f32(20.0))
+        if iq:
+            out[i] = np.complex64(complex(f32(g * re[i]), f32(g * im[i])))
+        else:
+            out[i] = f32(g * x[i])
+    return out, env

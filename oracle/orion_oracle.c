@@ -170,7 +170,8 @@ enum {
     K_FIR_LOWPASS = 1, K_FIR_DECIM, K_FIR_IQ, K_ROTATOR, K_NCO, K_BIQUAD, K_LP_CASCADE,
     K_LP_DC_CASCADE, K_DC_BLOCKER, K_FM, K_PM, K_AM, K_SSB, K_CW,
     K_MOD_FM, K_MOD_PM, K_MOD_AM, K_MOD_SSB, K_MOD_CW,     /* f32 -> c32; SURVEY.md 8(f) row 1 */
-    K_HCMF                                                 /* HalfCosineMf, SURVEY.md 8(f) row 2 */
+    K_HCMF,                                                /* HalfCosineMf, SURVEY.md 8(f) row 2 */
+    K_AGC, K_AGC_IQ                                        /* AgcRms / AgcRmsIq, SURVEY.md 8(f) row 3 */
 };
 
 typedef struct { float *taps; float *delay; size_t len, idx; } fir_real;     /* fir.rs:7-12 */
@@ -204,6 +205,8 @@ struct oo_block {
     oo_c32 mz; uint32_t mctr;        /* FM running phasor + its renorm counter */
     float carrier, mindex; int clamp, usb;
     float env, a_rise, a_fall;
+    /* AGC (src/dsp/agc.rs): env above, a_rise = attack_a, a_fall = release_a */
+    float target_rms, min_gain, max_gain;
 };
 
 static void fir_real_init(fir_real *f, const float *taps, size_t n) {
@@ -571,6 +574,34 @@ oo_block *oo_cw_mod_new(float fs, float tone_hz, float rise_ms, float fall_ms) {
 }
 void oo_mod_set_gain(oo_block *b, float g) { b->gain = g; }
 
+/* AgcRms::new / AgcRmsIq::new, src/dsp/agc.rs:20-31,93-104 */
+static oo_block *agc_new(int kind, float fs, float attack_ms, float release_ms, float target_rms) {
+    oo_block *b = blk_new(kind);
+    b->fs = fs;
+    b->a_rise = expf(-1.0f / (fs * (oo_maxf(attack_ms, 1e-3f) / 1000.0f)));
+    b->a_fall = expf(-1.0f / (fs * (oo_maxf(release_ms, 1e-3f) / 1000.0f)));
+    b->target_rms = oo_maxf(target_rms, 1e-6f);
+    b->min_gain = 0.05f; b->max_gain = 20.0f;
+    b->env = 0.0f;
+    return b;
+}
+oo_block *oo_agc_rms_new(float fs, float attack_ms, float release_ms, float target_rms) {
+    return agc_new(K_AGC, fs, attack_ms, release_ms, target_rms);
+}
+oo_block *oo_agc_rms_iq_new(float fs, float attack_ms, float release_ms, float target_rms) {
+    return agc_new(K_AGC_IQ, fs, attack_ms, release_ms, target_rms);
+}
+float oo_agc_env(const oo_block *b) { return b->env; }
+/* agc.rs:33-40 (update_env) + :64-69: gain from the tracked power */
+static inline float agc_gain_step(oo_block *b, float x2) {
+    float a = (x2 > b->env) ? b->a_rise : b->a_fall;
+    b->env = a * b->env + (1.0f - a) * x2;
+    float rms = oo_maxf(sqrtf(b->env), 1e-6f);
+    float g = b->target_rms / rms;
+    g = oo_minf(oo_maxf(g, b->min_gain), b->max_gain);       /* f32::clamp */
+    return g;
+}
+
 void oo_reset(oo_block *b) {
     if (b->fi.delay) { memset(b->fi.delay, 0, b->fi.len * sizeof(float)); b->fi.idx = 0; }
     if (b->fq.delay) { memset(b->fq.delay, 0, b->fq.len * sizeof(float)); b->fq.idx = 0; }
@@ -894,6 +925,28 @@ oo_work_report oo_process(oo_block *b, const void *in, size_t n_in, void *out, s
                                      : b->a_fall * b->env + (1.0f - b->a_fall) * tgt;
             oo_c32 base = { b->env * b->gain, 0.0f };
             cout[i] = mix_nco_step(&b->rot, base);
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
+    case K_AGC:                                              /* agc.rs:47-74 */
+        if (n == 0) break;
+        if (b->env == 0.0f) b->env = oo_maxf(fin[0] * fin[0], 1e-12f);
+        for (size_t i = 0; i < n; ++i) {
+            float x = fin[i];
+            float g = agc_gain_step(b, x * x);
+            fout[i] = g * x;
+        }
+        wr.in_read = n; wr.out_written = n;
+        break;
+
+    case K_AGC_IQ:                                           /* agc.rs:121-149 */
+        if (n == 0) break;
+        if (b->env == 0.0f) b->env = oo_maxf(cin[0].re * cin[0].re + cin[0].im * cin[0].im, 1e-12f);
+        for (size_t i = 0; i < n; ++i) {
+            oo_c32 x = cin[i];
+            float g = agc_gain_step(b, x.re * x.re + x.im * x.im);
+            cout[i].re = g * x.re; cout[i].im = g * x.im;
         }
         wr.in_read = n; wr.out_written = n;
         break;

@@ -105,6 +105,9 @@ void      oo_am_mod_set_clamp(oo_block *b, int on);
 oo_block *oo_ssb_mod_new(float fs, float audio_bw_hz, float audio_if_hz, float rf_hz, int usb); /* modulate/ssb.rs:23-114 */
 oo_block *oo_cw_mod_new(float fs, float tone_hz, float rise_ms, float fall_ms); /* modulate/cw.rs:21-102 */
 void      oo_mod_set_gain(oo_block *b, float g);
+oo_block *oo_agc_rms_new(float fs, float attack_ms, float release_ms, float target_rms);     /* src/dsp/agc.rs:8-75 (f32 -> f32) */
+oo_block *oo_agc_rms_iq_new(float fs, float attack_ms, float release_ms, float target_rms);  /* src/dsp/agc.rs:81-150 (c32 -> c32) */
+float     oo_agc_env(const oo_block *b);
 
 /* test accelerators (see the .c): the outputs [j0, j1) a keep-every-m-th caller retains from a FRESH
  * FirDecimator / FirLowpassIq fed x[0, n) -- bit-identical to running the block loop-for-loop */

@@ -279,12 +279,25 @@ DEV float2 mix_apply(int mix, float2 x, float2 p) {
     return make_float2(x.x * p.x - x.y * p.y, x.x * p.y + x.y * p.x);   // nco.rs:63-66
 }
 
+// n / d rounded to nearest like the IEEE division the reference performs, without the compiler's out-of-line slow
+// path (a CALL with spills around it in the middle of the demodulator loop): reciprocal refined by one Newton step,
+// quotient corrected with the exact FMA remainder (Markstein).  Operands here are finite with d >= 2^-23 (an epsilon
+// is added to the denominator) and 0 <= n <= d, where the sequence returns the correctly rounded quotient.
+DEV float div_rn_fast(float n, float d) {
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d));
+    const float r1 = fmaf(fmaf(-d, r0, 1.0f), r0, r0);
+    const float q = n * r1;
+    const float rem = fmaf(-d, q, n);
+    return fmaf(rem, r1, q);
+}
+
 // util.rs:305-322, op for op
 DEV float atan2_approx(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const bool sw = ax < ay;
     const float mn = sw ? ax : ay, mx = sw ? ay : ax;
-    const float r = mn / (mx + 1.1920929e-07f);
+    const float r = div_rn_fast(mn, mx + 1.1920929e-07f);
     const float r2 = r * r;
     float phi = r * (0.78539816339744830962f + r2 * (-0.2447f + r2 * 0.0663f));
     if (sw) phi = 1.57079632679489661923f - phi;

@@ -36,6 +36,17 @@ struct BankFirArgs {             // bank_kernels.cu
 };
 size_t bank_fir_smem_bytes(const BankFirArgs &a);
 cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, cudaStream_t stream);
+chain_kernel_t get_kernel_ws(int dm);                       // chain_inst_ws.cu: warp-specialised decimate-by-8 chain
+size_t ws_dyn_smem(int nstages, int ntaps2, int Lg);
+int ws_warps();
+int ws_max_stages(size_t smem_limit, int ntaps2, int Lg);
+struct AgcArgs {                 // agc_kernels.cu
+    const void *in; void *out; long long n; int iq;
+    float attack_a, release_a, target_rms, min_gain, max_gain;
+    long long L, W;
+    const CarryState *carry_in; CarryState *carry_out;
+};
+cudaError_t agc_launch(const AgcArgs &a, cudaStream_t stream);
 cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, unsigned long long c0, long long fine_len,
                               cudaStream_t stream);
 }  // namespace orion
@@ -257,7 +268,8 @@ void build_group(const SecParam *secs, const GroupHost &gh, int npt, GroupParam 
 // ---- exact-replay oscillator: the reference recurrence walked on the host --------------------------------------
 // rotator.rs:44-61 / nco.rs:42-58 restated: z <- (fma(zr, wr, -(zi*wi)), fma(zi, wr, zr*wi)); every 1024 steps
 // z *= 1 / sqrt(|z|^2).  The walk is inherently sequential (each step rounds), ~3 ns per step on a host core; it leaves
-// one anchor per 1024 items of a call, from which the device replays in parallel (chain_kernels.cuh).
+// one anchor per 1024 steps, from which the device replays in parallel (chain_kernels.cuh).  The sequence is independent
+// of the data, so a caller may have it walked ahead of the stream (orion_b200_block_prepare_oscillator).
 struct ExactOsc {
     bool enabled = false;
     float wre = 1.f, wim = 0.f;               // the reference's f32 step (cosf(phi), sinf(phi))
@@ -274,20 +286,64 @@ struct ExactOsc {
     float2 *h_hist = nullptr;
     cudaEvent_t staged = nullptr;             // the last upload from the pinned staging buffers has completed
 
+    // Look-ahead: anc[i] = Z(origin_ctr + 1024 i).  The sequence does not depend on the data, so it may be walked any
+    // distance ahead of the items consumed so far (orion_b200_block_prepare_oscillator); a call only copies the anchors
+    // its items need.  (ctr, zr, zi) stays the state after the last CONSUMED item.
+    unsigned long long origin_ctr = 0;
+    std::vector<float2> anc;
+
+    void rebase() {                           // the consumed state becomes the origin of a fresh walk
+        origin_ctr = ctr;
+        anc.assign(1, make_float2(zr, zi));
+    }
     void set_freq(float freq_hz, float fs) {  // rotator.rs:16-18,35-38
         const float phi = kTau * freq_hz / fs;
         wre = cosf(phi); wim = sinf(phi);
+        rebase();
     }
-    void reset_phase() { zr = 1.f; zi = 0.f; ctr = 0; }     // rotator.rs:28-31; the FIR history keeps what it was mixed with
-    inline void step() {
-        const float nr = fmaf(zr, wre, -(zi * wim));
-        const float ni = fmaf(zi, wre, zr * wim);
-        zr = nr; zi = ni;
-        ctr += 1;
-        if ((ctr & 0x3FFull) == 0) {
-            const float r2 = zr * zr + zi * zi;
+    void reset_phase() { zr = 1.f; zi = 0.f; ctr = 0; rebase(); }     // rotator.rs:28-31; the FIR history keeps what it was mixed with
+    static inline void step1(float &r, float &i, unsigned long long &c, const float wr, const float wi) {
+        const float nr = fmaf(r, wr, -(i * wi));
+        const float ni = fmaf(i, wr, r * wi);
+        r = nr; i = ni;
+        c += 1;
+        if ((c & 0x3FFull) == 0) {
+            const float r2 = r * r + i * i;
             const float inv = 1.0f / sqrtf(r2);
-            zr *= inv; zi *= inv;
+            r *= inv; i *= inv;
+        }
+    }
+    // anchors up to and including the one at or below counter c
+    void ensure(unsigned long long c) {
+        if (anc.empty()) rebase();
+        const size_t need = (size_t)((c - origin_ctr) >> 10) + 1;
+        if (anc.size() >= need) return;
+        anc.reserve(need + need / 8);
+        float r = anc.back().x, i = anc.back().y;
+        unsigned long long cc = origin_ctr + (((unsigned long long)anc.size() - 1ull) << 10);
+        const float wr = wre, wi = wim;
+        while (anc.size() < need) {
+            for (int k = 0; k < 1024; ++k) step1(r, i, cc, wr, wi);
+            anc.push_back(make_float2(r, i));
+        }
+    }
+    // Z(c), c >= origin_ctr: replay from the anchor below it
+    float2 at(unsigned long long c) {
+        ensure(c);
+        const size_t a = (size_t)((c - origin_ctr) >> 10);
+        float r = anc[a].x, i = anc[a].y;
+        unsigned long long cc = origin_ctr + ((unsigned long long)a << 10);
+        while (cc < c) step1(r, i, cc, wre, wim);
+        return make_float2(r, i);
+    }
+    // the consumed state moves to counter c (>= ctr); anchors far behind it are dropped
+    void consume_to(unsigned long long c) {
+        const float2 z = at(c);
+        ctr = c; zr = z.x; zi = z.y;
+        const size_t a = (size_t)((c - origin_ctr) >> 10);
+        if (a >= 65536) {
+            anc.erase(anc.begin(), anc.begin() + (long)a);
+            origin_ctr += (unsigned long long)a << 10;
         }
     }
     void free_device() {
@@ -459,11 +515,14 @@ struct orion_b200_block {
     int opt_exact = -1;                   // -1 auto (by block kind), 0 closed form everywhere, 1 exact everywhere
     double exact_host_ms = 0.0;           // host time spent walking the recurrence (reported separately from kernel time)
     int cw_gain_sec = -1;
+    int agc = 0;                          // 1: AgcRms (f32), 2: AgcRmsIq (C32) -- agc_kernels.cu instead of the chain kernel
+    float agc_attack_a = 0.f, agc_release_a = 0.f, agc_target = 0.f, agc_min_gain = 0.05f, agc_max_gain = 20.0f;
     // ---- plan ----
     FirPlan plan;
     bool plan_dirty = true;
     chain_kernel_t kernel = nullptr;
     int ctas_per_sm = 1, sm_count = 1;
+    int ws = 0;                           // the warp-specialised instance is selected
     // ---- options ----
     int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0, opt_overlap = 0;
     long long *trace = nullptr;           // debug: device buffer of 8 x int64 per tile
@@ -560,6 +619,20 @@ int finalize_plan(orion_b200_block *b) {
                        sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
                        (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +                             // + per-lane scan tables (LR4 instance)
                        (b->plan.front == FRONT_DIRECT ? (size_t)b->plan.warps * 32 * 144 + 16 : 0);  // + transposing scratch (rate-1 blocks)
+    // FIR /8 + FM | PM + LR4 (the C1 chain): the warp-specialised instance (chain_inst_ws.cu) unless ORION_B200_NO_WS is set
+    b->ws = 0;
+    if (sp == 1 && (dm == 100 + DEMOD_FM || dm == 100 + DEMOD_PM) && b->nbatch == 1 && !b->opt_serial && !getenv("ORION_B200_NO_WS")) {
+        chain_kernel_t kw = get_kernel_ws(dm);
+        if (kw) {
+            b->kernel = kw;
+            b->ws = 1;
+            b->plan.warps = ws_warps();
+            int ns = ws_max_stages(227 * 1024, (int)b->plan.taps2.size(), (int)b->plan.g.size());
+            if (const char *e = getenv("ORION_B200_STAGES")) ns = std::max(1, std::min(ns, atoi(e)));
+            b->plan.nstages = ns;
+            b->plan.dyn_smem = ws_dyn_smem(ns, (int)b->plan.taps2.size(), (int)b->plan.g.size());
+        }
+    }
     CK(chain_kernel_prepare(b->kernel, b->plan.dyn_smem, b->plan.warps, &b->ctas_per_sm));
     if (b->ctas_per_sm < 1) return fail(b, ORION_B200_ERR_INTERNAL, "kernel does not fit on an SM");
     // FIR taps + history
@@ -722,7 +795,8 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     if (x.ctr != kbase)
         return fail(b, ORION_B200_ERR_INVALID, "exact oscillator mode must be selected before the first call after a reset");
     if (n_items == 0) return ORION_B200_OK;
-    const size_t n_an = (n_items + 1023) / 1024;
+    const size_t n_an = (n_items + 1023) / 1024 + 2;      // capacity: the consumed state + one per 1024-grid point
+    size_t n_an_used = 0;
     const long long fine_len = (long long)((n_items - 1) >> 4) + 1;
     if (!x.staged) CK(cudaEventCreateWithFlags(&x.staged, cudaEventDisableTiming));
     else CK(cudaEventSynchronize(x.staged));               // the pinned staging buffers are free again
@@ -755,44 +829,49 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     // phasors of the items before this call (newest last)
     const size_t nh = std::min(x.recent.size(), hist_len);
     for (size_t i = 0; i < nh; ++i) x.h_hist[i] = x.recent[x.recent.size() - nh + i];
-    // the walk
+    // the walk (nothing to do for the part orion_b200_block_prepare_oscillator has covered already)
     timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     const unsigned long long ctr0 = x.ctr;
-    const unsigned long long c_last = ctr0 + 1ull + 16ull * (unsigned long long)(fine_len - 1);
-    std::vector<float2> tail;
-    const size_t n_tail = std::min(n_items, hist_len);
-    tail.reserve(n_tail);
-    size_t done = 0;
-    for (size_t a = 0; a < n_an; ++a) {
-        OscAnchor &A = x.h_an[a];
-        A.ctr = x.ctr; A.z = make_float2(x.zr, x.zi); A.w = make_float2(x.wre, x.wim);
-        A.nsteps = (unsigned)std::min<unsigned long long>(1024ull, c_last - x.ctr);
-        A.pad = 0;
-        const size_t m = std::min<size_t>(1024, n_items - done);
-        if (done + m + n_tail > n_items) {                 // the last hist_len phasors of the call feed the next call's history
-            for (size_t i = 0; i < m; ++i) {
-                x.step();
-                if (done + i + n_tail >= n_items) tail.push_back(make_float2(x.zr, x.zi));
-            }
-        } else {
-            for (size_t i = 0; i < m; ++i) x.step();
+    const unsigned long long c_last = ctr0 + 1ull + 16ull * (unsigned long long)(fine_len - 1);   // last counter the expansion writes
+    x.ensure(ctr0 + (unsigned long long)n_items);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    b->exact_host_ms += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    // device anchors: anchor 0 is the consumed state itself, the others sit on the walk's 1024-grid
+    {
+        size_t k = 0;
+        OscAnchor &A0 = x.h_an[k++];
+        const unsigned long long g1 = x.origin_ctr + ((((ctr0 - x.origin_ctr) >> 10) + 1ull) << 10);   // first grid point above ctr0
+        A0.ctr = ctr0; A0.z = make_float2(x.zr, x.zi); A0.w = make_float2(x.wre, x.wim);
+        A0.nsteps = (unsigned)(std::min(g1, c_last) - ctr0); A0.pad = 0;
+        for (unsigned long long g = g1; g < c_last; g += 1024ull) {
+            OscAnchor &A = x.h_an[k++];
+            A.ctr = g; A.z = x.anc[(size_t)((g - x.origin_ctr) >> 10)]; A.w = make_float2(x.wre, x.wim);
+            A.nsteps = (unsigned)std::min<unsigned long long>(1024ull, c_last - g); A.pad = 0;
         }
-        done += m;
+        n_an_used = k;
     }
-    if (hist_len) {
+    if (hist_len) {                                            // the last hist_len phasors of the call feed the next call's history
+        const size_t n_tail = std::min(n_items, hist_len);
+        std::vector<float2> tail(n_tail);
+        const unsigned long long c_first = ctr0 + (unsigned long long)(n_items - n_tail) + 1ull;   // item i sees Z(ctr0 + i + 1)
+        float2 z = x.at(c_first);
+        unsigned long long cc = c_first;
+        for (size_t i = 0; i < n_tail; ++i) {
+            tail[i] = z;
+            ExactOsc::step1(z.x, z.y, cc, x.wre, x.wim);
+        }
         if (n_tail >= hist_len) x.recent.swap(tail);
         else {
             x.recent.insert(x.recent.end(), tail.begin(), tail.end());
             if (x.recent.size() > hist_len) x.recent.erase(x.recent.begin(), x.recent.end() - (long)hist_len);
         }
     }
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    b->exact_host_ms += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
-    CK(cudaMemcpyAsync(x.d_an, x.h_an, n_an * sizeof(OscAnchor), cudaMemcpyHostToDevice, b->stream));
+    x.consume_to(ctr0 + (unsigned long long)n_items);
+    CK(cudaMemcpyAsync(x.d_an, x.h_an, n_an_used * sizeof(OscAnchor), cudaMemcpyHostToDevice, b->stream));
     if (nh) CK(cudaMemcpyAsync(x.d_hist, x.h_hist, nh * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
     CK(cudaEventRecord(x.staged, b->stream));
-    CK(osc_expand_launch(x.d_an, (int)n_an, x.d_fine, ctr0 + 1ull, fine_len, b->stream));
+    CK(osc_expand_launch(x.d_an, (int)n_an_used, x.d_fine, ctr0 + 1ull, fine_len, b->stream));
     b->launches += 1;
     np->exact = 1;
     np->xfine = x.d_fine; np->xfine_len = (int)fine_len;
@@ -801,11 +880,34 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     return ORION_B200_OK;
 }
 
+// AgcRms / AgcRmsIq: chunked evaluation of the data-dependent envelope recurrence (agc_kernels.cu)
+int launch_agc(orion_b200_block *b, const void *d_in, size_t n, void *d_out) {
+    AgcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = d_in; a.out = d_out; a.n = (long long)n; a.iq = b->agc == 2;
+    a.attack_a = b->agc_attack_a; a.release_a = b->agc_release_a; a.target_rms = b->agc_target;
+    a.min_gain = b->agc_min_gain; a.max_gain = b->agc_max_gain;
+    // warm-up: amax^W <= 2^-26  ->  W = 18.03 / -ln(amax)
+    const double amax = std::max((double)b->agc_attack_a, (double)b->agc_release_a);
+    double w = (amax > 0.0 && amax < 1.0) ? std::ceil(18.03 / -std::log(amax)) : 1.0;
+    if (amax >= 1.0) w = (double)n;                               // no contraction: one exact sequential chunk
+    a.W = (long long)std::min<double>(std::max(w, 1.0), (double)n);
+    a.L = std::max<long long>(std::max<long long>(a.W / 4, 64), ((long long)n + 65535) / 65536);
+    if (const char *e = getenv("ORION_B200_AGC_CHUNK")) a.L = std::max(1, atoi(e));        // experiments / tests
+    a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
+    cudaError_t e = agc_launch(a, b->stream);
+    if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "agc kernel launch", e);
+    b->launches += 1;
+    b->pp = (b->pp + 1) % 3;
+    return ORION_B200_OK;
+}
+
 int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
            long long batch_in_stride = 0, long long batch_out_stride = 0) {
     if (b->plan_dirty) { int st = finalize_plan(b); if (st) return st; }
     if (n_in == 0) return ORION_B200_OK;
     CK(cudaSetDevice(b->device));
+    if (b->agc) return launch_agc(b, d_in, n_in, d_out);
     const int npt = npt_of(b);
     const long long tile_items = (long long)kThreads * npt;
     long long ntiles = ((long long)n_out + tile_items - 1) / tile_items;
@@ -1290,6 +1392,31 @@ int orion_b200_mod_set_gain(orion_b200_block *b, float gain) {      // set_gain,
     return ORION_B200_OK;
 }
 
+// ---- AGC (next-row scope) ------------------------------------------------------------------
+static int agc_create(int kind, float fs, float attack_ms, float release_ms, float target_rms, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // AgcRms::new / AgcRmsIq::new, agc.rs:20-31, :93-104
+    b->agc = kind;
+    b->demod = kind == 1 ? DEMOD_F32 : DEMOD_NONE;                   // item types: f32 -> f32 | C32 -> C32
+    b->agc_attack_a = expf(-1.0f / (fs * (maxf_rs(attack_ms, 1e-3f) / 1000.0f)));
+    b->agc_release_a = expf(-1.0f / (fs * (maxf_rs(release_ms, 1e-3f) / 1000.0f)));
+    b->agc_target = maxf_rs(target_rms, 1e-6f);
+    return finish_create(b, out);
+}
+int orion_b200_agc_rms_create(float fs, float attack_ms, float release_ms, float target_rms, orion_b200_block **out) {
+    return agc_create(1, fs, attack_ms, release_ms, target_rms, out);
+}
+int orion_b200_agc_rms_iq_create(float fs, float attack_ms, float release_ms, float target_rms, orion_b200_block **out) {
+    return agc_create(2, fs, attack_ms, release_ms, target_rms, out);
+}
+float orion_b200_agc_env(orion_b200_block *b) {                     // the tracked power (agc.rs `env`), for the parity harness
+    if (!b || !b->agc) return 0.0f;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    CarryState cs;
+    if (cudaMemcpy(&cs, b->d_carry[b->pp], sizeof(cs), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0f;
+    return cs.pad.x;
+}
+
 // ---- channel bank --------------------------------------------------------------------------------
 struct BankGroup {                       // channels that share one demodulator configuration: one batched launch
     orion_b200_block *proto = nullptr;   // rate-1 block with nbatch members (kernel instance, section tables, per-member state)
@@ -1766,7 +1893,9 @@ int orion_b200_block_set_option(orion_b200_block *b, int option, double value) {
             if (b->opt_force_global != v) { b->opt_force_global = v; b->plan_dirty = true; }
             break;
         case ORION_B200_OPT_USE_TMA: b->opt_use_tma = v; break;
-        case ORION_B200_OPT_SERIAL_TILES: b->opt_serial = v; break;
+        case ORION_B200_OPT_SERIAL_TILES:
+            if (b->opt_serial != v) { b->opt_serial = v; b->plan_dirty = true; }     // the warp-specialised instance has no one-warp mode
+            break;
         case ORION_B200_OPT_OVERLAP_LAUNCHES: b->opt_overlap = v; break;
         case ORION_B200_OPT_EXACT_NCO: b->opt_exact = value < 0.0 ? -1 : v; break;
         default: return fail(b, ORION_B200_ERR_INVALID, "unknown option");
@@ -1878,6 +2007,7 @@ int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) 
         SnapshotExact xs;
         memcpy(&xs, p, sizeof(xs)); p += sizeof(xs);
         o->x.ctr = xs.ctr; o->x.zr = xs.zr; o->x.zi = xs.zi; o->x.wre = xs.wre; o->x.wim = xs.wim;
+        o->x.rebase();
         o->x.recent.clear();
         if (o == &b->pre) {
             const float2 *r = reinterpret_cast<const float2 *>(p);
@@ -1890,6 +2020,18 @@ int orion_b200_block_restore(orion_b200_block *b, const void *buf, size_t size) 
 
 uint64_t orion_b200_block_launch_count(const orion_b200_block *b) { return b ? b->launches : 0; }
 double orion_b200_block_exact_host_ms(const orion_b200_block *b) { return b ? b->exact_host_ms : 0.0; }
+int orion_b200_block_prepare_oscillator(orion_b200_block *b, size_t n_in_per_call, size_t n_calls) {
+    if (!b) return ORION_B200_ERR_INVALID;
+    size_t consume = 0, produce = 0;
+    length_rules(b, n_in_per_call, (size_t)-1, &consume, &produce);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (want_exact_pre(b)) b->pre.x.ensure(b->pre.x.ctr + (unsigned long long)consume * n_calls);
+    if (want_exact_post(b)) b->post.x.ensure(b->post.x.ctr + (unsigned long long)produce * n_calls);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    b->exact_host_ms += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    return ORION_B200_OK;
+}
 
 // debug: per-tile SM clock stamps (8 x int64 per tile, device pointer; NULL disables)
 int orion_b200_debug_set_trace(orion_b200_block *b, void *d_trace) {

@@ -97,6 +97,9 @@ def lib():
     sig("orion_b200_oscillator_reset_phase", i, vp)
     sig("orion_b200_biquad_create", i, f, f, f, f, f, pp)
     sig("orion_b200_lp_cascade_create", i, f, f, pp)
+    sig("orion_b200_agc_rms_create", i, f, f, f, f, pp)
+    sig("orion_b200_agc_rms_iq_create", i, f, f, f, f, pp)
+    sig("orion_b200_agc_env", f, vp)
     sig("orion_b200_lp_dc_cascade_create", i, f, f, f, i, pp)
     sig("orion_b200_dc_blocker_create", i, f, f, pp)
     sig("orion_b200_iir_cascade_create", i, vp, sz, pp)
@@ -124,6 +127,7 @@ def lib():
     sig("orion_b200_block_get_state", sz, vp, vp, sz)
     sig("orion_b200_block_launch_count", C.c_uint64, vp)
     sig("orion_b200_block_exact_host_ms", d, vp)
+    sig("orion_b200_block_prepare_oscillator", i, vp, sz, sz)
     sig("orion_b200_last_create_error", C.c_char_p)
     sig("orion_b200_block_snapshot_size", sz, vp)
     sig("orion_b200_block_snapshot", i, vp, vp, sz)
@@ -175,7 +179,8 @@ EXPORTED_SYMBOLS = [
     "orion_b200_bank_create", "orion_b200_bank_destroy", "orion_b200_bank_reset", "orion_b200_bank_channels",
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
-    "orion_b200_block_exact_host_ms", "orion_b200_last_create_error",
+    "orion_b200_block_exact_host_ms", "orion_b200_last_create_error", "orion_b200_block_prepare_oscillator",
+    "orion_b200_agc_rms_create", "orion_b200_agc_rms_iq_create", "orion_b200_agc_env",
 ]
 
 
@@ -383,6 +388,10 @@ class Block:
         """Host time spent walking the oscillator recurrence (exact-replay mode), reported apart from kernel time."""
         return float(lib().orion_b200_block_exact_host_ms(self._h))
 
+    def prepare_oscillator(self, n_in_per_call: int, n_calls: int = 1):
+        """Walk the exact-mode oscillator ahead of the stream (enough for `n_calls` calls of `n_in_per_call` items)."""
+        _check(lib().orion_b200_block_prepare_oscillator(self._h, n_in_per_call, n_calls), self._h)
+
 
 def _check_create(status):
     if status != OK:
@@ -552,6 +561,25 @@ class CwEnvelopeDemod(Block):                                         # src/demo
 
     def set_gain(self, g):
         _check(lib().orion_b200_cw_demod_set_gain(self._h, g), self._h)
+
+
+# ---- src/dsp/agc.rs (next-row scope) ----------------------------------------------------------------
+class AgcRms(Block):                                                  # src/dsp/agc.rs:8-75
+    def __init__(self, fs, attack_ms, release_ms, target_rms):
+        super().__init__(_mk("orion_b200_agc_rms_create", fs, attack_ms, release_ms, target_rms))
+
+    @property
+    def env(self) -> float:
+        return float(lib().orion_b200_agc_env(self._h))
+
+
+class AgcRmsIq(Block):                                                # src/dsp/agc.rs:81-150
+    def __init__(self, fs, attack_ms, release_ms, target_rms):
+        super().__init__(_mk("orion_b200_agc_rms_iq_create", fs, attack_ms, release_ms, target_rms))
+
+    @property
+    def env(self) -> float:
+        return float(lib().orion_b200_agc_env(self._h))
 
 
 # ---- src/modulate (next-row scope; the FM / SSB / CW modulators are not built on the GPU) ---------------

@@ -45,13 +45,16 @@ if "lp" in which:
     bench("LpCascade rate-1 (f32->f32)", ob.LpCascade(48e3, 4.5e3), n, torch.float32, n, torch.float32, 8.0)
 
 # ---- the other BASELINE configs at their full sizes (parity for them: tests/test_gpu_parity.py) -------------
-if "configs" in which:
+if "configs" in which: which = list(which) + ["c2", "c3", "c4"]
+if "c2" in which:
     t2 = ob.kaiser_lowpass_taps(201, 0.01, 60.0)
     bench("C2 rot+FIRiq201/25+SSB, 12 M @1.2 MS/s", ob.Chain(mix=ob.MIX_ROTATE, mix_freq_hz=-250e3, mix_fs=1.2e6, fir=ob.FIR_IQ, taps=t2, decim=25,
           demod=ob.DEMOD_SSB, fs_demod=48e3, p0=0.0, audio_bw_hz=2800.0), 12_000_000, torch.complex64, 480_000, torch.float32, 8.16)
+if "c3" in which:
     t3 = ob.fir_lowpass_design(384e3, 10e3, 6144.0)
     extra = np.stack([ob.lp_biquad_design(48e3, 3e3)] * 2)
     bench("C3 FIR63/8+AM+DC+LR4, 38.4 M @384 kS/s", ob.Chain(fir=ob.FIR_DECIM, taps=t3, decim=8, demod=ob.DEMOD_AM, fs_demod=48e3, audio_bw_hz=5e3,
           post_sos=extra), 38_400_000, torch.complex64, 4_800_000, torch.float32, 8.5)
+if "c4" in which:
     bench("C4 FirDecimator 1023/32, 100 M @100 MS/s", ob.FirDecimator(100e6, 32, 450e3, 97800.0), 100_000_000, torch.complex64, 3_125_000,
           torch.complex64, 8.25, reps=10, nbuf=2)

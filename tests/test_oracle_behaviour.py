@@ -231,3 +231,12 @@ def test_two_instances_are_independent_and_state_persists():
     c = oracle.FmQuadratureDemod(48_000.0, 2_500.0, 5_000.0)
     whole = c.run(np.concatenate([iq, iq]))
     np.testing.assert_array_equal(a.run(iq), whole[4096:])
+
+
+def test_agc_rms_converges_on_iq():                           # tests/unit/agc.rs:8-32
+    fs, n = 48_000.0, 8_000
+    x = np.where(np.arange(n) < n // 2, 0.02, 1.0).astype(np.float32).astype(np.complex64)
+    out = oracle.AgcRmsIq(fs, 0.2, 5.0, 0.2).run(x)
+    tail = out[n - 1000:]
+    rms_tail = np.sqrt(np.mean(np.abs(tail).astype(np.float64) ** 2))
+    assert abs(rms_tail - 0.2) < 0.03, rms_tail

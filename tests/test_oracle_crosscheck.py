@@ -152,3 +152,20 @@ def test_kept_output_accelerators_equal_the_loop_for_loop_blocks(L, m, n):
     # negative zero and denormal inputs go through the same adds
     x2 = x.copy(); x2[::7] = np.complex64(complex(-0.0, 1e-42))
     same(O.fir_decim_kept(taps, m, x2), O.FirDecimator(taps=taps, m=m).run(x2))
+
+
+@pytest.mark.parametrize("iq", [False, True])
+def test_agc_c_and_numpy_restatements_agree_bit_for_bit(iq):   # src/dsp/agc.rs:47-74, :121-149
+    r = np.random.default_rng(0xA6C)
+    n = 6000
+    lvl = np.where((np.arange(n) // 1500) % 2 == 0, 0.05, 0.9)
+    if iq:
+        x = (lvl * (r.standard_normal(n) + 1j * r.standard_normal(n))).astype(np.complex64)
+        blk = O.AgcRmsIq(48e3, 2.0, 40.0, 0.25)
+    else:
+        x = (lvl * r.standard_normal(n)).astype(np.float32)
+        blk = O.AgcRms(48e3, 2.0, 40.0, 0.25)
+    a = np.concatenate([blk.run(x[:2500]), blk.run(x[2500:])])            # env persists across calls
+    b, env = N.agc_rms(48e3, 2.0, 40.0, 0.25, x, iq=iq)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.float32(blk.env) == env
