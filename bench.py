@@ -184,16 +184,13 @@ def c5_wideband_torch(n, dev, n_channels, fs, spacing_hz, seed=0x0514):
     return x
 
 
-def run_c5(args):
+def measure_c5(args, rank, world, local, steps, cpu_baseline):
+    """The sharded 1024-channel workload on the ranks of the (already initialised) process group; returns the JSON
+    line as a dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     import orion_b200 as ob
     from signals import c5_oracle_channel, c5_specs, parity
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    ob.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     C = args.channels
     cfg = dict(C5, n_channels=C)
     n = args.samples if args.samples != N_SAMPLES else 8_192_000
@@ -203,24 +200,28 @@ def run_c5(args):
     specs = c5_specs(ob, **cfg)
     bank = ob.ChannelBank(specs, channels=mine)
     y = torch.empty((len(mine), n_out), dtype=torch.float32, device="cuda")
-    W, K = max(args.warmup, 3), args.steps
+    W, K = max(args.warmup, 3), steps
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    bank.set_stream(st.cuda_stream)
     for _ in range(W):
         bank.process_dev(x.data_ptr(), n, y.data_ptr(), n_out)
     bank.synchronize()
     barrier()
     l0 = bank.launch_count
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)                                        # device time on the bank's stream, max over ranks below
     for _ in range(K):
         bank.process_dev(x.data_ptr(), n, y.data_ptr(), n_out)
+    e1.record(st)
     bank.synchronize()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    barrier()
+    dt = e0.elapsed_time(e1) * 1e-3
     launches = bank.launch_count - l0
     if world > 1:
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -239,6 +240,11 @@ def run_c5(args):
     for i in sorted(set([0, 1, len(mine) // 2, len(mine) - 1])):
         e, snr = parity(yh[i], c5_oracle_channel(oracle_mod(), xh, mine[i], **cfg))
         worst_e, worst_snr = max(worst_e, e), min(worst_snr, snr)
+    worst = torch.tensor([worst_e, -worst_snr], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)        # every rank checks channels of its own shard
+    worst_e, worst_snr = float(worst[0].item()), -float(worst[1].item())
+    line = None
     if rank == 0:
         line = {"metric": "wideband input MS/s, 1024-channel bank (NCO->FIR513/128->FM|AM each), channels sharded across GPUs",
                 "value": n / (ms * 1e-3) / 1e6, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
@@ -247,9 +253,9 @@ def run_c5(args):
                            "channels_per_gpu": len(mine), "parallelism": f"channel ranges over {world} GPU(s), no collective",
                            "l2": "wideband input 65.5 MB is L2-resident by design (read once per channel)"},
                 "channel_msps": C * n / (ms * 1e-3) / 1e6, "gpu_launches": int(launches),
-                "parity_check": {"channels_checked": 4, "samples": nchk, "max_err_fs": worst_e, "snr_db": worst_snr,
+                "parity_check": {"channels_checked": 4 * world, "samples": nchk, "max_err_fs": worst_e, "snr_db": worst_snr,
                                  "pass": bool(worst_e <= 1e-4 and worst_snr >= 90.0)}}
-        if not args.no_cpu_baseline and world == 1:
+        if cpu_baseline and world == 1:
             import oracle
             ncpu = 819_200
             t1 = time.perf_counter()
@@ -259,6 +265,22 @@ def run_c5(args):
             nn = min(ncpu, nchk)
             line["cpu_baseline"] = {"value": nn / dtc / 1e6 / C, "unit": "MS/s", "cores": 1, "kind": "port",
                                     "sample": f"2 channels x {nn} wideband samples, scaled to {C} channels (oracle port, one core)"}
+    del bank, x, y, yh
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    import orion_b200 as ob
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ob.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_c5(args, rank, world, local, args.steps, not args.no_cpu_baseline)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -279,6 +301,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c1", choices=["c1", "c5"])
     ap.add_argument("--channels", type=int, default=1024)
+    ap.add_argument("--no-c5", action="store_true", help="skip the sharded 1024-channel measurement carried in the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -428,6 +451,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e = world * n * Ke / dt / 1e6
+    # ... and from ordinary (pageable) host memory, what a Rust Vec<C32> or a numpy array is
+    xp, yp = np.array(xh, copy=True), np.empty_like(yh)
+    chain.reset()
+    chain.process(xh, yh)                                # same stream position on both sides: the outputs must be bit-equal
+    chain.reset()
+    chain.process(xp, yp)
+    e2e_equal = bool(np.array_equal(yp.view(np.uint32), yh.view(np.uint32)))
+    chain.process(xp, yp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        chain.process(xp, yp)
+    torch.cuda.synchronize()
+    dtp = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dtp], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dtp = float(t.item())
+    e2e_pageable = world * n * Ke / dtp / 1e6
+    del xp, yp
+
+    # ---- the sharded 1024-channel workload (north_star: channels split across the GPUs of the box) -------
+    c5_line = None
+    if not args.no_c5:
+        del x_devs, x_dev
+        torch.cuda.empty_cache()
+        c5_args = argparse.Namespace(**vars(args))
+        c5_args.samples = N_SAMPLES
+        c5_line = measure_c5(c5_args, rank, world, local, max(3, min(K, 5)), False)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -441,13 +493,24 @@ def main():
                        "launch_overlap": "consecutive launches overlap (programmatic dependent launch); carried state is waited for", "tolerance": "max abs err <= 1e-4 of full scale, SNR >= 90 dB vs oracle"},
             "clocks": clocks, "parity_check": check,
             "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n_out * 4),
-                    "steps": Ke, "api": "orion_b200_block_process (host pointers, pinned)"},
+                    "steps": Ke, "api": "orion_b200_block_process (host pointers, pinned); chunks are pipelined: H2D / kernel / D2H overlap",
+                    "pageable": {"value": e2e_pageable, "unit": "MS/s", "vs_pinned": e2e_pageable / e2e,
+                                 "bit_equal_to_pinned_run": e2e_equal,
+                                 "api": "same call, ordinary pageable host buffers (staged through the block's pinned ring)"}},
+            "value_definition": "K launches enqueued back to back on one stream, CUDA events around the whole region, total / K "
+                                "(consecutive launches overlap); roofline.kernel_ms_isolated_launch is the median of launches timed one by one",
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_isolated_launch": isolated_ms,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n},
         }
+        if c5_line is not None:
+            line["c5"] = {"workload": c5_line["config"]["workload"], "scaling": "strong", "n_gpus": world,
+                          "channels_per_gpu": c5_line["config"]["channels_per_gpu"], "ms_per_wideband_second": c5_line["ms_per_step"],
+                          "wideband_msps": c5_line["value"], "channel_msps": c5_line["channel_msps"], "steps": c5_line["steps"],
+                          "gpu_launches": c5_line["gpu_launches"], "parity_check": c5_line["parity_check"],
+                          "timing": "CUDA events on the bank's stream, max over ranks"}
         if not args.no_cpu_baseline and world == 1:
             ncpu = 6_000_000                                   # ~3 s of single-core work
             step = cpu_reference_run(ncpu, 1)

@@ -126,6 +126,7 @@ extern "C" {
     pub fn orion_b200_chain_create(spec: *const orion_b200_chain_spec, out: *mut *mut orion_b200_block) -> c_int;
 
     pub fn orion_b200_bank_create(specs: *const orion_b200_chain_spec, n_channels: usize, out: *mut *mut orion_b200_bank) -> c_int;
+    pub fn orion_b200_bank_set_stream(bank: *mut orion_b200_bank, cuda_stream: *mut c_void) -> c_int;
     pub fn orion_b200_bank_destroy(k: *mut orion_b200_bank);
     pub fn orion_b200_bank_reset(k: *mut orion_b200_bank) -> c_int;
     pub fn orion_b200_bank_channels(k: *const orion_b200_bank) -> usize;

@@ -224,6 +224,8 @@ float orion_b200_agc_env(orion_b200_block *b);      /* the tracked power `env` a
  * ---------------------------------------------------------------------------------- */
 typedef struct orion_b200_bank orion_b200_bank;
 int    orion_b200_bank_create(const orion_b200_chain_spec *specs, size_t n_channels, orion_b200_bank **out);
+/* Run the bank on a caller's CUDA stream (NULL: back to its own); only for banks on the shared front-end path. */
+int    orion_b200_bank_set_stream(orion_b200_bank *bank, void *cuda_stream);
 void   orion_b200_bank_destroy(orion_b200_bank *k);
 int    orion_b200_bank_reset(orion_b200_bank *k);
 size_t orion_b200_bank_channels(const orion_b200_bank *k);                         /* [host-only] */

@@ -119,7 +119,7 @@ DEV void bank_mac(f32x2 (&acc)[PM], const float *gp, f32x2 x0, f32x2 x1) {
     for (int p = 0; p < PM; ++p) acc[p] = ffma2(pack2(t1[p], t1[p]), x1, acc[p]);
 }
 
-constexpr int kBankConsumerWarps = 8;        // 256 channels per CTA
+constexpr int kBankConsumerWarps = 8;        // at most 256 channels per CTA (blockDim.x / 32 - 1 consumer warps at run time)
 constexpr int kBankMaxSlots = 6;
 
 template <int PM, int MIXK>
@@ -129,13 +129,14 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     __shared__ __align__(8) unsigned long long full[kBankMaxSlots], empty[kBankMaxSlots];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int NS = a.NS, M = a.M, BT = a.BT;
+    const int NWC = (int)(blockDim.x >> 5) - 1;      // consumer warps of this launch (small banks use small CTAs, more of them per SM)
     const size_t slot_bytes = (size_t)BT * M * sizeof(float2);
     float *gt_sh = reinterpret_cast<float *>(smem + (size_t)NS * slot_bytes);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), kBankConsumerWarps);
+            mbar_init(smem_u32(&empty[s]), NWC);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,7 +149,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     if (Ta >= Tb) return;
     const long long ntile = Tb - Ta + 1;             // + the warm-up tile Ta - 1 (its last PM blocks)
 
-    if (wid == kBankConsumerWarps) {
+    if (wid == NWC) {
         // ---------------- producer warp: stream the tiles of the range through the ring ----------------
         if (blockIdx.x == 0 && blockIdx.y == 0 && a.H > 0) {                 // FIR history for the next call
             for (int k0 = 0; k0 < a.H; k0 += 32)
@@ -182,7 +183,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     }
 
     // ---------------- consumer warps: lane = channel ----------------
-    const int ch_raw = (blockIdx.y * kBankConsumerWarps + wid) * 32 + lane;
+    const int ch_raw = (blockIdx.y * NWC + wid) * 32 + lane;
     const bool ch_ok = ch_raw < a.nch;
     const int ch = ch_ok ? ch_raw : a.nch - 1;
     NcoParam osc = a.osc[ch];
@@ -299,8 +300,14 @@ size_t bank_fir_smem_bytes(const BankFirArgs &a) {
     return (size_t)a.NS * a.BT * a.M * sizeof(float2) + (size_t)a.M * a.PM * sizeof(float) + 16;
 }
 
-// occupancy set-up once per (PM, smem); grid = (time ranges, channel groups of 256)
-cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, cudaStream_t stream) {
+// consumer warps per CTA for a bank of nch channels: as few channel groups as possible, evenly filled
+int bank_fir_consumer_warps(int nch) {
+    const int w = (nch + 31) / 32;
+    const int groups = (w + kBankConsumerWarps - 1) / kBankConsumerWarps;
+    return (w + groups - 1) / groups;
+}
+// occupancy set-up once per (PM, smem); grid = (time ranges, channel groups of 32 * nwc channels)
+cudaError_t bank_fir_prepare(const BankFirArgs &a, int nwc, int *ctas_per_sm) {
     bank_fir_kernel_t k = bank_fir_instance(a.PM, a.mix);
     if (!k) return cudaErrorInvalidValue;
     const size_t smem = bank_fir_smem_bytes(a);
@@ -308,9 +315,15 @@ cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, cudaStream_t stre
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    const int ngroups = (a.nch + 32 * kBankConsumerWarps - 1) / (32 * kBankConsumerWarps);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, (const void *)k, 32 * (nwc + 1), smem);
+}
+cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, int nwc, cudaStream_t stream) {
+    bank_fir_kernel_t k = bank_fir_instance(a.PM, a.mix);
+    if (!k) return cudaErrorInvalidValue;
+    const size_t smem = bank_fir_smem_bytes(a);
+    const int ngroups = (a.nch + 32 * nwc - 1) / (32 * nwc);
     dim3 grid((unsigned)nranges, (unsigned)ngroups);
-    k<<<grid, 32 * (kBankConsumerWarps + 1), smem, stream>>>(a);
+    k<<<grid, 32 * (nwc + 1), smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -64,6 +64,7 @@ struct GroupTables {         // global memory, one per group
     float lane[32][kMaxGroupDim * kMaxGroupDim];       // Ac^(n*lane)   (carry into a lane's chunk)
     float lb[32][kMaxGroupDim * kMaxGroupDim];         // Ac^(T*k)      (inter-tile look-back)
     float lb32[kMaxGroupDim * kMaxGroupDim];           // Ac^(32*T)
+    float lbb[33][kMaxGroupDim * kMaxGroupDim];        // Ac^(32*T*k): block-level look-back of slow poles (k = 32: the superblock chain)
     float tile[kMaxGroupDim * kMaxGroupDim];           // Ac^T
     int   depth;             // predecessor tiles with a non-zero weight: Ac^(T*k) == 0 in f32 for k >= depth
     int   pad[3];
@@ -138,6 +139,7 @@ struct ChainArgs {
     int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
     long long tma_row0;          // global row index of tensor-map row 0
     long long tma_rows;          // rows the tensor map covers
+    int   l2_prefetch;           // > 0: every fill also prefetches into L2 the tile this CTA stages that many fills later
     // demodulator
     int   demod;
     int   translate;             // FM: multiply by conj(post phasor) first (fm.rs:34-37)

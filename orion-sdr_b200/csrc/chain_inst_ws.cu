@@ -31,8 +31,15 @@ namespace orion {
 #endif
 #define ORION_STR2(x) #x
 #define ORION_STR(x) ORION_STR2(x)
-constexpr int kWsFirWarps = 8;
-constexpr int kWsPostWarps = 16;
+#ifndef ORION_WS_WAIT_NS
+#define ORION_WS_WAIT_NS 20000
+#endif
+#ifndef ORION_WS_FIR_WARPS
+#define ORION_WS_FIR_WARPS 8
+#define ORION_WS_POST_WARPS 16
+#endif
+constexpr int kWsFirWarps = ORION_WS_FIR_WARPS;
+constexpr int kWsPostWarps = ORION_WS_POST_WARPS;
 constexpr int kWsWarps = kWsFirWarps + kWsPostWarps;
 constexpr int kWsZSlots = 16;                       // >= kWsPostWarps (see above)
 constexpr int kWsZPitch = 80;                       // bytes per lane: 8 complex outputs + 16 (conflict-free LDS.128 / STS.128)
@@ -53,8 +60,8 @@ struct __align__(16) WsCtl {
 DEV void ring_wait(uint32_t bar, unsigned parity, const int *counter, int want, int *err_flag, int code) {
     int spins = 0;
     for (;;) {
-        while (!mbar_try_wait(bar, parity)) {
-            if (++spins > (1 << 22)) { atomicExch(err_flag, code); return; }     // watchdog: never hang the device
+        while (!mbar_try_wait_hint(bar, parity, ORION_WS_WAIT_NS)) {
+            if (++spins > (1 << 20)) { atomicExch(err_flag, code); return; }     // watchdog: never hang the device
         }
         if (*reinterpret_cast<const volatile int *>(counter) == want) return;
         while (*reinterpret_cast<const volatile int *>(counter) != want) {
@@ -122,6 +129,11 @@ chain_ws_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUt
         } else {
             mbar_arrive_pred(pred, bar);
         }
+        if (a.l2_prefetch > 0) {
+            const long long tp = t + G * (long long)a.l2_prefetch;
+            if (tp < a.ntiles && tile_is_interior(a, tp))
+                tma_prefetch_l2_pred(lane == 0, &tmap, 0, (int)(tp * kThreads - GE::HR - a.tma_row0));
+        }
     };
     if (wid < kWsFirWarps)
         for (int s = wid; s < NS; s += kWsFirWarps) fill_slot(s, 0);           // the first tiles are in flight while the CTA sets up
@@ -162,10 +174,10 @@ chain_ws_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUt
                 const uint32_t bar = smem_u32(&ctl.full[s]);
                 int spins = 0;
                 for (;;) {
-                    while (!mbar_try_wait(bar, (unsigned)k & 1u)) {
-                        if (++spins > (1 << 22)) { atomicExch(a.err_flag, 2); break; }
+                    while (!mbar_try_wait_hint(bar, (unsigned)k & 1u, ORION_WS_WAIT_NS)) {
+                        if (++spins > (1 << 20)) { atomicExch(a.err_flag, 2); break; }
                     }
-                    if (*reinterpret_cast<volatile int *>(&ctl.gen[s]) == k || spins > (1 << 22)) break;
+                    if (*reinterpret_cast<volatile int *>(&ctl.gen[s]) == k || spins > (1 << 20)) break;
                     while (*reinterpret_cast<volatile int *>(&ctl.gen[s]) != k) {
                         if (++spins > (1 << 22)) { atomicExch(a.err_flag, 3); break; }
                         __nanosleep(64);

@@ -114,6 +114,16 @@ DEV bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
         : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
     return ok != 0;
 }
+// the same with a suspend-time hint (ns): the waiting warp stays off the issue slots for up to that long per try
+DEV bool mbar_try_wait_hint(uint32_t mbar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(mbar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t mbar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -159,6 +169,15 @@ DEV void tma_fill_pred(bool p, uint32_t dst, const CUtensorMap *map, int c0, int
         "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%5], %6;\n\t"
         "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%1], [%2, {%3, %4}], [%5];\n\t}"
         ::"r"((uint32_t)p), "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar), "r"(bytes) : "memory");
+}
+// L2 prefetch of a tile the stage ring will ask for later: the ring holds ~10 tiles per SM, which at 16 warps is only
+// ~2.5 k cycles of look-ahead -- about one loaded HBM round trip, so warps used to wait for their slot (trace: 2.5 k
+// cycles per tile).  With the tile already in L2 the TMA fill is an L2 hit.
+DEV void tma_prefetch_l2_pred(bool p, const CUtensorMap *map, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+        "@p cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%1, {%2, %3}];\n\t}"
+        ::"r"((uint32_t)p), "l"(map), "r"(c0), "r"(c1) : "memory");
 }
 DEV void mbar_arrive_pred(bool p, uint32_t mbar) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%1];\n\t}"
@@ -540,6 +559,129 @@ DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int
     }
 }
 
+// Slow poles (the DC blocker: no truncation) -- two-level look-back with a FIXED recipe, so results repeat to the bit.
+// Tiles are grouped in blocks of 32 and blocks in superblocks of 32 (1024 tiles).  Three kinds of records:
+//   * the zero-state aggregate of every tile (lk[t].agg, published by the tile's front),
+//   * B_b, the zero-state aggregate of block b = tiles 32b .. 32b+31: a function of that block's tile aggregates alone,
+//     formed by the warp that finishes the block's last tile from the window it reads anyway (lk[32b+31].incl),
+//   * SS_s, the TRUE state at the end of superblock s, chained SS_s = Ac^(1024T) SS_(s-1) + sum_i Ac^(32T(31-i)) B_(32s+i)
+//     by the warp that finishes the superblock's last tile (lk[1024s+1022].incl -- a slot no block uses).
+// The state at the start of tile t (block b, position j; b = 32s + jb) is then
+//   Ac^(Tj) [ Ac^(32T jb) SS_(s-1) + sum_(i<jb) Ac^(32T(jb-1-i)) B_(32s+i) ]  +  sum_(i<j) Ac^(T(j-1-i)) agg_(32b+i):
+// two windows and one record, all loads in flight together, and the only serial chain runs over superblocks
+// (18 steps for the 38.4 M-sample AM configuration, where the earlier per-grid-block chain had 127 links of five windows).
+template <int D>
+DEV void lookback_slow(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, const float (&agg_own)[D], float (&sin)[D]) {
+    const GroupParam &G = hot->grp[g];
+    const GroupTables *T = a.gtabs + g;
+    const int j = (int)(tile & 31);
+    const long long b = tile >> 5;
+    const int jb = (int)(b & 31);
+    const long long sb = b >> 5;
+    // ---- tile level: lane l < j reads the aggregate of tile t-1-l
+    float pa[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pa[d] = 0.f;
+    const bool want1 = lane < j;
+    {
+        const TileLink *lk = a.links + (want1 ? (tile - 1 - lane) : tile) * kMaxGroups + g;
+        int spins = 0;
+        for (;;) {
+            const bool ready = !want1 || read_link<D>(lk->agg, a.epoch, pa);
+            if (__all_sync(FULLMASK, ready)) break;
+            if (++spins > (1 << 21)) { if (lane == 0) atomicExch(a.err_flag, 9); break; }   // watchdog: never hang the device
+            __nanosleep(32);
+        }
+    }
+    float term1[D];
+    {
+        float t1[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t1[d] = 0.f;
+        if (want1) {
+            float m[D * D];
+            load_mat<D>(T->lb[lane], m);
+            matvec<D>(m, pa, t1);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float v = t1[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+            term1[d] = v;
+        }
+    }
+    float Bb[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) Bb[d] = 0.f;
+    if (j == 31) {                                   // block-last tile: B_b = Ac^T (window sum) + own aggregate
+        float m[D * D];
+        load_mat<D>(T->tile, m);
+        matvec<D>(m, term1, Bb);
+#pragma unroll
+        for (int d = 0; d < D; ++d) Bb[d] += agg_own[d];
+        publish<D>(lane == 0, a, tile, g, Bb, true);
+    }
+    // ---- block level: lane l < jb reads B of block b-1-l; lane 31 reads SS of the previous superblock (or the carried state)
+    float pb[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pb[d] = 0.f;
+    const bool want2 = lane < jb;
+    const bool want_ss = lane == 31;
+    {
+        const long long rec_tile = want2 ? ((b - 1 - lane) * 32 + 31) : (want_ss && sb > 0 ? (sb - 1) * 1024 + 1022 : tile);
+        const TileLink *lk = a.links + rec_tile * kMaxGroups + g;
+        int spins = 0;
+        for (;;) {
+            bool ready = true;
+            if (want2 || (want_ss && sb > 0)) ready = read_link<D>(lk->incl, a.epoch, pb);
+            if (__all_sync(FULLMASK, ready)) break;
+            if (++spins > (1 << 21)) { if (lane == 0) atomicExch(a.err_flag, 10); break; }
+            __nanosleep(32);
+        }
+        if (want_ss && sb == 0) {                    // the state carried into this call sits before superblock 0
+#pragma unroll
+            for (int d = 0; d < D; d += 2) {
+                const float2 c = __ldcg(&a.carry_in->sec[G.first + d / 2]);
+                pb[d] = c.x; pb[d + 1] = c.y;
+            }
+        }
+    }
+    float base[D];                                   // state at the start of block b
+    {
+        float t2[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t2[d] = 0.f;
+        if (want2 || want_ss) {
+            float m[D * D];
+            load_mat<D>(T->lbb[want_ss ? jb : lane], m);
+            matvec<D>(m, pb, t2);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float v = t2[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+            base[d] = v;
+        }
+    }
+    {
+        float m[D * D], t3[D];
+        load_mat<D>(T->lb[j], m);
+        matvec<D>(m, base, t3);
+#pragma unroll
+        for (int d = 0; d < D; ++d) sin[d] = t3[d] + term1[d];
+    }
+    if (j == 31 && jb == 31) {                       // superblock-last tile: SS_s = Ac^(32T) base + B_b
+        float m[D * D], ss[D];
+        load_mat<D>(T->lbb[1], m);
+        matvec<D>(m, base, ss);
+#pragma unroll
+        for (int d = 0; d < D; ++d) ss[d] += Bb[d];
+        publish<D>(lane == 0, a, sb * 1024 + 1022, g, ss, true);
+    }
+}
+
 // one recursive-section step, reference arithmetic
 template <int TYPE>
 DEV float sec_step_t(const SecParam &P, float x, float &s0, float &s1) {
@@ -610,7 +752,7 @@ DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, i
     const GroupParam &G = hot->grp[g];
     if ((ORION_TRACE && a.trace) && g == 0) {
         const unsigned am = __activemask();
-        if (lane == 0) { a.trace[tile * 16 + 11] = clock64(); a.trace[tile * 16 + 14] = am; }
+        if (lane == 0) { a.trace[tile * 16 + 11] = clock64(); }
         if (lane == 31) a.trace[tile * 16 + 15] = am;
     }
     __syncwarp();                                  // converged here: the shuffles below take the fast path
@@ -642,16 +784,9 @@ DEV void group_finish(const ChainArgs &a, const Hot *hot, int g, long long tile,
     const GroupParam &G = hot->grp[g];
     const GroupTables *T = a.gtabs + g;
     float sin[D];
-    lookback<D>(a, hot, g, tile, lane, sin);
+    if (G.agg_only) lookback<D>(a, hot, g, tile, lane, sin);
+    else lookback_slow<D>(a, hot, g, tile, lane, agg, sin);        // slow poles: two-level fixed recipe (publishes B_b / SS_s)
     if ((ORION_TRACE && a.trace) && lane == 0 && g == 0) a.trace[tile * 16 + 10] = clock64();
-    if (!G.agg_only) {                            // uniform branch; the store itself is predicated on lane 0
-        float tm[D * D], inc[D];
-        load_mat<D>(T->tile, tm);
-        matvec<D>(tm, sin, inc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) inc[d] += agg[d];
-        publish<D>(lane == 0, a, tile, g, inc, true);
-    }
     float lm[D * D], st[D];
     load_mat<D>(T->lane[lane], lm);
     matvec<D>(lm, sin, st);
@@ -1337,16 +1472,14 @@ DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *ta
     const float4 xv = *reinterpret_cast<const float4 *>(park + lane * kMaxGroupDim);
     float sin[4];
     const GroupParam &G = hot->grp[0];
+    if ((ORION_TRACE && a.trace) && lane == 0) a.trace[tile * 16 + 14] = clock64();       // finish phase entered
     if (G.agg_only) {
         lr4_lookback_short(a, tabs, tile, lane, __ldg(&a.gtabs->depth), sin);
-    } else {                                       // slow poles: the general chained look-back, inclusive values published
+        if ((ORION_TRACE && a.trace) && lane == 0) a.trace[tile * 16 + 10] = clock64();   // look-back done
+    } else {                                       // slow poles: the two-level look-back
         const float4 av = *reinterpret_cast<const float4 *>(park + 32 * kMaxGroupDim);
-        lookback<4>(a, hot, 0, tile, lane, sin);
-        float tm[16], inc[4];
-        load_mat<4>(a.gtabs->tile, tm);
-        matvec<4>(tm, sin, inc);
-        inc[0] += av.x; inc[1] += av.y; inc[2] += av.z; inc[3] += av.w;
-        publish<4>(lane == 0, a, tile, 0, inc, true);
+        const float agg_own[4] = { av.x, av.y, av.z, av.w };
+        lookback_slow<4>(a, hot, 0, tile, lane, agg_own, sin);
     }
     float lm[16], st[4];
     load_mat4_sh(tabs->lane[lane], lm);
@@ -1562,6 +1695,11 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         } else {
             mbar_arrive_pred(pred, bar);
         }
+        if (a.l2_prefetch > 0) {                                          // the tile this CTA stages l2_prefetch fills from now
+            const long long tp = t + G * (long long)a.l2_prefetch;
+            if (tp < a.ntiles && tile_is_interior(a, tp))
+                tma_prefetch_l2_pred(lane == 0, &tmap, 0, (int)(tp * kThreads - HRc - a.tma_row0));
+        }
     };
 
     if (FRONT == FRONT_STAGED)
@@ -1689,6 +1827,15 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
                 if (jt + i < a.n_out) z[i] = fir_global_one(a, jt + i);
             if (need_prev && j0 > 0 && lane == 0) zhalo = fir_global_one(a, j0 - 1);
         } else {
+            if (a.l2_prefetch > 0) {
+                // rate-1 blocks read their tile straight from global memory, one round trip per iteration and warp: pull
+                // the tile this CTA takes l2_prefetch tickets from now into L2 (one 128-byte line per lane)
+                const long long tp = tile + G * (long long)a.l2_prefetch;
+                const int item = kind_f32_in(demod) ? 4 : 8;
+                const long long off = tp * (long long)(kThreads * NPT) * item + (long long)lane * 128;
+                if (off + 128 <= a.n_in * item && lane * 128 < kThreads * NPT * item)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(a.in) + off));
+            }
             front_direct<NPT>(a, tile, lane, z, u, zhalo, xs);
         }
         if (handoff_tile) handoff_wait(a, 1, a.carry_target);   // `prev` now, section states in this tile's look-back

@@ -10,7 +10,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,7 +39,9 @@ struct BankFirArgs {             // bank_kernels.cu
     int *err_flag;
 };
 size_t bank_fir_smem_bytes(const BankFirArgs &a);
-cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, cudaStream_t stream);
+int bank_fir_consumer_warps(int nch);
+cudaError_t bank_fir_prepare(const BankFirArgs &a, int nwc, int *ctas_per_sm);
+cudaError_t bank_fir_launch(const BankFirArgs &a, int nranges, int nwc, cudaStream_t stream);
 chain_kernel_t get_kernel_ws(int dm);                       // chain_inst_ws.cu: warp-specialised decimate-by-8 chain
 size_t ws_dyn_smem(int nstages, int ntaps2, int Lg);
 int ws_warps();
@@ -244,6 +250,7 @@ void build_group(const SecParam *secs, const GroupHost &gh, int npt, GroupParam 
     for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, n * k, D), gt->lane[k]);
     for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, T * k, D), gt->lb[k]);
     mat_store(mat_pow(A, T * 32ull, D), gt->lb32);
+    for (int k = 0; k <= 32; ++k) mat_store(mat_pow(A, T * 32ull * (unsigned long long)k, D), gt->lbb[k]);
     mat_store(mat_pow(A, T, D), gt->tile);
     // look-back depth: first k with Ac^(T*k) == 0; geometric search then bisection (the decay of the
     // norm is not strictly monotone for complex poles, so a margin of 4 further powers is verified)
@@ -489,6 +496,71 @@ encode_tiled_t get_encode_tiled() {
     return fn;
 }
 
+// ---- host copy pool: pageable caller buffers are moved to / from the pinned staging ring by a few threads ------
+class CopyPool {
+public:
+    static CopyPool &get() { static CopyPool p; return p; }
+    void copy(void *dst, const void *src, size_t bytes) {
+        if (bytes < (1u << 20) || workers_.empty()) { memcpy(dst, src, bytes); return; }
+        std::lock_guard<std::mutex> job(job_m_);                  // one job at a time (blocks on different threads share the pool)
+        const size_t parts = workers_.size() + 1;
+        const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; per_ = per;
+            next_ = 1; pending_ = (int)workers_.size(); ++gen_;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(per, bytes));                    // the caller's share
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw >= 32 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+        if (const char *e = getenv("ORION_B200_COPY_THREADS")) n = std::max(0, std::min(15, atoi(e) - 1));
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (std::thread &t : workers_) t.join();
+    }
+    void run() {
+        unsigned long long seen = 0;
+        for (;;) {
+            size_t part;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                part = next_++;
+            }
+            const size_t off = part * per_;
+            if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, job_m_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr; const char *src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0, next_ = 0;
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 thread_local int t_device = 0;
 thread_local std::string t_create_error;       // why the last constructor on this thread failed
 
@@ -552,6 +624,13 @@ struct orion_b200_block {
     unsigned int calls_since_reset = 0;
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
+    // host-pointer calls are pipelined in chunks: copies in, kernels and copies out overlap (orion_b200_block_process)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    static const int kPipeSlots = 3;
+    cudaEvent_t ev_h2d[kPipeSlots] = { nullptr, nullptr, nullptr }, ev_k[kPipeSlots] = { nullptr, nullptr, nullptr },
+                ev_d2h[kPipeSlots] = { nullptr, nullptr, nullptr };
+    void *h_stage_in[kPipeSlots] = { nullptr, nullptr, nullptr }, *h_stage_out[kPipeSlots] = { nullptr, nullptr, nullptr };
+    size_t h_stage_in_cap = 0, h_stage_out_cap = 0;      // pinned staging for pageable callers
     // ---- counters ----
     unsigned long long k_pre = 0, k_post = 0;     // items consumed at the input rate / demod rate since reset
     uint64_t launches = 0;
@@ -589,6 +668,7 @@ int npt_of(const orion_b200_block *b) { return b->plan.R * b->plan.U; }
 // (re)build everything derived from the specification and upload it
 int finalize_plan(orion_b200_block *b) {
     CK(cudaSetDevice(b->device));
+    b->plan.warps = kMaxWarpsPerCta;               // (a previous plan may have been the 24-warp warp-specialised one)
     if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     // shape / demodulator specialisations of the kernel family (chain_kernels.cuh, Geo<SP> and Dm<DM>)
@@ -609,7 +689,11 @@ int finalize_plan(orion_b200_block *b) {
         else if ((b->demod == DEMOD_FM || b->demod == DEMOD_PM || b->demod == DEMOD_F32) && lr4_only) dm = 100 + b->demod;
     }
     if (getenv("ORION_B200_NO_SPECIALIZE")) { sp = 0; dm = -1; }
-    if (b->nbatch > 1) b->plan.warps = 4;          // one small CTA per member; many of them per SM
+    if (b->nbatch > 1) {                           // one CTA per member: 4 warps when the members fill the machine, more for small banks
+        int w = 4;
+        while (w < kMaxWarpsPerCta && (long long)b->nbatch * (2 * w) <= 148LL * kMaxWarpsPerCta) w *= 2;
+        b->plan.warps = w;
+    }
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm, b->nbatch > 1);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
     b->plan.dyn_smem = b->plan.stage_bytes * b->plan.nstages +
@@ -619,9 +703,10 @@ int finalize_plan(orion_b200_block *b) {
                        sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
                        (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +                             // + per-lane scan tables (LR4 instance)
                        (b->plan.front == FRONT_DIRECT ? (size_t)b->plan.warps * 32 * 144 + 16 : 0);  // + transposing scratch (rate-1 blocks)
-    // FIR /8 + FM | PM + LR4 (the C1 chain): the warp-specialised instance (chain_inst_ws.cu) unless ORION_B200_NO_WS is set
+    // FIR /8 + FM | PM + LR4 (the C1 chain): the warp-specialised instance (chain_inst_ws.cu) is an experiment, selected with
+    // ORION_B200_WS=1 only -- measured 4-7 % SLOWER than the unified kernel on B200 (profiles/r02_experiments.txt)
     b->ws = 0;
-    if (sp == 1 && (dm == 100 + DEMOD_FM || dm == 100 + DEMOD_PM) && b->nbatch == 1 && !b->opt_serial && !getenv("ORION_B200_NO_WS")) {
+    if (sp == 1 && (dm == 100 + DEMOD_FM || dm == 100 + DEMOD_PM) && b->nbatch == 1 && !b->opt_serial && getenv("ORION_B200_WS")) {
         chain_kernel_t kw = get_kernel_ws(dm);
         if (kw) {
             b->kernel = kw;
@@ -1007,9 +1092,16 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r == CUDA_SUCCESS) { a.use_tma = 1; a.tma_row0 = row0; a.tma_rows = nrows; }
+            // L2 look-ahead of the stage ring, in fills (tiles of this CTA): ~2 ring depths; 0 = off
+            a.l2_prefetch = 0;                 // measured on B200: any distance costs 3-10 % (profiles/r02_experiments.txt); kept for experiments
+            if (const char *e2 = getenv("ORION_B200_L2_PREFETCH")) a.l2_prefetch = std::max(0, atoi(e2));
         }
     }
 
+    if (b->plan.front == FRONT_DIRECT) {                   // L2 look-ahead of the rate-1 blocks, in tickets of a CTA (two per warp)
+        a.l2_prefetch = 0;
+        if (const char *e2 = getenv("ORION_B200_L2_PREFETCH")) a.l2_prefetch = std::max(0, atoi(e2));
+    }
     int grid = 1;
     if (!b->opt_serial) {
         const long long resident = (long long)b->sm_count * b->ctas_per_sm;
@@ -1440,7 +1532,7 @@ struct orion_b200_bank {
     float2 *d_z = nullptr;
     size_t z_cap = 0;
     std::vector<BankGroup> groups;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     uint64_t launches = 0;
     // ---- general path: one block per channel ----
     std::vector<orion_b200_block *> ch;
@@ -1512,7 +1604,8 @@ int bank_fast_create(orion_b200_bank *k, const orion_b200_chain_spec *specs, siz
         if (k->mix != MIX_NONE) k->osc[c].set(specs[c].mix_freq_hz, specs[c].mix_fs, 0);
         op[c] = k->osc[c].param(0);
     }
-    if (cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&k->own_stream, cudaStreamNonBlocking) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    k->stream = k->own_stream;
     if (cudaMalloc(&k->d_osc, n * sizeof(NcoParam)) != cudaSuccess || cudaMalloc(&k->d_gt, gt.size() * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&k->d_hist[0], k->H * sizeof(float2)) != cudaSuccess || cudaMalloc(&k->d_hist[1], k->H * sizeof(float2)) != cudaSuccess ||
         cudaMalloc(&k->d_err, sizeof(int)) != cudaSuccess || cudaMallocHost(&k->h_err, sizeof(int)) != cudaSuccess)
@@ -1577,19 +1670,22 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     a.mix = k->mix; a.osc = k->d_osc; a.kbase = k->k_pre;
     a.M = (int)M; a.Lg = (int)k->g.size(); a.PM = k->PM;
     a.BT = std::max(k->PM, std::max(1, 2048 / (int)M));               // 16 KB tiles (16 blocks of 128 samples)
-    a.NS = 4;
+    const int nwc = bank_fir_consumer_warps((int)k->nch);
+    a.NS = nwc > 4 ? 4 : 3;                                            // small CTAs: smaller rings, more CTAs per SM
     a.gt = k->d_gt; a.g0 = k->g[0];
     a.z = k->d_z; a.z_stride = (long long)n_out_all; a.nch = (int)k->nch;
     a.tiles_total = ((long long)n_out_all + a.BT - 1) / a.BT;
     a.err_flag = k->d_err;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, k->device);
-    const int ngroups = (int)((k->nch + 255) / 256);
-    long long want = std::max<long long>(1, (2LL * sms + ngroups - 1) / ngroups);    // two CTAs per SM
+    int per_sm = 2;
+    if (bank_fir_prepare(a, nwc, &per_sm) != cudaSuccess || per_sm < 1) return bank_fail(k, ORION_B200_ERR_CUDA, "bank front-end set-up");
+    const int ngroups = (int)((k->nch + 32 * nwc - 1) / (32 * nwc));
+    long long want = std::max<long long>(1, ((long long)per_sm * sms + ngroups - 1) / ngroups);    // fill every SM once
     if (const char *e = getenv("ORION_B200_BANK_RANGES")) want = std::max(1, atoi(e));
     a.tiles_per_range = (int)std::max<long long>(1, (a.tiles_total + want - 1) / want);
     const int nranges = (int)((a.tiles_total + a.tiles_per_range - 1) / a.tiles_per_range);
-    cudaError_t e = bank_fir_launch(a, nranges, k->stream);
+    cudaError_t e = bank_fir_launch(a, nranges, nwc, k->stream);
     if (e != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, std::string("bank front-end launch: ") + cudaGetErrorString(e));
     k->launches += 1;
     k->pp ^= 1;
@@ -1674,7 +1770,7 @@ void orion_b200_bank_destroy(orion_b200_bank *k) {
         cudaFree(k->d_osc); cudaFree(k->d_gt); cudaFree(k->d_hist[0]); cudaFree(k->d_hist[1]); cudaFree(k->d_z);
         cudaFree(k->d_in); cudaFree(k->d_out); cudaFree(k->d_err);
         if (k->h_err) cudaFreeHost(k->h_err);
-        if (k->stream) cudaStreamDestroy(k->stream);
+        if (k->own_stream) cudaStreamDestroy(k->own_stream);
         cudaGetLastError();
         delete k;
         return;
@@ -1703,6 +1799,19 @@ int orion_b200_bank_reset(orion_b200_bank *k) {
         return ORION_B200_OK;
     }
     for (orion_b200_block *b : k->ch) { const int st = reset_state(b); if (st) return bank_fail(k, st, b->err); }
+    return ORION_B200_OK;
+}
+int orion_b200_bank_set_stream(orion_b200_bank *k, void *cuda_stream) {
+    if (!k) return ORION_B200_ERR_INVALID;
+    if (!k->fast) return cuda_stream ? bank_fail(k, ORION_B200_ERR_UNSUPPORTED, "only a bank on the shared front-end path runs on one caller stream") : ORION_B200_OK;
+    if (cudaSetDevice(k->device) != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, "cudaSetDevice");
+    cudaStreamSynchronize(k->stream);
+    k->stream = cuda_stream ? (cudaStream_t)cuda_stream : k->own_stream;
+    k->streams.assign(1, k->stream);
+    for (BankGroup &g : k->groups) {
+        const int st = orion_b200_block_set_stream(g.proto, (void *)k->stream);
+        if (st != ORION_B200_OK) return bank_fail(k, st, g.proto->err);
+    }
     return ORION_B200_OK;
 }
 size_t orion_b200_bank_channels(const orion_b200_bank *k) { return k ? (k->fast ? k->nch : k->ch.size()) : 0; }
@@ -1780,6 +1889,15 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err); cudaFree(b->d_handoff);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_batch_chan);
     if (b->h_err) cudaFreeHost(b->h_err);
+    for (int i = 0; i < orion_b200_block::kPipeSlots; ++i) {
+        if (b->h_stage_in[i]) cudaFreeHost(b->h_stage_in[i]);
+        if (b->h_stage_out[i]) cudaFreeHost(b->h_stage_out[i]);
+        if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]);
+        if (b->ev_k[i]) cudaEventDestroy(b->ev_k[i]);
+        if (b->ev_d2h[i]) cudaEventDestroy(b->ev_d2h[i]);
+    }
+    if (b->s_h2d) cudaStreamDestroy(b->s_h2d);
+    if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     cudaGetLastError();
     delete b;
@@ -1836,10 +1954,96 @@ int orion_b200_block_process(orion_b200_block *b, const void *in, size_t n_in, v
         CK(cudaMalloc(&b->d_out, cap));
         b->d_out_cap = cap;
     }
-    CK(cudaMemcpyAsync(b->d_in, in, ib, cudaMemcpyHostToDevice, b->stream));
-    const int st = launch(b, b->d_in, consume, b->d_out, produce);
-    if (st != ORION_B200_OK) return st;
-    if (ob) CK(cudaMemcpyAsync(out, b->d_out, ob, cudaMemcpyDeviceToHost, b->stream));
+    // Chunked pipeline: the copy in of chunk i+1, the kernel on chunk i and the copy out of chunk i-1 overlap (three
+    // streams, events between them).  Chunks are multiples of the decimation factor (and of the warp tile), so the
+    // per-call decimation phase of the reference (decim.rs:44-76) holds across the internal launches, whose streaming
+    // state carries over like between process() calls.  Pageable caller memory goes through a pinned staging ring.
+    const size_t M = (b->fir != FIR_NONE) ? b->M : 1;
+    const bool whole_output = produce == (consume + M - 1) / M;           // a short output slice keeps the one-launch path
+    size_t chunk = 0;
+    if (whole_output && !getenv("ORION_B200_NO_PIPELINE")) {
+        const size_t unit = M * (size_t)kThreads * (size_t)npt_of(b);       // input items of one warp tile
+        size_t want = (size_t)(4u << 20) / in_item_bytes(b);                // ~4 MB of input per chunk ...
+        if (const char *e = getenv("ORION_B200_PIPE_CHUNK_BYTES")) want = std::max<size_t>(1, (size_t)atoll(e) / in_item_bytes(b));
+        want = std::max(want, consume / 64 + 1);                            // ... but at most ~64 chunks
+        chunk = std::max<size_t>(1, (want + unit - 1) / unit) * unit;
+        if (chunk * 2 > consume) chunk = 0;                                 // short calls: one launch
+    }
+    if (chunk == 0) {
+        CK(cudaMemcpyAsync(b->d_in, in, ib, cudaMemcpyHostToDevice, b->stream));
+        const int st = launch(b, b->d_in, consume, b->d_out, produce);
+        if (st != ORION_B200_OK) return st;
+        if (ob) CK(cudaMemcpyAsync(out, b->d_out, ob, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        if (!b->s_h2d) {
+            CK(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
+            for (int i = 0; i < orion_b200_block::kPipeSlots; ++i) {
+                CK(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&b->ev_k[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&b->ev_d2h[i], cudaEventDisableTiming));
+            }
+        }
+        const int NSL = orion_b200_block::kPipeSlots;
+        const bool in_pageable = is_pageable(in), out_pageable = ob && is_pageable(out);
+        const size_t cib = chunk * in_item_bytes(b), cob = (chunk / M) * out_item_bytes(b);
+        if (in_pageable && cib > b->h_stage_in_cap) {
+            for (int i = 0; i < NSL; ++i) { if (b->h_stage_in[i]) cudaFreeHost(b->h_stage_in[i]); b->h_stage_in[i] = nullptr; }
+            b->h_stage_in_cap = 0;
+            for (int i = 0; i < NSL; ++i) CK(cudaMallocHost(&b->h_stage_in[i], cib));
+            b->h_stage_in_cap = cib;
+        }
+        if (out_pageable && cob > b->h_stage_out_cap) {
+            for (int i = 0; i < NSL; ++i) { if (b->h_stage_out[i]) cudaFreeHost(b->h_stage_out[i]); b->h_stage_out[i] = nullptr; }
+            b->h_stage_out_cap = 0;
+            for (int i = 0; i < NSL; ++i) CK(cudaMallocHost(&b->h_stage_out[i], cob));
+            b->h_stage_out_cap = cob;
+        }
+        // the staging streams start after whatever the block's stream still has queued (earlier process_dev calls)
+        CK(cudaEventRecord(b->ev_k[0], b->stream));
+        CK(cudaStreamWaitEvent(b->s_h2d, b->ev_k[0], 0));
+        const size_t nchunks = (consume + chunk - 1) / chunk;
+        struct Pending { size_t off_out, n_out; bool live; } pend[orion_b200_block::kPipeSlots] = {};
+        auto drain_out = [&](int slot) -> cudaError_t {                     // staged output of an earlier chunk -> the caller's buffer
+            if (!pend[slot].live) return cudaSuccess;
+            cudaError_t e = cudaEventSynchronize(b->ev_d2h[slot]);
+            if (e != cudaSuccess) return e;
+            CopyPool::get().copy((char *)out + pend[slot].off_out * out_item_bytes(b), b->h_stage_out[slot], pend[slot].n_out * out_item_bytes(b));
+            pend[slot].live = false;
+            return cudaSuccess;
+        };
+        for (size_t c = 0; c < nchunks; ++c) {
+            const int slot = (int)(c % NSL);
+            const size_t off = c * chunk, cn = std::min(chunk, consume - off);
+            const size_t off_out = off / M, pn = (cn + M - 1) / M;
+            const char *src = (const char *)in + off * in_item_bytes(b);
+            if (in_pageable) {
+                if (c >= (size_t)NSL) CK(cudaEventSynchronize(b->ev_h2d[slot]));       // the slot's previous copy in has left it
+                CopyPool::get().copy(b->h_stage_in[slot], src, cn * in_item_bytes(b));
+                src = (const char *)b->h_stage_in[slot];
+            }
+            CK(cudaMemcpyAsync((char *)b->d_in + off * in_item_bytes(b), src, cn * in_item_bytes(b), cudaMemcpyHostToDevice, b->s_h2d));
+            CK(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
+            CK(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
+            const int st = launch(b, (char *)b->d_in + off * in_item_bytes(b), cn, (char *)b->d_out + off_out * out_item_bytes(b), pn);
+            if (st != ORION_B200_OK) { cudaStreamSynchronize(b->s_h2d); cudaStreamSynchronize(b->s_d2h); return st; }
+            if (ob) {
+                CK(cudaEventRecord(b->ev_k[slot], b->stream));
+                CK(cudaStreamWaitEvent(b->s_d2h, b->ev_k[slot], 0));
+                char *dst = (char *)out + off_out * out_item_bytes(b);
+                if (out_pageable) {
+                    CK(drain_out(slot));
+                    dst = (char *)b->h_stage_out[slot];
+                    pend[slot].off_out = off_out; pend[slot].n_out = pn; pend[slot].live = true;
+                }
+                CK(cudaMemcpyAsync(dst, (char *)b->d_out + off_out * out_item_bytes(b), pn * out_item_bytes(b), cudaMemcpyDeviceToHost, b->s_d2h));
+                CK(cudaEventRecord(b->ev_d2h[slot], b->s_d2h));
+            }
+        }
+        for (int i = 0; i < NSL; ++i) CK(drain_out(i));
+        CK(cudaStreamSynchronize(b->s_d2h));
+        CK(cudaStreamSynchronize(b->s_h2d));
+    }
     const int es = check_device_error(b);                          // also synchronises the stream
     if (es != ORION_B200_OK) return es;
     if (in_read) *in_read = consume;

@@ -100,6 +100,7 @@ def lib():
     sig("orion_b200_agc_rms_create", i, f, f, f, f, pp)
     sig("orion_b200_agc_rms_iq_create", i, f, f, f, f, pp)
     sig("orion_b200_agc_env", f, vp)
+    sig("orion_b200_bank_set_stream", i, vp, vp)
     sig("orion_b200_lp_dc_cascade_create", i, f, f, f, i, pp)
     sig("orion_b200_dc_blocker_create", i, f, f, pp)
     sig("orion_b200_iir_cascade_create", i, vp, sz, pp)
@@ -180,7 +181,7 @@ EXPORTED_SYMBOLS = [
     "orion_b200_bank_last_error", "orion_b200_bank_process", "orion_b200_bank_process_dev",
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
     "orion_b200_block_exact_host_ms", "orion_b200_last_create_error", "orion_b200_block_prepare_oscillator",
-    "orion_b200_agc_rms_create", "orion_b200_agc_rms_iq_create", "orion_b200_agc_env",
+    "orion_b200_agc_rms_create", "orion_b200_agc_rms_iq_create", "orion_b200_agc_env", "orion_b200_bank_set_stream",
 ]
 
 
@@ -737,6 +738,10 @@ class ChannelBank:
 
     def synchronize(self):
         self._ck(lib().orion_b200_bank_synchronize(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        """Run the bank on a caller's CUDA stream (0: back to its own)."""
+        self._ck(lib().orion_b200_bank_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def reset(self):
         self._ck(lib().orion_b200_bank_reset(self._h))

@@ -66,7 +66,6 @@ stats("front rest (front-fir_done)", (t[:, 3] - t[:, 2]).astype(float))
 stats("  halo+refill (8-2)", (t[:, 8] - t[:, 2]).astype(float))
 stats("  front_map (9-8)", (t[:, 9] - t[:, 8]).astype(float))
 stats("  group_front (3-9)", (t[:, 3] - t[:, 9]).astype(float))
-print("active mask at scan entry (lane0 view):", {hex(int(v)): int(c) for v, c in zip(*np.unique(t[:, 14], return_counts=True))}, " lane31 view:", {hex(int(v)): int(c) for v, c in zip(*np.unique(t[:, 15], return_counts=True))})
 stats("    dot (11-9)", (t[:, 11] - t[:, 9]).astype(float))
 stats("    scan (12-11)", (t[:, 12] - t[:, 11]).astype(float))
 stats("    publish (13-12)", (t[:, 13] - t[:, 12]).astype(float))
@@ -74,8 +73,11 @@ stats("    park (3-13)", (t[:, 3] - t[:, 13]).astype(float))
 if which != "dec":
     f = t[:, 4] > 0
     stats("issue->finish (pending)", (t[f, 4] - t[f, 3]).astype(float))
-    f2 = f & (t[:, 10] > 0)
-    stats("  lookback done -> finish done", (t[f2, 4] - t[f2, 10]).astype(float))
+    f2 = f & (t[:, 10] > 0) & (t[:, 14] > 0)
+    if f2.any():
+        stats("  front done -> finish entered", (t[f2, 14] - t[f2, 3]).astype(float))
+        stats("  look-back (entered -> done)", (t[f2, 10] - t[f2, 14]).astype(float))
+        stats("  recursion + store (-> finish done)", (t[f2, 4] - t[f2, 10]).astype(float))
 # per-warp iteration time: sort by (warp id), consecutive consume stamps
 w = t[:, 7]
 order = np.lexsort((t[:, 0], w))
