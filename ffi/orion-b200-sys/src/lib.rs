@@ -105,6 +105,14 @@ extern "C" {
     pub fn orion_b200_oscillator_reset_phase(b: *mut orion_b200_block) -> c_int;
     pub fn orion_b200_biquad_create(b0: f32, b1: f32, b2: f32, a1: f32, a2: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_lp_cascade_create(fs: f32, fc: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_fm_mod_create(sample_rate: f32, deviation_hz: f32, rf_hz: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_fm_mod_set_deviation(b: *mut orion_b200_block, deviation_hz: f32) -> c_int;
+    pub fn orion_b200_cw_mod_create(sample_rate: f32, tone_hz: f32, rise_ms: f32, fall_ms: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_ssb_mod_create(fs: f32, audio_bw_hz: f32, audio_if_hz: f32, rf_hz: f32, usb: c_int, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_symbol_gain_create(gain: f32, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_symbol_gain_set(b: *mut orion_b200_block, gain: f32) -> c_int;
+    pub fn orion_b200_decider_create(bits_per_symbol: c_int, out: *mut *mut orion_b200_block) -> c_int;
+    pub fn orion_b200_cfo_derotate(cfo_hz: f32, fs: f32, input: *const orion_b200_c32, output: *mut orion_b200_c32, n: usize) -> c_int;
     pub fn orion_b200_agc_rms_create(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_agc_rms_iq_create(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32, out: *mut *mut orion_b200_block) -> c_int;
     pub fn orion_b200_agc_env(b: *mut orion_b200_block) -> f32;

@@ -55,6 +55,7 @@ extern "C" {
 /* item types */
 #define ORION_B200_ITEM_F32 1
 #define ORION_B200_ITEM_C32 2
+#define ORION_B200_ITEM_U8  3   /* one hard-decision bit per byte (the deciders of src/demodulate/{bpsk,qpsk,qam}.rs) */
 
 typedef struct orion_b200_block orion_b200_block;      /* opaque; one per reference block instance */
 
@@ -201,6 +202,34 @@ typedef struct orion_b200_chain_spec {
 } orion_b200_chain_spec;
 
 int orion_b200_chain_create(const orion_b200_chain_spec *spec, orion_b200_block **out);
+
+/* ------------------------------------------------------------------------------------
+ * Modulators, continued (next-row scope; AmDsbMod and PmDirectPhaseMod are declared further up).
+ *  - FmPhaseAccumMod (src/modulate/fm.rs:11-75), f32 -> C32: the running phasor of the reference is a prefix sum of the
+ *    phase; the GPU accumulates it exactly in 64-bit fixed point (tile sums, scan, per-item phasor) and mixes with the rf
+ *    oscillator replayed bit for bit.  The reference's own f32 rounding walk (~4e-8 rad per step) is not reproducible in
+ *    parallel: outputs stay within 1e-4 of the reference for about 10^6 samples after a reset.
+ *  - CwKeyedMod (src/modulate/cw.rs:10-102), f32 key envelope -> C32: chunked evaluation of the rise / fall envelope.
+ *  - SsbPhasingMod (src/modulate/ssb.rs:11-114), f32 -> C32: audio oscillator, two LpCascade filters, rf oscillator.
+ * orion_b200_mod_set_gain (above) applies to all of them.
+ * ---------------------------------------------------------------------------------- */
+int orion_b200_fm_mod_create(float sample_rate, float deviation_hz, float rf_hz, orion_b200_block **out);
+int orion_b200_fm_mod_set_deviation(orion_b200_block *b, float deviation_hz);
+int orion_b200_cw_mod_create(float sample_rate, float tone_hz, float rise_ms, float fall_ms, orion_b200_block **out);
+int orion_b200_ssb_mod_create(float fs, float audio_bw_hz, float audio_if_hz, float rf_hz, int usb, orion_b200_block **out);
+
+/* ------------------------------------------------------------------------------------
+ * Soft-symbol gain blocks and hard-decision slicers (next-row scope, src/demodulate/{bpsk,qpsk,qam}.rs).
+ *  - symbol gain: BpskDemod / QpskDemod / QamDemod::process, C32 -> C32, out = (g*re, g*im).
+ *  - decider: C32 -> U8, bits_per_symbol = 1 (BpskDecider: re < 0), 2 (QpskDecider: re < 0, im < 0), 4 / 6 / 8
+ *    (QamDecider<BITS>: per-axis thresholds, Gray coded, MSB first).  n_syms = min(n_in, out_cap / bits); the WorkReport
+ *    is (n_syms, n_syms * bits) like the reference's.
+ *  - CFO de-rotation: the one-shot Rotator::new(-cfo_hz, fs).rotate_block(in, out) of sync/ofdm_sync.rs:527-528.
+ * ---------------------------------------------------------------------------------- */
+int orion_b200_symbol_gain_create(float gain, orion_b200_block **out);
+int orion_b200_symbol_gain_set(orion_b200_block *b, float gain);
+int orion_b200_decider_create(int bits_per_symbol, orion_b200_block **out);
+int orion_b200_cfo_derotate(float cfo_hz, float fs, const orion_b200_c32 *in, orion_b200_c32 *out, size_t n);
 
 /* ------------------------------------------------------------------------------------
  * AGC (next-row scope): AgcRms (f32 -> f32, src/dsp/agc.rs:8-75) and AgcRmsIq (C32 -> C32, agc.rs:81-150).

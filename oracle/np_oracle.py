@@ -388,3 +388,60 @@ def agc_rms(fs, attack_ms, release_ms, target_rms, x, env0=0.0, iq=False):
         else:
             out[i] = f32(g * x[i])
     return out, env
+
+
+# ---- soft-symbol gain and hard-decision slicers (src/demodulate/{bpsk,qpsk,qam}.rs) ----------------------------
+def symbol_gain(x, g):
+    """BpskDemod / QpskDemod / QamDemod::process (bpsk.rs:31-50): out = (g*re, g*im)."""
+    x = np.asarray(x, np.complex64)
+    g = f32(g)
+    out = np.empty(x.size, np.complex64)
+    out.real = (g * x.real.astype(f32)).astype(f32)
+    out.imag = (g * x.imag.astype(f32)).astype(f32)
+    return out
+
+
+def bpsk_decide(x, out_cap=None):
+    """BpskDecider::process (bpsk.rs:67-88): one bit per symbol, re < 0."""
+    x = np.asarray(x, np.complex64)
+    n = x.size if out_cap is None else min(x.size, out_cap)
+    return (x.real[:n] < 0).astype(np.uint8)
+
+
+def qpsk_decide(x, out_cap=None):
+    """QpskDecider::process (qpsk.rs:68-98): bits (re < 0, im < 0) per symbol; n_syms = min(len(in), len(out) / 2)."""
+    x = np.asarray(x, np.complex64)
+    n = x.size if out_cap is None else min(x.size, out_cap // 2)
+    out = np.empty(2 * n, np.uint8)
+    out[0::2] = x.real[:n] < 0
+    out[1::2] = x.imag[:n] < 0
+    return out
+
+
+def qam_axis_scale(bits):
+    """modulate/qam.rs:27-31: f64 average energy, f64 sqrt and reciprocal, cast to f32."""
+    m = 1 << (bits // 2)
+    return f32(1.0 / np.sqrt(2.0 * float(m * m - 1) / 3.0))
+
+
+def qam_thresholds(bits):
+    """qam.rs:20-31: midpoints -(M-2) + 2j, scaled, j < M-1."""
+    m = 1 << (bits // 2)
+    scale = qam_axis_scale(bits)
+    return np.array([f32(f32(f32(2 * j) - f32(m - 2)) * scale) for j in range(m - 1)], f32)
+
+
+def qam_decide(x, bits, out_cap=None):
+    """QamDecider<BITS>::process (qam.rs:122-178): per axis, natural index = thresholds below v, Gray, MSB first."""
+    assert bits in (4, 6, 8)
+    x = np.asarray(x, np.complex64)
+    n = x.size if out_cap is None else min(x.size, out_cap // bits)
+    k = bits // 2
+    th = qam_thresholds(bits)
+    out = np.empty(n * bits, np.uint8)
+    for axis, v in ((0, x.real[:n].astype(f32)), (1, x.imag[:n].astype(f32))):
+        nat = (v[:, None] > th[None, :]).sum(axis=1)
+        gray = nat ^ (nat >> 1)
+        for b in range(k):
+            out[axis * k + b::bits] = (gray >> (k - 1 - b)) & 1
+    return out

@@ -18,11 +18,12 @@ struct AgcArgs {
     const void *in;
     void *out;
     long long n;
-    int iq;                          // 0: f32 -> f32 (AgcRms), 1: C32 -> C32 (AgcRmsIq)
+    int iq;                          // 0: f32 -> f32 (AgcRms), 1: C32 -> C32 (AgcRmsIq), 2: f32 -> C32 (CwKeyedMod, below)
     float attack_a, release_a, target_rms, min_gain, max_gain;
     long long L, W;                  // chunk length, warm-up length
     const CarryState *carry_in;
     CarryState *carry_out;
+    NcoParam osc; float gain;        // CwKeyedMod: tone oscillator (replayed bit-exactly) and output gain
 };
 
 template <bool IQ>
@@ -74,11 +75,49 @@ __global__ void __launch_bounds__(128) agc_kernel(const __grid_constant__ AgcArg
     }
 }
 
+// CwKeyedMod (src/modulate/cw.rs:44-102): tgt = clamp(x, 0, 1); env <- a*env + (1-a)*tgt with a = alpha_rise if tgt >= env
+// else alpha_fall; out = mix_with_nco((env * gain, 0), nco).  The same kind of recurrence as the AGC's tracker (both
+// branches contract, they meet at env = tgt), so the same chunking applies; attack_a / release_a carry alpha_rise / alpha_fall.
+__global__ void __launch_bounds__(128) cw_mod_kernel(const __grid_constant__ AgcArgs a) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s0 = c * a.L;
+    if (s0 >= a.n) return;
+    const long long s1 = min(s0 + a.L, a.n);
+    const float *x = reinterpret_cast<const float *>(a.in);
+    float env;
+    long long i = s0 - a.W;
+    if (i <= 0) { i = 0; env = __ldcg(&a.carry_in->pad.x); }
+    else env = fminf(fmaxf(__ldg(x + i), 0.0f), 1.0f);
+    for (; i < s0; ++i) {
+        const float tgt = fminf(fmaxf(__ldg(x + i), 0.0f), 1.0f);
+        const float al = (tgt >= env) ? a.attack_a : a.release_a;
+        env = al * env + (1.0f - al) * tgt;
+    }
+    unsigned ctr;
+    float2 p = nco_exact_any(a.osc, s0);
+    ctr = (unsigned)(a.osc.kbase + 1ull + (unsigned long long)s0);
+    const float2 w = make_float2(a.osc.xwre, a.osc.xwim);
+    for (; i < s1; ++i) {
+        const float tgt = fminf(fmaxf(__ldg(x + i), 0.0f), 1.0f);                // cw.rs:52
+        const float al = (tgt >= env) ? a.attack_a : a.release_a;
+        env = al * env + (1.0f - al) * tgt;                                       // cw.rs:53-57
+        const float xr = env * a.gain, xi = 0.0f;
+        reinterpret_cast<float2 *>(a.out)[i] = make_float2(xr * p.x - xi * p.y, xr * p.y + xi * p.x);   // nco.rs:63-66
+        nco_step_exact(p, w, ctr);
+    }
+    if (s1 == a.n) {
+        CarryState cs = *a.carry_in;
+        cs.pad.x = env;
+        *a.carry_out = cs;
+    }
+}
+
 cudaError_t agc_launch(const AgcArgs &a, cudaStream_t stream) {
     const long long nchunks = (a.n + a.L - 1) / a.L;
     const int threads = 128;
     const unsigned blocks = (unsigned)((nchunks + threads - 1) / threads);
-    if (a.iq) agc_kernel<true><<<blocks, threads, 0, stream>>>(a);
+    if (a.iq == 2) cw_mod_kernel<<<blocks, threads, 0, stream>>>(a);
+    else if (a.iq) agc_kernel<true><<<blocks, threads, 0, stream>>>(a);
     else agc_kernel<false><<<blocks, threads, 0, stream>>>(a);
     return cudaGetLastError();
 }

@@ -149,6 +149,8 @@ struct ChainArgs {
     // recursive sections
     int   nsec;
     int   ngroups;
+    int   pipe_park_slots;       // per-warp scan-state slots (2, or ngroups + 1 for the multi-group pipeline)
+    int   pipe_u_slots;          // per-warp item slots of the multi-group pipeline (0: single-group path)
     GroupParam grp[kMaxGroups];  // grp immediately followed by sec: the kernels view the pair as one block
     SecParam sec[kMaxSections];
     const GroupTables *gtabs;    // [ngroups]

@@ -1515,6 +1515,34 @@ DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int
     store_f32<NPT>(a, tile, lane, u, xs);
 }
 
+// Chains with more than one section group run a software pipeline that is as deep as they have groups: in every loop
+// iteration a warp runs the front of a new tile (up to the aggregate of group 0) and then, for each older tile it still
+// holds, ONE stage: stage k finishes group k-1 (look-back, the reference recursion) and, unless that was the last
+// group, forms and publishes the aggregate of group k.  Every aggregate is therefore published a whole iteration before
+// the tiles behind it look for it -- for every group, not just the first.  (Before, groups 1.. were handled front +
+// finish back to back, so each tile waited for aggregates its 31 predecessors were publishing at that very moment:
+// the AM chain of BASELINE config 3 spent 56 % of its stall samples polling link records.)  The items of the tiles in
+// flight live in shared memory between stages (item-major, conflict free).
+template <int NPT>
+DEV void stage_step(const ChainArgs &a, const Hot *hot, int k, int S, long long tile, int lane, float *us, float *park,
+                    unsigned char *xs) {
+    float u[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) u[i] = us[i * kThreads + lane];
+    const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
+    const bool full = jt + NPT <= a.n_out;
+    group_finish_parked<NPT>(a, hot, k - 1, tile, lane, u, full, jt, park);
+    if (k < S) {
+        group_front_park<NPT>(a, hot, k, tile, lane, u, full, park);
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) us[i * kThreads + lane] = u[i];
+        __syncwarp();
+    } else {
+        store_f32<NPT>(a, tile, lane, u, xs);
+        if (tile == a.ntiles - 1) handoff_signal(a, 1, lane);
+    }
+}
+
 // direct front: items straight from global memory (rate-1 blocks)
 template <int NPT>
 DEV void front_direct(const ChainArgs &a, long long tile, int lane, float2 (&z)[NPT], float (&u)[NPT], float2 &zhalo,
@@ -1660,12 +1688,16 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     const long long G = gridDim.x, cta = blockIdx.x;
     const size_t stage_bytes = (size_t)(kThreads + HRc) * (GE::fixed ? GE::pitch : a.row_pitch);      // bytes one TMA load delivers
     const size_t stage_stride = (stage_bytes + 127) & ~(size_t)127;          // TMA destinations are 128-byte aligned
-    // group-0 scan state of the two tiles a warp has in flight: behind the stage ring in dynamic smem
-    float (*park)[33 * kMaxGroupDim] = reinterpret_cast<float (*)[33 * kMaxGroupDim]>(
-        smem + (size_t)NS * stage_stride + (size_t)wid * 2 * 33 * kMaxGroupDim * sizeof(float));
-    // polyphase tap table: behind the park area
-    float2 *taps_sh = reinterpret_cast<float2 *>(smem + (size_t)NS * stage_stride +
-                                                 (size_t)NW * 2 * 33 * kMaxGroupDim * sizeof(float));
+    // per-warp pipeline area behind the stage ring: [tile ids of the tiles in flight (16 B)] [scan state ("park") slots]
+    // [item slots of the multi-group pipeline]
+    const size_t park_bytes = 33 * kMaxGroupDim * sizeof(float);
+    const size_t warp_pipe = 16 + (size_t)a.pipe_park_slots * park_bytes + (size_t)a.pipe_u_slots * (kThreads * NPT * sizeof(float));
+    unsigned char *pipe = smem + (size_t)NS * stage_stride + (size_t)wid * warp_pipe;
+    int *qtile = reinterpret_cast<int *>(pipe);
+    float (*park)[33 * kMaxGroupDim] = reinterpret_cast<float (*)[33 * kMaxGroupDim]>(pipe + 16);
+    float *uslots = reinterpret_cast<float *>(pipe + 16 + (size_t)a.pipe_park_slots * park_bytes);
+    // polyphase tap table: behind the pipeline areas
+    float2 *taps_sh = reinterpret_cast<float2 *>(smem + (size_t)NS * stage_stride + (size_t)NW * warp_pipe);
     // ... then the generic taps g[] (discriminator halo) and the section / group launch data
     float *g_sh = reinterpret_cast<float *>(taps_sh + a.ntaps2);
     Hot *hot_sh = reinterpret_cast<Hot *>(reinterpret_cast<unsigned char *>(g_sh) + (((size_t)a.Lg * sizeof(float) + 15) & ~(size_t)15));
@@ -1756,6 +1788,7 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     for (int i = 0; i < NPT; ++i) u_pend[i] = 0.f;
     long long pend_tile = -1;
     int slot_pp = 0;
+    int pipe_it = 0;                                       // tiles this warp has put into the multi-group pipeline
     auto stamp = [&](long long t, int k) {
         if ((ORION_TRACE && a.trace) && lane == 0) a.trace[t * 16 + k] = clock64();
         __syncwarp();
@@ -1861,7 +1894,26 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
             if (!has_sections) a.trace[tile * 16 + 3] = clock64();
         }
         if (!has_sections && tile == a.ntiles - 1) handoff_signal(a, 1, lane);      // the call's carried state is complete
-        if (has_sections) {
+        if (has_sections && !Dm<DM>::lr4 && a.pipe_u_slots > 0) {
+            // multi-group chain: pipeline of depth S = ngroups (stage_step)
+            const int S = a.ngroups;
+            group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[pipe_it % (S + 1)]);
+            for (int k = S; k >= 1; --k) {
+                if (pipe_it - k < 0) continue;
+                const int e = (pipe_it - k) % S;
+                const long long t = qtile[e];
+                stage_step<NPT>(a, hot, k, S, t, lane, uslots + (size_t)e * (kThreads * NPT), park[(pipe_it - k) % (S + 1)], xs);
+            }
+            {
+                const int e = pipe_it % S;
+                float *us = uslots + (size_t)e * (kThreads * NPT);
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) us[i * kThreads + lane] = u[i];
+                if (lane == 0) qtile[e] = (int)tile;
+                __syncwarp();
+            }
+            ++pipe_it;
+        } else if (has_sections) {
             if (Dm<DM>::lr4) lr4_front_park<NPT>(a, hot, tile, lane, E4, park[slot_pp]);
             else if (a.ngroups > 0) group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[slot_pp]);
             stamp(tile, 3);
@@ -1881,6 +1933,17 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
         else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
         if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
+    }
+    if (!Dm<DM>::lr4 && a.pipe_u_slots > 0 && pipe_it > 0) {           // drain the multi-group pipeline
+        const int S = a.ngroups;
+        for (int j = pipe_it; j < pipe_it + S; ++j)
+            for (int k = S; k >= 1; --k) {
+                const int en = j - k;                                    // entry iteration of the tile at stage k
+                if (en < 0 || en >= pipe_it) continue;
+                const int e = en % S;
+                const long long t = qtile[e];
+                stage_step<NPT>(a, hot, k, S, t, lane, uslots + (size_t)e * (kThreads * NPT), park[en % (S + 1)], xs);
+            }
     }
     if ((ORION_TRACE && a.trace) && lane == 0) {
         unsigned long long gt;

@@ -53,7 +53,17 @@ cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, u
 }
 
 cudaError_t chain_kernel_prepare(chain_kernel_t k, size_t dyn_smem, int warps, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    // the opt-in limit is a property of the FUNCTION, and blocks of different shapes share one instance: always raise it to
+    // the device maximum (a per-block value would be overwritten by the next block that is created)
+    int dev = 0, optin = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)k);
+    if (e != cudaSuccess) return e;
+    optin -= (int)fa.sharedSizeBytes;                        // static shared memory counts against the same limit
+    if (dyn_smem > (size_t)optin) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;

@@ -21,6 +21,9 @@
 #include <new>
 #include <string>
 #include <vector>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 namespace orion {
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);
@@ -51,8 +54,19 @@ struct AgcArgs {                 // agc_kernels.cu
     float attack_a, release_a, target_rms, min_gain, max_gain;
     long long L, W;
     const CarryState *carry_in; CarryState *carry_out;
+    NcoParam osc; float gain;    // iq == 2 (CwKeyedMod): tone oscillator and output gain
 };
 cudaError_t agc_launch(const AgcArgs &a, cudaStream_t stream);
+struct SliceArgs { const float2 *in; unsigned char *out; long long n_syms; int bits; float th[15]; };     // aux_kernels.cu
+struct FmApplyArgs { const float *x; float2 *out; long long n; float kf, gain; const long long *tile_off; NcoParam rf;
+                     const CarryState *carry_in; CarryState *carry_out; };
+struct SsbSplitArgs { const float *x; float *xi, *xq; long long n; NcoParam aud; };
+struct SsbCombineArgs { const float *yi, *yq; float2 *out; long long n; float side; NcoParam rf; };
+cudaError_t gain_c32_launch(const void *in, void *out, long long n, float g, int sms, cudaStream_t st);
+cudaError_t slice_launch(const SliceArgs &a, int sms, cudaStream_t st);
+cudaError_t fm_mod_launch(const FmApplyArgs &a, long long *d_tile, cudaStream_t st);
+cudaError_t ssb_split_launch(const SsbSplitArgs &a, cudaStream_t st);
+cudaError_t ssb_combine_launch(const SsbCombineArgs &a, cudaStream_t st);
 cudaError_t osc_expand_launch(const OscAnchor *d_an, int n_an, float2 *d_fine, unsigned long long c0, long long fine_len,
                               cudaStream_t stream);
 }  // namespace orion
@@ -409,6 +423,7 @@ struct FirPlan {
     std::vector<float2> taps2;     // [u][q][c]
 };
 
+enum : int { AUX_NONE = 0, AUX_GAIN = 1, AUX_SLICE = 2, AUX_FMMOD = 3, AUX_SSBMOD = 4 };
 const size_t kMaxStageBytes = 100 * 1024;      // one staged tile
 const size_t kRingBudget = 176 * 1024;         // per-CTA shared memory for the stage ring (two CTAs per SM)
 
@@ -496,12 +511,37 @@ encode_tiled_t get_encode_tiled() {
     return fn;
 }
 
+// Streaming copy for the staging ring: the destination is written with non-temporal stores, so the copy moves 2 bytes of
+// memory traffic per byte instead of 3 (no read-for-ownership of the destination lines) -- the staging copy of a pageable
+// caller buffer is bound by host memory bandwidth, not by PCIe.
+static void stream_copy(void *dst, const void *src, size_t bytes) {
+#if defined(__AVX2__)
+    char *d = (char *)dst;
+    const char *s = (const char *)src;
+    const size_t head = (32 - ((uintptr_t)d & 31)) & 31;
+    if (bytes < 4096 + head) { memcpy(dst, src, bytes); return; }
+    if (head) { memcpy(d, s, head); d += head; s += head; bytes -= head; }
+    size_t n128 = bytes / 128;
+    for (size_t i = 0; i < n128; ++i, d += 128, s += 128) {
+        _mm_prefetch(s + 1024, _MM_HINT_NTA);
+        const __m256i a = _mm256_loadu_si256((const __m256i *)s), b = _mm256_loadu_si256((const __m256i *)(s + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(s + 64)), e = _mm256_loadu_si256((const __m256i *)(s + 96));
+        _mm256_stream_si256((__m256i *)d, a); _mm256_stream_si256((__m256i *)(d + 32), b);
+        _mm256_stream_si256((__m256i *)(d + 64), c); _mm256_stream_si256((__m256i *)(d + 96), e);
+    }
+    _mm_sfence();
+    if (bytes & 127) memcpy(d, s, bytes & 127);
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
 // ---- host copy pool: pageable caller buffers are moved to / from the pinned staging ring by a few threads ------
 class CopyPool {
 public:
     static CopyPool &get() { static CopyPool p; return p; }
     void copy(void *dst, const void *src, size_t bytes) {
-        if (bytes < (1u << 20) || workers_.empty()) { memcpy(dst, src, bytes); return; }
+        if (bytes < (1u << 20) || workers_.empty()) { stream_copy(dst, src, bytes); return; }
         std::lock_guard<std::mutex> job(job_m_);                  // one job at a time (blocks on different threads share the pool)
         const size_t parts = workers_.size() + 1;
         const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
@@ -511,14 +551,14 @@ public:
             next_ = 1; pending_ = (int)workers_.size(); ++gen_;
         }
         cv_.notify_all();
-        memcpy(dst, src, std::min(per, bytes));                    // the caller's share
+        stream_copy(dst, src, std::min(per, bytes));               // the caller's share
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this] { return pending_ == 0; });
     }
 private:
     CopyPool() {
         unsigned hw = std::thread::hardware_concurrency();
-        int n = hw >= 32 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+        int n = hw >= 16 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
         if (const char *e = getenv("ORION_B200_COPY_THREADS")) n = std::max(0, std::min(15, atoi(e) - 1));
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
     }
@@ -539,7 +579,7 @@ private:
                 part = next_++;
             }
             const size_t off = part * per_;
-            if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+            if (off < bytes_) stream_copy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
             {
                 std::lock_guard<std::mutex> lk(m_);
                 if (--pending_ == 0) done_.notify_all();
@@ -587,7 +627,14 @@ struct orion_b200_block {
     int opt_exact = -1;                   // -1 auto (by block kind), 0 closed form everywhere, 1 exact everywhere
     double exact_host_ms = 0.0;           // host time spent walking the recurrence (reported separately from kernel time)
     int cw_gain_sec = -1;
-    int agc = 0;                          // 1: AgcRms (f32), 2: AgcRmsIq (C32) -- agc_kernels.cu instead of the chain kernel
+    int agc = 0;                          // 1: AgcRms (f32), 2: AgcRmsIq (C32), 3: CwKeyedMod -- agc_kernels.cu instead of the chain kernel
+    int aux = 0;                          // AUX_*: the elementwise / scan kernels of aux_kernels.cu
+    int slice_bits = 0;                   // AUX_SLICE: 1 BPSK, 2 QPSK, 4 / 6 / 8 QAM
+    float slice_th[15] = { 0 };
+    float aux_gain = 1.0f, aux_p0 = 0.f, aux_side = 1.0f;
+    long long *d_fm_tiles = nullptr; size_t fm_tiles_cap = 0;
+    orion_b200_block *child[2] = { nullptr, nullptr };   // AUX_SSBMOD: the two LpCascade filters
+    float *d_ssb[4] = { nullptr, nullptr, nullptr, nullptr }; size_t ssb_cap = 0;
     float agc_attack_a = 0.f, agc_release_a = 0.f, agc_target = 0.f, agc_min_gain = 0.05f, agc_max_gain = 20.0f;
     // ---- plan ----
     FirPlan plan;
@@ -595,6 +642,7 @@ struct orion_b200_block {
     chain_kernel_t kernel = nullptr;
     int ctas_per_sm = 1, sm_count = 1;
     int ws = 0;                           // the warp-specialised instance is selected
+    int pipe_park_slots = 2, pipe_u_slots = 0;   // per-warp pipeline area of the chain kernel (multi-group chains)
     // ---- options ----
     int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0, opt_overlap = 0;
     long long *trace = nullptr;           // debug: device buffer of 8 x int64 per tile
@@ -660,8 +708,9 @@ cudaError_t dev_copy(orion_b200_block *b, void *dst, const void *src, size_t n) 
     return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, b->stream);
 }
 
-size_t in_item_bytes(const orion_b200_block *b) { return b->in_item == ORION_B200_ITEM_C32 ? 8 : 4; }
-size_t out_item_bytes(const orion_b200_block *b) { return b->out_item == ORION_B200_ITEM_C32 ? 8 : 4; }
+size_t item_bytes(int item) { return item == ORION_B200_ITEM_C32 ? 8 : (item == ORION_B200_ITEM_U8 ? 1 : 4); }
+size_t in_item_bytes(const orion_b200_block *b) { return item_bytes(b->in_item); }
+size_t out_item_bytes(const orion_b200_block *b) { return item_bytes(b->out_item); }
 
 int npt_of(const orion_b200_block *b) { return b->plan.R * b->plan.U; }
 
@@ -696,8 +745,29 @@ int finalize_plan(orion_b200_block *b) {
     }
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm, b->nbatch > 1);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
+    // per-warp pipeline area (chain_kernels.cuh): chains with several section groups keep one tile per group in flight
+    {
+        const int ng = (int)split_groups(b->secs).size();
+        const bool multi = ng >= 2 && dm < 100;
+        b->pipe_park_slots = multi ? ng + 1 : 2;
+        b->pipe_u_slots = multi ? ng : 0;
+    }
+    const size_t warp_pipe = 16 + (size_t)b->pipe_park_slots * 33 * kMaxGroupDim * sizeof(float) +
+                             (size_t)b->pipe_u_slots * kThreads * npt_of(b) * sizeof(float);
+    auto rest_of = [&](int warps) {
+        return (size_t)warps * warp_pipe + b->plan.taps2.size() * sizeof(float2) +
+               ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +
+               sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +
+               (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +
+               (b->plan.front == FRONT_DIRECT ? (size_t)warps * 32 * 144 + 16 : 0);
+    };
+    const size_t smem_limit = (size_t)(227 - 3) * 1024;
+    // deep pipelines of wide tiles: fewer ring slots first (down to 4), then fewer warps
+    while (b->plan.nstages > 4 && b->plan.stage_bytes * b->plan.nstages + rest_of(b->plan.warps) > smem_limit) b->plan.nstages -= 1;
+    while (b->plan.warps > 4 && b->plan.stage_bytes * b->plan.nstages + rest_of(b->plan.warps) > smem_limit) b->plan.warps -= 2;
+    while (b->plan.nstages > 1 && b->plan.stage_bytes * b->plan.nstages + rest_of(b->plan.warps) > smem_limit) b->plan.nstages -= 1;
     b->plan.dyn_smem = b->plan.stage_bytes * b->plan.nstages +
-                       (size_t)b->plan.warps * 2 * 33 * kMaxGroupDim * sizeof(float) +     // stage ring + park area
+                       (size_t)b->plan.warps * warp_pipe +                                  // stage ring + per-warp pipeline area
                        b->plan.taps2.size() * sizeof(float2) +                              // + tap table
                        ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +            // + generic taps
                        sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
@@ -780,6 +850,8 @@ int reset_state(orion_b200_block *b) {
     b->post.reset_phase();
     b->pre.x.recent.clear();
     b->post.x.recent.clear();
+    for (orion_b200_block *c : b->child)
+        if (c) { const int st = reset_state(c); if (st != ORION_B200_OK) return st; }
     return ORION_B200_OK;
 }
 
@@ -818,8 +890,10 @@ int init_device_side(orion_b200_block *b) {
 
 int finish_create(orion_b200_block *b, orion_b200_block **out) {
     if (b->secs.size() > (size_t)kMaxSections) { delete b; return ORION_B200_ERR_UNSUPPORTED; }
-    b->in_item = kind_f32_in(b->demod) ? ORION_B200_ITEM_F32 : ORION_B200_ITEM_C32;
-    b->out_item = kind_c32_out(b->demod) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
+    if (!b->aux && b->agc != 3) {
+        b->in_item = kind_f32_in(b->demod) ? ORION_B200_ITEM_F32 : ORION_B200_ITEM_C32;
+        b->out_item = kind_c32_out(b->demod) ? ORION_B200_ITEM_C32 : ORION_B200_ITEM_F32;
+    }
     int st = init_device_side(b);
     if (st != ORION_B200_OK) {
         t_create_error = b->err;                 // orion_b200_last_create_error()
@@ -849,6 +923,12 @@ void add_lr4(orion_b200_block *b, float fs, float fc) {
 }
 
 void length_rules(const orion_b200_block *b, size_t n_in, size_t out_cap, size_t *consume, size_t *produce) {
+    if (b->aux == AUX_SLICE) {                         // qpsk.rs:70 / qam.rs:150: n_syms = min(len(in), len(out) / BITS)
+        const size_t n = std::min(n_in, out_cap / (size_t)b->slice_bits);
+        *consume = n;
+        *produce = n * (size_t)b->slice_bits;
+        return;
+    }
     if (b->fir == FIR_DECIM || (b->fir != FIR_NONE && b->M > 1)) {   // decim.rs:45,66-75 (any m, m = 1 included): all input read, ceil(n/m) capped
         *consume = n_in;
         const size_t n_out = (n_in + b->M - 1) / b->M;
@@ -980,19 +1060,101 @@ int launch_agc(orion_b200_block *b, const void *d_in, size_t n, void *d_out) {
     a.L = std::max<long long>(std::max<long long>(a.W / 4, 64), ((long long)n + 65535) / 65536);
     if (const char *e = getenv("ORION_B200_AGC_CHUNK")) a.L = std::max(1, atoi(e));        // experiments / tests
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
+    if (b->agc == 3) {                                            // CwKeyedMod: rise / fall envelope + tone oscillator (replayed bit-exactly)
+        a.iq = 2;
+        a.gain = b->aux_gain;
+        a.osc = b->post.param(b->k_post);
+        const int st = prepare_exact(b, b->post, b->k_post, n, 0, &a.osc);
+        if (st != ORION_B200_OK) return st;
+    }
     cudaError_t e = agc_launch(a, b->stream);
     if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "agc kernel launch", e);
     b->launches += 1;
     b->pp = (b->pp + 1) % 3;
+    if (b->agc == 3) b->k_post += n;
+    return ORION_B200_OK;
+}
+
+int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out, long long batch_in_stride = 0, long long batch_out_stride = 0);
+
+// the blocks of aux_kernels.cu: symbol gain, slicers, FM and SSB modulators
+int launch_aux(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out) {
+    cudaError_t e = cudaSuccess;
+    if (b->aux == AUX_GAIN) {
+        e = gain_c32_launch(d_in, d_out, (long long)n_in, b->aux_gain, b->sm_count, b->stream);
+        b->launches += 1;
+    } else if (b->aux == AUX_SLICE) {
+        SliceArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = (const float2 *)d_in; a.out = (unsigned char *)d_out; a.n_syms = (long long)n_in; a.bits = b->slice_bits;
+        memcpy(a.th, b->slice_th, sizeof(a.th));
+        e = slice_launch(a, b->sm_count, b->stream);
+        b->launches += 1;
+    } else if (b->aux == AUX_FMMOD) {
+        const size_t ntiles = (n_in + 1023) / 1024;
+        if (ntiles > b->fm_tiles_cap) {
+            CK(cudaStreamSynchronize(b->stream));
+            cudaFree(b->d_fm_tiles); b->d_fm_tiles = nullptr;
+            CK(cudaMalloc(&b->d_fm_tiles, (ntiles + ntiles / 4 + 64) * sizeof(long long)));
+            b->fm_tiles_cap = ntiles + ntiles / 4 + 64;
+        }
+        FmApplyArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = (const float *)d_in; a.out = (float2 *)d_out; a.n = (long long)n_in;
+        a.kf = kTau * b->aux_p0 / b->fs_demod;                          // fm.rs:50
+        a.gain = b->aux_gain;
+        a.tile_off = b->d_fm_tiles;
+        a.rf = b->post.param(b->k_post);
+        const int st = prepare_exact(b, b->post, b->k_post, n_in, 0, &a.rf);
+        if (st != ORION_B200_OK) return st;
+        a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
+        e = fm_mod_launch(a, b->d_fm_tiles, b->stream);
+        b->launches += 3;
+        b->pp = (b->pp + 1) % 3;
+        b->k_post += n_in;
+    } else if (b->aux == AUX_SSBMOD) {
+        if (n_in > b->ssb_cap) {
+            CK(cudaStreamSynchronize(b->stream));
+            for (float *&p : b->d_ssb) { cudaFree(p); p = nullptr; }
+            const size_t cap = n_in + n_in / 4 + 64;
+            for (float *&p : b->d_ssb) CK(cudaMalloc(&p, cap * sizeof(float)));
+            b->ssb_cap = cap;
+        }
+        SsbSplitArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.x = (const float *)d_in; sa.xi = b->d_ssb[0]; sa.xq = b->d_ssb[1]; sa.n = (long long)n_in;
+        sa.aud = b->pre.param(b->k_pre);
+        int st = prepare_exact(b, b->pre, b->k_pre, n_in, 0, &sa.aud);
+        if (st != ORION_B200_OK) return st;
+        e = ssb_split_launch(sa, b->stream);
+        if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "ssb split launch", e);
+        for (int c = 0; c < 2; ++c) {                                    // lp_i, lp_q: the library's own LpCascade blocks
+            b->child[c]->stream = b->stream;
+            st = launch(b->child[c], b->d_ssb[c], n_in, b->d_ssb[2 + c], n_in, 0, 0);
+            if (st != ORION_B200_OK) return fail(b, st, b->child[c]->err.c_str());
+        }
+        SsbCombineArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.yi = b->d_ssb[2]; ca.yq = b->d_ssb[3]; ca.out = (float2 *)d_out; ca.n = (long long)n_in; ca.side = b->aux_side;
+        ca.rf = b->post.param(b->k_post);
+        st = prepare_exact(b, b->post, b->k_post, n_in, 0, &ca.rf);
+        if (st != ORION_B200_OK) return st;
+        e = ssb_combine_launch(ca, b->stream);
+        b->launches += 2;
+        b->k_pre += n_in; b->k_post += n_in;
+    }
+    if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "aux kernel launch", e);
+    (void)n_out;
     return ORION_B200_OK;
 }
 
 int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
-           long long batch_in_stride = 0, long long batch_out_stride = 0) {
+           long long batch_in_stride, long long batch_out_stride) {
     if (b->plan_dirty) { int st = finalize_plan(b); if (st) return st; }
     if (n_in == 0) return ORION_B200_OK;
     CK(cudaSetDevice(b->device));
     if (b->agc) return launch_agc(b, d_in, n_in, d_out);
+    if (b->aux) return launch_aux(b, d_in, n_in, d_out, n_out);
     const int npt = npt_of(b);
     const long long tile_items = (long long)kThreads * npt;
     long long ntiles = ((long long)n_out + tile_items - 1) / tile_items;
@@ -1048,6 +1210,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.nsec = nsec;
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
     a.ngroups = (int)b->groups.size();
+    a.pipe_park_slots = b->pipe_park_slots; a.pipe_u_slots = b->pipe_u_slots;
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
@@ -1478,7 +1641,8 @@ int orion_b200_pm_mod_create(float fs, float kp_rad_per_unit, float rf_hz, orion
 }
 int orion_b200_mod_set_gain(orion_b200_block *b, float gain) {      // set_gain, modulate/am.rs:31-33, pm.rs:24-26
     if (!b) return ORION_B200_ERR_INVALID;
-    if (b->demod == MOD_AM) b->k3 = gain;
+    if (b->aux == AUX_FMMOD || b->agc == 3) b->aux_gain = gain;      // modulate/fm.rs:35-37, cw.rs:35-37
+    else if (b->demod == MOD_AM) b->k3 = gain;
     else if (b->demod == MOD_PM) b->k2 = gain;
     else return fail(b, ORION_B200_ERR_INVALID, "not a modulator");
     return ORION_B200_OK;
@@ -1509,6 +1673,91 @@ float orion_b200_agc_env(orion_b200_block *b) {                     // the track
     return cs.pad.x;
 }
 
+// ---- modulators, continued: FM (phase prefix sum), CW (chunked envelope), SSB (phasing) ------
+int orion_b200_fm_mod_create(float sample_rate, float deviation_hz, float rf_hz, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // FmPhaseAccumMod::new, modulate/fm.rs:22-31
+    b->aux = AUX_FMMOD;
+    b->in_item = ORION_B200_ITEM_F32; b->out_item = ORION_B200_ITEM_C32;
+    b->demod = DEMOD_F32;
+    b->fs_demod = sample_rate;
+    b->aux_p0 = deviation_hz;
+    b->post.set(rf_hz, sample_rate, 0);
+    return finish_create(b, out);
+}
+int orion_b200_fm_mod_set_deviation(orion_b200_block *b, float deviation_hz) {    // modulate/fm.rs:32-34
+    if (!b || b->aux != AUX_FMMOD) return b ? fail(b, ORION_B200_ERR_INVALID, "not an FM modulator") : ORION_B200_ERR_INVALID;
+    b->aux_p0 = deviation_hz;
+    return ORION_B200_OK;
+}
+int orion_b200_cw_mod_create(float sample_rate, float tone_hz, float rise_ms, float fall_ms, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // CwKeyedMod::new, modulate/cw.rs:21-34
+    b->agc = 3;
+    b->in_item = ORION_B200_ITEM_F32; b->out_item = ORION_B200_ITEM_C32;
+    b->demod = DEMOD_F32;
+    const float tau_r = (maxf_rs(rise_ms, 0.1f) * 1e-3f) * sample_rate;
+    const float tau_f = (maxf_rs(fall_ms, 0.1f) * 1e-3f) * sample_rate;
+    b->agc_attack_a = expf(-1.0f / tau_r);
+    b->agc_release_a = expf(-1.0f / tau_f);
+    b->post.set(tone_hz, sample_rate, 0);
+    return finish_create(b, out);
+}
+int orion_b200_ssb_mod_create(float fs, float audio_bw_hz, float audio_if_hz, float rf_hz, int usb, orion_b200_block **out) {
+    NEW_BLOCK();                                                     // SsbPhasingMod::new, modulate/ssb.rs:23-35
+    b->aux = AUX_SSBMOD;
+    b->in_item = ORION_B200_ITEM_F32; b->out_item = ORION_B200_ITEM_C32;
+    b->demod = DEMOD_F32;
+    b->aux_side = usb ? 1.0f : -1.0f;
+    b->pre.set(audio_if_hz, fs, 0);
+    b->post.set(rf_hz, fs, 0);
+    for (int c = 0; c < 2; ++c) {
+        const int st = orion_b200_lp_cascade_create(fs, audio_bw_hz * 0.9f, &b->child[c]);     // ssb.rs:25-30
+        if (st != ORION_B200_OK) { orion_b200_block_destroy(b->child[0]); delete b; return st; }
+    }
+    return finish_create(b, out);
+}
+
+// ---- soft-symbol gain blocks and hard-decision slicers ------------------------------------
+int orion_b200_symbol_gain_create(float gain, orion_b200_block **out) {       // BpskDemod / QpskDemod / QamDemod::new
+    NEW_BLOCK();
+    b->aux = AUX_GAIN;
+    b->in_item = ORION_B200_ITEM_C32; b->out_item = ORION_B200_ITEM_C32;
+    b->aux_gain = gain;
+    return finish_create(b, out);
+}
+int orion_b200_symbol_gain_set(orion_b200_block *b, float gain) {             // set_gain, bpsk.rs:22-24
+    if (!b || b->aux != AUX_GAIN) return b ? fail(b, ORION_B200_ERR_INVALID, "not a symbol gain block") : ORION_B200_ERR_INVALID;
+    b->aux_gain = gain;
+    return ORION_B200_OK;
+}
+int orion_b200_decider_create(int bits_per_symbol, orion_b200_block **out) {
+    if (!(bits_per_symbol == 1 || bits_per_symbol == 2 || bits_per_symbol == 4 || bits_per_symbol == 6 || bits_per_symbol == 8)) {
+        if (out) *out = nullptr;
+        return ORION_B200_ERR_INVALID;                               // qam.rs:13-18 check_bits
+    }
+    NEW_BLOCK();
+    b->aux = AUX_SLICE;
+    b->in_item = ORION_B200_ITEM_C32; b->out_item = ORION_B200_ITEM_U8;
+    b->slice_bits = bits_per_symbol;
+    if (bits_per_symbol >= 4) {                                      // qam.rs:20-31 with modulate/qam.rs:27-31 axis_scale
+        const int m = 1 << (bits_per_symbol / 2);
+        const double avg_e_total = 2.0 * (double)(m * m - 1) / 3.0;
+        const float scale = (float)(1.0 / sqrt(avg_e_total));
+        for (int j = 0; j < m - 1; ++j) b->slice_th[j] = ((float)(2 * j) - (float)(m - 2)) * scale;
+    }
+    return finish_create(b, out);
+}
+// The CFO de-rotation call sites (sync/ofdm_sync.rs:527-528, demodulate/ofdm_frame.rs:1489, dvb_t_frame.rs:389): a fresh
+// Rotator::new(-cfo_hz, fs).rotate_block(in, out) over one buffer.
+int orion_b200_cfo_derotate(float cfo_hz, float fs, const orion_b200_c32 *in, orion_b200_c32 *out, size_t n) {
+    orion_b200_block *r = nullptr;
+    int st = orion_b200_rotator_create(-cfo_hz, fs, &r);
+    if (st != ORION_B200_OK) return st;
+    size_t ir = 0, ow = 0;
+    st = orion_b200_block_process(r, in, n, out, n, &ir, &ow);
+    orion_b200_block_destroy(r);
+    return st;
+}
+
 // ---- channel bank --------------------------------------------------------------------------------
 struct BankGroup {                       // channels that share one demodulator configuration: one batched launch
     orion_b200_block *proto = nullptr;   // rate-1 block with nbatch members (kernel instance, section tables, per-member state)
@@ -1533,6 +1782,8 @@ struct orion_b200_bank {
     size_t z_cap = 0;
     std::vector<BankGroup> groups;
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_join;
     uint64_t launches = 0;
     // ---- general path: one block per channel ----
     std::vector<orion_b200_block *> ch;
@@ -1646,6 +1897,10 @@ int bank_fast_create(orion_b200_bank *k, const orion_b200_chain_spec *specs, siz
         st = orion_b200_block_set_stream(made, (void *)k->stream);
         if (st != ORION_B200_OK) return st;
     }
+    if (cudaEventCreateWithFlags(&k->ev_fork, cudaEventDisableTiming) != cudaSuccess) return ORION_B200_ERR_CUDA;
+    k->ev_join.assign(k->groups.size(), nullptr);
+    for (cudaEvent_t &e : k->ev_join)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return ORION_B200_ERR_CUDA;
     return ORION_B200_OK;
 }
 int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
@@ -1691,9 +1946,24 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     k->pp ^= 1;
     k->k_pre += n_in;
     const size_t ob = 4;
-    for (BankGroup &g : k->groups) {
+    // the demodulator groups are independent: with more than one they run side by side on their own streams between two
+    // events on the bank's stream (a small bank's group does not fill the machine by itself)
+    const bool fork = k->groups.size() > 1 && k->ev_fork != nullptr;
+    if (fork) cudaEventRecord(k->ev_fork, k->stream);
+    for (size_t gi = 0; gi < k->groups.size(); ++gi) {
+        BankGroup &g = k->groups[gi];
+        if (fork && gi > 0) {
+            g.proto->stream = g.proto->own_stream;
+            cudaStreamWaitEvent(g.proto->stream, k->ev_fork, 0);
+        } else {
+            g.proto->stream = k->stream;
+        }
         const int st = launch(g.proto, k->d_z, n_out, d_out, n_out, (long long)(n_out_all * sizeof(float2)), (long long)(out_stride * ob));
         if (st != ORION_B200_OK) return bank_fail(k, st, "bank demodulator group: " + g.proto->err);
+        if (fork && gi > 0) {
+            cudaEventRecord(k->ev_join[gi], g.proto->stream);
+            cudaStreamWaitEvent(k->stream, k->ev_join[gi], 0);
+        }
     }
     return ORION_B200_OK;
 }
@@ -1767,6 +2037,8 @@ void orion_b200_bank_destroy(orion_b200_bank *k) {
     if (k->fast) {
         if (k->stream) cudaStreamSynchronize(k->stream);
         for (BankGroup &g : k->groups) if (g.proto) { g.proto->stream = g.proto->own_stream; orion_b200_block_destroy(g.proto); }
+        if (k->ev_fork) cudaEventDestroy(k->ev_fork);
+        for (cudaEvent_t e : k->ev_join) if (e) cudaEventDestroy(e);
         cudaFree(k->d_osc); cudaFree(k->d_gt); cudaFree(k->d_hist[0]); cudaFree(k->d_hist[1]); cudaFree(k->d_z);
         cudaFree(k->d_in); cudaFree(k->d_out); cudaFree(k->d_err);
         if (k->h_err) cudaFreeHost(k->h_err);
@@ -1888,6 +2160,9 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     b->pre.x.free_device(); b->post.x.free_device();
     cudaFree(b->d_links); cudaFree(b->d_ticket); cudaFree(b->d_err); cudaFree(b->d_handoff);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_batch_chan);
+    cudaFree(b->d_fm_tiles);
+    for (float *p : b->d_ssb) cudaFree(p);
+    for (orion_b200_block *c : b->child) if (c) { c->stream = c->own_stream; orion_b200_block_destroy(c); }
     if (b->h_err) cudaFreeHost(b->h_err);
     for (int i = 0; i < orion_b200_block::kPipeSlots; ++i) {
         if (b->h_stage_in[i]) cudaFreeHost(b->h_stage_in[i]);

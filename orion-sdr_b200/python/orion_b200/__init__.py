@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("ORION_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "l
 WorkReport = namedtuple("WorkReport", ["in_read", "out_written"])   # src/core.rs:7-10
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED, ERR_INTERNAL = range(7)
-ITEM_F32, ITEM_C32 = 1, 2
+ITEM_F32, ITEM_C32, ITEM_U8 = 1, 2, 3
 MIX_NONE, MIX_ROTATE, MIX_NCO = 0, 1, 2
 FIR_NONE, FIR_DECIM, FIR_IQ = 0, 1, 2
 DEMOD_NONE, DEMOD_FM, DEMOD_PM, DEMOD_AM, DEMOD_AM_ABS, DEMOD_SSB, DEMOD_CW, DEMOD_USB = range(8)
@@ -101,6 +101,14 @@ def lib():
     sig("orion_b200_agc_rms_iq_create", i, f, f, f, f, pp)
     sig("orion_b200_agc_env", f, vp)
     sig("orion_b200_bank_set_stream", i, vp, vp)
+    sig("orion_b200_fm_mod_create", i, f, f, f, pp)
+    sig("orion_b200_fm_mod_set_deviation", i, vp, f)
+    sig("orion_b200_cw_mod_create", i, f, f, f, f, pp)
+    sig("orion_b200_ssb_mod_create", i, f, f, f, f, i, pp)
+    sig("orion_b200_symbol_gain_create", i, f, pp)
+    sig("orion_b200_symbol_gain_set", i, vp, f)
+    sig("orion_b200_decider_create", i, i, pp)
+    sig("orion_b200_cfo_derotate", i, f, f, vp, vp, sz)
     sig("orion_b200_lp_dc_cascade_create", i, f, f, f, i, pp)
     sig("orion_b200_dc_blocker_create", i, f, f, pp)
     sig("orion_b200_iir_cascade_create", i, vp, sz, pp)
@@ -182,6 +190,8 @@ EXPORTED_SYMBOLS = [
     "orion_b200_bank_synchronize", "orion_b200_bank_launch_count",
     "orion_b200_block_exact_host_ms", "orion_b200_last_create_error", "orion_b200_block_prepare_oscillator",
     "orion_b200_agc_rms_create", "orion_b200_agc_rms_iq_create", "orion_b200_agc_env", "orion_b200_bank_set_stream",
+    "orion_b200_fm_mod_create", "orion_b200_fm_mod_set_deviation", "orion_b200_cw_mod_create", "orion_b200_ssb_mod_create",
+    "orion_b200_symbol_gain_create", "orion_b200_symbol_gain_set", "orion_b200_decider_create", "orion_b200_cfo_derotate",
 ]
 
 
@@ -285,7 +295,7 @@ def debug_group_tables(sections, npt):
             "lb32": lb32, "tile": tile}
 
 
-_DT = {ITEM_F32: np.float32, ITEM_C32: np.complex64}
+_DT = {ITEM_F32: np.float32, ITEM_C32: np.complex64, ITEM_U8: np.uint8}
 
 
 class Block:
@@ -583,7 +593,7 @@ class AgcRmsIq(Block):                                                # src/dsp/
         return float(lib().orion_b200_agc_env(self._h))
 
 
-# ---- src/modulate (next-row scope; the FM / SSB / CW modulators are not built on the GPU) ---------------
+# ---- src/modulate (next-row scope) ------------------------------------------------------------------
 class AmDsbMod(Block):                                                # src/modulate/am.rs:10-120
     def __init__(self, fs, rf_hz, carrier_level, modulation_index):
         super().__init__(_mk("orion_b200_am_mod_create", fs, rf_hz, carrier_level, modulation_index))
@@ -601,6 +611,86 @@ class PmDirectPhaseMod(Block):                                        # src/modu
 
     def set_gain(self, g):
         _check(lib().orion_b200_mod_set_gain(self._h, g), self._h)
+
+
+class FmPhaseAccumMod(Block):                                         # src/modulate/fm.rs:11-75
+    def __init__(self, sample_rate, deviation_hz, rf_hz):
+        super().__init__(_mk("orion_b200_fm_mod_create", sample_rate, deviation_hz, rf_hz))
+
+    def set_deviation(self, deviation_hz):
+        _check(lib().orion_b200_fm_mod_set_deviation(self._h, deviation_hz), self._h)
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_mod_set_gain(self._h, g), self._h)
+
+
+class CwKeyedMod(Block):                                              # src/modulate/cw.rs:10-102
+    def __init__(self, sample_rate, tone_hz, rise_ms, fall_ms):
+        super().__init__(_mk("orion_b200_cw_mod_create", sample_rate, tone_hz, rise_ms, fall_ms))
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_mod_set_gain(self._h, g), self._h)
+
+
+class SsbPhasingMod(Block):                                           # src/modulate/ssb.rs:11-114
+    def __init__(self, fs, audio_bw_hz, audio_if_hz, rf_hz, usb):
+        super().__init__(_mk("orion_b200_ssb_mod_create", fs, audio_bw_hz, audio_if_hz, rf_hz, int(bool(usb))))
+
+
+# ---- src/demodulate/{bpsk,qpsk,qam}.rs (next-row scope): soft-symbol gain and hard-decision slicers -------------
+class _SymbolGain(Block):
+    def __init__(self, gain):
+        super().__init__(_mk("orion_b200_symbol_gain_create", gain))
+
+    def set_gain(self, g):
+        _check(lib().orion_b200_symbol_gain_set(self._h, g), self._h)
+
+
+class BpskDemod(_SymbolGain):                                         # src/demodulate/bpsk.rs:14-51
+    pass
+
+
+class QpskDemod(_SymbolGain):                                         # src/demodulate/qpsk.rs:13-50
+    pass
+
+
+class QamDemod(_SymbolGain):                                          # src/demodulate/qam.rs:44-82
+    pass
+
+
+class _Decider(Block):
+    bits = 1
+
+    def __init__(self):
+        super().__init__(_mk("orion_b200_decider_create", self.bits))
+
+
+class BpskDecider(_Decider):                                          # src/demodulate/bpsk.rs:54-88
+    bits = 1
+
+
+class QpskDecider(_Decider):                                          # src/demodulate/qpsk.rs:53-98
+    bits = 2
+
+
+class Qam16Decider(_Decider):                                         # src/demodulate/qam.rs:88-186
+    bits = 4
+
+
+class Qam64Decider(_Decider):
+    bits = 6
+
+
+class Qam256Decider(_Decider):
+    bits = 8
+
+
+def cfo_derotate(iq: np.ndarray, cfo_hz: float, fs: float) -> np.ndarray:
+    """Rotator::new(-cfo_hz, fs).rotate_block(iq, out) on the GPU (sync/ofdm_sync.rs:527-528)."""
+    iq = np.ascontiguousarray(iq, np.complex64)
+    out = np.empty_like(iq)
+    _check(lib().orion_b200_cfo_derotate(cfo_hz, fs, iq.ctypes.data if iq.size else None, out.ctypes.data if out.size else None, iq.size))
+    return out
 
 
 # ---- fused chain ----------------------------------------------------------------------------------
