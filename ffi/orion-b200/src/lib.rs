@@ -266,3 +266,66 @@ impl GpuChain {
         GpuBlock::from_create(|h| unsafe { sys::orion_b200_chain_create(&spec, h) }).map(Self)
     }
 }
+
+// ---- next-row blocks: AGC, the remaining modulators, symbol gain and deciders --------------------
+gpu_block!(/// `dsp::AgcRms` (agc.rs:8-75).
+    GpuAgcRms: f32 => f32);
+gpu_block!(/// `dsp::AgcRmsIq` (agc.rs:81-150).
+    GpuAgcRmsIq: C32 => C32);
+gpu_block!(/// `modulate::FmPhaseAccumMod` (modulate/fm.rs:11-75).
+    GpuFmPhaseAccumMod: f32 => C32);
+gpu_block!(/// `modulate::CwKeyedMod` (modulate/cw.rs:10-102).
+    GpuCwKeyedMod: f32 => C32);
+gpu_block!(/// `modulate::SsbPhasingMod` (modulate/ssb.rs:11-114).
+    GpuSsbPhasingMod: f32 => C32);
+gpu_block!(/// `BpskDemod` / `QpskDemod` / `QamDemod` (demodulate/{bpsk,qpsk,qam}.rs): soft symbols scaled by a gain.
+    GpuSymbolGain: C32 => C32);
+gpu_block!(/// `BpskDecider` / `QpskDecider` / `QamDecider<BITS>`: one hard-decision bit per output byte.
+    GpuDecider: C32 => u8);
+
+impl GpuAgcRms {
+    pub fn new(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_agc_rms_create(fs, attack_ms, release_ms, target_rms, h) }).map(Self)
+    }
+}
+impl GpuAgcRmsIq {
+    pub fn new(fs: f32, attack_ms: f32, release_ms: f32, target_rms: f32) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_agc_rms_iq_create(fs, attack_ms, release_ms, target_rms, h) }).map(Self)
+    }
+}
+impl GpuFmPhaseAccumMod {
+    pub fn new(sample_rate: f32, deviation_hz: f32, rf_hz: f32) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_fm_mod_create(sample_rate, deviation_hz, rf_hz, h) }).map(Self)
+    }
+    pub fn set_deviation(&mut self, deviation_hz: f32) { unsafe { sys::orion_b200_fm_mod_set_deviation(self.0.h, deviation_hz) }; }
+    pub fn set_gain(&mut self, g: f32) { unsafe { sys::orion_b200_mod_set_gain(self.0.h, g) }; }
+}
+impl GpuCwKeyedMod {
+    pub fn new(sample_rate: f32, tone_hz: f32, rise_ms: f32, fall_ms: f32) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_cw_mod_create(sample_rate, tone_hz, rise_ms, fall_ms, h) }).map(Self)
+    }
+    pub fn set_gain(&mut self, g: f32) { unsafe { sys::orion_b200_mod_set_gain(self.0.h, g) }; }
+}
+impl GpuSsbPhasingMod {
+    pub fn new(fs: f32, audio_bw_hz: f32, audio_if_hz: f32, rf_hz: f32, usb: bool) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_ssb_mod_create(fs, audio_bw_hz, audio_if_hz, rf_hz, usb as i32, h) }).map(Self)
+    }
+}
+impl GpuSymbolGain {
+    pub fn new(gain: f32) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_symbol_gain_create(gain, h) }).map(Self)
+    }
+    pub fn set_gain(&mut self, g: f32) { unsafe { sys::orion_b200_symbol_gain_set(self.0.h, g) }; }
+}
+impl GpuDecider {
+    /// bits per symbol: 1 BPSK, 2 QPSK, 4 / 6 / 8 QAM-16 / 64 / 256 (qam.rs:13-18)
+    pub fn new(bits_per_symbol: usize) -> Result<Self, Error> {
+        GpuBlock::from_create(|h| unsafe { sys::orion_b200_decider_create(bits_per_symbol as i32, h) }).map(Self)
+    }
+}
+/// `Rotator::new(-cfo_hz, fs).rotate_block(iq, out)` (sync/ofdm_sync.rs:527-528) in one call.
+pub fn cfo_derotate(iq: &[C32], out: &mut [C32], cfo_hz: f32, fs: f32) -> Result<(), Error> {
+    let n = iq.len().min(out.len());
+    let st = unsafe { sys::orion_b200_cfo_derotate(cfo_hz, fs, iq.as_ptr() as *const sys::orion_b200_c32, out.as_mut_ptr() as *mut sys::orion_b200_c32, n) };
+    if st == sys::ORION_B200_OK { Ok(()) } else { Err(status_to_error(st, ptr::null())) }
+}

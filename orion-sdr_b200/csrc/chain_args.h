@@ -139,6 +139,7 @@ struct ChainArgs {
     int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
     long long tma_row0;          // global row index of tensor-map row 0
     long long tma_rows;          // rows the tensor map covers
+    int   split;                 // FIR-only staged instance: warps that share the FIR of one tile (1, 2 or 4: slices of the tap rows)
     int   l2_prefetch;           // > 0: every fill also prefetches into L2 the tile this CTA stages that many fills later
     // demodulator
     int   demod;

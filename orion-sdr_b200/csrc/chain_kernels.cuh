@@ -563,9 +563,9 @@ DEV void lookback(const ChainArgs &a, const Hot *hot, int g, long long tile, int
 // Tiles are grouped in blocks of 32 and blocks in superblocks of 32 (1024 tiles).  Three kinds of records:
 //   * the zero-state aggregate of every tile (lk[t].agg, published by the tile's front),
 //   * B_b, the zero-state aggregate of block b = tiles 32b .. 32b+31: a function of that block's tile aggregates alone,
-//     formed by the warp that finishes the block's last tile from the window it reads anyway (lk[32b+31].incl),
+//     formed by the block's last tile right after it has published its own aggregate (slow_block_publish; lk[32b+31].incl),
 //   * SS_s, the TRUE state at the end of superblock s, chained SS_s = Ac^(1024T) SS_(s-1) + sum_i Ac^(32T(31-i)) B_(32s+i)
-//     by the warp that finishes the superblock's last tile (lk[1024s+1022].incl -- a slot no block uses).
+//     by the superblock's last tile at the same point (lk[1024s+1022].incl -- a slot no block uses).
 // The state at the start of tile t (block b, position j; b = 32s + jb) is then
 //   Ac^(Tj) [ Ac^(32T jb) SS_(s-1) + sum_(i<jb) Ac^(32T(jb-1-i)) B_(32s+i) ]  +  sum_(i<j) Ac^(T(j-1-i)) agg_(32b+i):
 // two windows and one record, all loads in flight together, and the only serial chain runs over superblocks
@@ -610,17 +610,6 @@ DEV void lookback_slow(const ChainArgs &a, const Hot *hot, int g, long long tile
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
             term1[d] = v;
         }
-    }
-    float Bb[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) Bb[d] = 0.f;
-    if (j == 31) {                                   // block-last tile: B_b = Ac^T (window sum) + own aggregate
-        float m[D * D];
-        load_mat<D>(T->tile, m);
-        matvec<D>(m, term1, Bb);
-#pragma unroll
-        for (int d = 0; d < D; ++d) Bb[d] += agg_own[d];
-        publish<D>(lane == 0, a, tile, g, Bb, true);
     }
     // ---- block level: lane l < jb reads B of block b-1-l; lane 31 reads SS of the previous superblock (or the carried state)
     float pb[D];
@@ -672,14 +661,102 @@ DEV void lookback_slow(const ChainArgs &a, const Hot *hot, int g, long long tile
 #pragma unroll
         for (int d = 0; d < D; ++d) sin[d] = t3[d] + term1[d];
     }
-    if (j == 31 && jb == 31) {                       // superblock-last tile: SS_s = Ac^(32T) base + B_b
-        float m[D * D], ss[D];
-        load_mat<D>(T->lbb[1], m);
-        matvec<D>(m, base, ss);
+    (void)agg_own;
+}
+
+// The block and superblock records of a slow-pole group are formed by the block's LAST tile right after it has published
+// its own aggregate -- in the same pipeline stage, i.e. a whole loop iteration before the tiles of the next block look for
+// them.  (Forming them in the finish stage, as a by-product of that tile's own look-back, made 32 tiles wait for one
+// warp that was running concurrently with them.)  Only this one warp per 32 tiles waits for concurrent publishes here.
+template <int D>
+DEV void slow_block_publish(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, const float (&agg_own)[D]) {
+    const GroupParam &G = hot->grp[g];
+    const GroupTables *T = a.gtabs + g;
+    const long long b = tile >> 5;
+    const int jb = (int)(b & 31);
+    const long long sb = b >> 5;
+    float pa[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) ss[d] += Bb[d];
-        publish<D>(lane == 0, a, sb * 1024 + 1022, g, ss, true);
+    for (int d = 0; d < D; ++d) pa[d] = 0.f;
+    const bool want1 = lane < 31;
+    {
+        const TileLink *lk = a.links + (want1 ? (tile - 1 - lane) : tile) * kMaxGroups + g;
+        int spins = 0;
+        for (;;) {
+            const bool ready = !want1 || read_link<D>(lk->agg, a.epoch, pa);
+            if (__all_sync(FULLMASK, ready)) break;
+            if (++spins > (1 << 21)) { if (lane == 0) atomicExch(a.err_flag, 11); break; }   // watchdog: never hang the device
+            __nanosleep(64);
+        }
     }
+    float Bb[D];
+    {
+        float t1[D], term1[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t1[d] = 0.f;
+        if (want1) {
+            float m[D * D];
+            load_mat<D>(T->lb[lane], m);
+            matvec<D>(m, pa, t1);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float v = t1[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+            term1[d] = v;
+        }
+        float m[D * D];
+        load_mat<D>(T->tile, m);
+        matvec<D>(m, term1, Bb);                     // B_b = Ac^T (sum over the 31 tiles before this one) + own aggregate
+#pragma unroll
+        for (int d = 0; d < D; ++d) Bb[d] += agg_own[d];
+    }
+    publish<D>(lane == 0, a, tile, g, Bb, true);
+    if (jb != 31) return;
+    // superblock-last tile: SS_s = Ac^(32T) [ Ac^(32T 31) SS_(s-1) + sum_(i<31) Ac^(32T(30-i)) B_(32s+i) ] + B_b
+    float pb[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pb[d] = 0.f;
+    const bool want2 = lane < 31, want_ss = lane == 31;
+    {
+        const long long rec_tile = want2 ? ((b - 1 - lane) * 32 + 31) : (sb > 0 ? (sb - 1) * 1024 + 1022 : tile);
+        const TileLink *lk = a.links + rec_tile * kMaxGroups + g;
+        int spins = 0;
+        for (;;) {
+            bool ready = true;
+            if (want2 || (want_ss && sb > 0)) ready = read_link<D>(lk->incl, a.epoch, pb);
+            if (__all_sync(FULLMASK, ready)) break;
+            if (++spins > (1 << 21)) { if (lane == 0) atomicExch(a.err_flag, 12); break; }
+            __nanosleep(64);
+        }
+        if (want_ss && sb == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 2) {
+                const float2 c = __ldcg(&a.carry_in->sec[G.first + d / 2]);
+                pb[d] = c.x; pb[d + 1] = c.y;
+            }
+        }
+    }
+    float base[D], t2[D];
+    {
+        float m[D * D];
+        load_mat<D>(T->lbb[want_ss ? 31 : lane], m);
+        matvec<D>(m, pb, t2);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float v = t2[d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+        base[d] = v;
+    }
+    float m[D * D], ss[D];
+    load_mat<D>(T->lbb[1], m);
+    matvec<D>(m, base, ss);
+#pragma unroll
+    for (int d = 0; d < D; ++d) ss[d] += Bb[d];
+    publish<D>(lane == 0, a, sb * 1024 + 1022, g, ss, true);
 }
 
 // one recursive-section step, reference arithmetic
@@ -745,6 +822,7 @@ DEV void group_front(const ChainArgs &a, const Hot *hot, int g, long long tile, 
             for (int d = 0; d < D; ++d) E[d] = fmaf(G.imp[i][d], u[i], E[d]);
     }
     group_scan<D>(a, hot, g, tile, lane, E, X, agg);
+    if (!G.agg_only && (tile & 31) == 31) slow_block_publish<D>(a, hot, g, tile, lane, agg);
 }
 // warp scan of the lanes' zero-state end states E with constant transition powers; publishes the tile aggregate
 template <int D>
@@ -982,8 +1060,11 @@ constexpr int kFirQUnroll = ORION_FIR_Q_UNROLL;
 #endif
 
 #if ORION_FIR_PACKED
+// rr0 .. rr1: the range of halo rows (tap steps rr*R .. rr*R + R - 1 of every pair) this call accumulates -- the whole
+// filter by default; a tile whose FIR is split over several warps (ChainArgs::split) gives each of them a slice.
 template <int R, int U, int SP, int QU>
-DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U]) {
+DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 *taps_sh, int lane, float2 (&z)[R * U],
+                    int rr0 = 0, int rr1 = -1) {
     typedef Geo<SP> GE;
     f32x2 acc[U][R];                                 // (re, im) of every output, one packed register pair each
 #pragma unroll
@@ -994,7 +1075,8 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
     const int Mb = GE::fixed ? GE::Mb : a.Mb, pitch = GE::fixed ? GE::pitch : a.row_pitch;
     const int P_pad = GE::fixed ? GE::P_pad : a.P_pad, HR = GE::fixed ? GE::HR : a.HR;
     const int blk_bytes = Mb * 8;
-    const unsigned char *row_own = smem + (size_t)lane * pitch;
+    if (rr1 < 0) rr1 = HR;
+    const unsigned char *row_own = smem + (size_t)(lane + rr0) * pitch;
     const int npairs = Mb >> 1;
 #pragma unroll QU
     for (int q = 0; q < npairs; ++q) {
@@ -1012,7 +1094,7 @@ DEV void fir_staged(const ChainArgs &a, const unsigned char *smem, const float2 
         const float2 *tp1 = ORION_TAPS + (size_t)(npairs + q) * P_pad;     // U == 2 only
         const unsigned char *rb = row_own + pitch + off_q;
 #pragma unroll (GE::fixed ? 2 : 1)
-        for (int rr = 0; rr < HR; ++rr, rb += pitch) {
+        for (int rr = rr0; rr < rr1; ++rr, rb += pitch) {
             // all loads of this row first (R LDS.128 + R*U broadcast LDS.64), then 2*R*R*U packed FMAs
             // in an order that touches every accumulator once per tap: dependent FMAs are R apart
             float2 t[U][R];
@@ -1422,6 +1504,7 @@ DEV void lr4_front_park(const ChainArgs &a, const Hot *hot, long long tile, int 
     float X[4], agg[4];
     __syncwarp();
     group_scan<4>(a, hot, 0, tile, lane, E, X, agg);
+    if (!hot->grp[0].agg_only && (tile & 31) == 31) slow_block_publish<4>(a, hot, 0, tile, lane, agg);
     *reinterpret_cast<float4 *>(park + lane * kMaxGroupDim) = make_float4(X[0], X[1], X[2], X[3]);
     if (lane == 0) *reinterpret_cast<float4 *>(park + 32 * kMaxGroupDim) = make_float4(agg[0], agg[1], agg[2], agg[3]);
     __syncwarp();
@@ -1634,6 +1717,8 @@ struct __align__(16) RingCtl {
     int gen[kMaxStages];                     // index of the slot's latest fill (use k may only look at fill k)
     unsigned int cons;                       // consume counter of the CTA
     unsigned int done;                       // warps of the CTA that have run out of tiles
+    int pgen[kMaxStages][3];                 // tap-split FIR: fill index for which partial sum q of the slot's tile is in place
+    int lgen[kMaxStages];                    // ... and for which an edge tile has been loaded cooperatively (by sub-warp 0)
 };
 
 // The kernel.  Tiles are assigned statically and round-robin: CTA b owns tiles b, b+G, b+2G, ...
@@ -1707,7 +1792,10 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     // are already in flight from HBM while the CTA sets itself up.
     if (FRONT == FRONT_STAGED) {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&ring.full[s]), 1); ring.gen[s] = -1; }
+            for (int s = 0; s < NS; ++s) {
+                mbar_init(smem_u32(&ring.full[s]), 1); ring.gen[s] = -1; ring.lgen[s] = -1;
+                ring.pgen[s][0] = ring.pgen[s][1] = ring.pgen[s][2] = -1;
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -1741,6 +1829,8 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     Lr4Tabs *tabs_sh = reinterpret_cast<Lr4Tabs *>(reinterpret_cast<unsigned char *>(hot_sh) + ((sizeof(Hot) + 15) & ~(size_t)15));
     // rate-1 blocks: per-warp transposing scratch behind the tables
     unsigned char *xs = (FRONT == FRONT_DIRECT) ? reinterpret_cast<unsigned char *>(tabs_sh + 1) + (size_t)wid * kXposeBytes : nullptr;
+    // tap-split FIR: three partial-sum buffers per ring slot, behind the tables
+    unsigned char *part_sh = reinterpret_cast<unsigned char *>(tabs_sh + 1);
     if (Dm<DM>::lr4) {
         const float *src_l = &a.gtabs->lane[0][0], *src_b = &a.gtabs->lb[0][0];
         for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
@@ -1798,6 +1888,11 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     for (;;) {
         unsigned c = atom_add_shared_pred(lane == 0, smem_u32(&ring.cons), 1u);
         c = __shfl_sync(FULLMASK, c, 0);
+        // tap-split FIR (long filters, FIR-only instance): `split` consecutive tickets share one tile, each takes a slice of
+        // the tap rows; the last one adds the partial sums (fixed order) and goes on with the tile
+        const int split = (FRONT == FRONT_STAGED && DM == DEMOD_NONE) ? a.split : 1;
+        const int sub = (split > 1) ? (int)(c % (unsigned)split) : 0;
+        if (split > 1) c /= (unsigned)split;
         const long long tile = cta + G * (long long)c;
         if (tile >= a.ntiles) break;
         // the first tiles read what the previous call carried over (FIR history, discriminator `prev`, section
@@ -1844,11 +1939,61 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         const long long jt = j0 + (long long)lane * NPT;
 
         if (FRONT == FRONT_STAGED) {
+            if (split > 1) {
+                if (!tile_is_interior(a, tile)) {                 // edge tile: sub-warp 0 loads it, the others wait for that
+                    if (sub == 0) {
+                        stage_load_generic(a, tile, stage, lane);
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) *reinterpret_cast<volatile int *>(&ring.lgen[s]) = k;
+                    } else {
+                        int spins = 0;
+                        while (*reinterpret_cast<volatile int *>(&ring.lgen[s]) != k) {
+                            if (++spins > (1 << 22)) { atomicExch(a.err_flag, 13); break; }
+                            __nanosleep(64);
+                        }
+                        __threadfence_block();
+                    }
+                    __syncwarp();
+                }
+                const int rows = HRc / split;
+                fir_staged<R, U, SP, kFirQUnroll>(a, stage, taps_sh, lane, z, sub * rows, sub * rows + rows);
+                float2 *part = reinterpret_cast<float2 *>(part_sh + ((size_t)s * 3) * (kThreads * NPT * sizeof(float2)));
+                if (sub < split - 1) {                            // a partial sum: park it, announce it, take the next ticket
+                    float2 *mine = part + (size_t)sub * (kThreads * NPT);
+#pragma unroll
+                    for (int i = 0; i < NPT; ++i) mine[i * kThreads + lane] = z[i];
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile int *>(&ring.pgen[s][sub]) = k;
+                    continue;
+                }
+                for (int q = 0; q < split - 1; ++q) {             // the last slice: add the others in a fixed order
+                    int spins = 0;
+                    while (*reinterpret_cast<volatile int *>(&ring.pgen[s][q]) != k) {
+                        if (++spins > (1 << 22)) { atomicExch(a.err_flag, 14); break; }
+                        __nanosleep(64);
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                {
+                    float2 sum[NPT];
+#pragma unroll
+                    for (int i = 0; i < NPT; ++i) sum[i] = part[i * kThreads + lane];
+                    for (int q = 1; q < split - 1; ++q)
+#pragma unroll
+                        for (int i = 0; i < NPT; ++i) sum[i] = add2(sum[i], part[(size_t)q * (kThreads * NPT) + i * kThreads + lane]);
+#pragma unroll
+                    for (int i = 0; i < NPT; ++i) z[i] = add2(sum[i], z[i]);
+                }
+            } else {
             if (!tile_is_interior(a, tile)) stage_load_generic(a, tile, stage, lane);
             if (a.mix != MIX_NONE) stage_mix(a, tile, stage, lane);
             // the FIR-only instance affords the fully unrolled pair loop (loads hoisted across pairs); with a post phase
             // behind it the smaller rolled body wins (instruction cache)
             fir_staged<R, U, SP, (SP == 1 && DM == DEMOD_NONE) ? 4 : kFirQUnroll>(a, stage, taps_sh, lane, z);
+            }
             if (need_prev && j0 > 0) zhalo = fir_staged_one(a, stage, g_sh, tile * kThreads - HRc, j0 - 1, lane);
             __syncwarp();                               // every lane is done with the slot: refill it
             stamp(tile, 2);
@@ -1898,7 +2043,9 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
             // multi-group chain: pipeline of depth S = ngroups (stage_step)
             const int S = a.ngroups;
             group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[pipe_it % (S + 1)]);
-            for (int k = S; k >= 1; --k) {
+            // youngest first: a stage that only publishes (k small) must never sit behind a stage that may wait for the
+            // records of older tiles -- otherwise the block records of a slow-pole group chain through those waits
+            for (int k = 1; k <= S; ++k) {
                 if (pipe_it - k < 0) continue;
                 const int e = (pipe_it - k) % S;
                 const long long t = qtile[e];
@@ -1937,7 +2084,7 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     if (!Dm<DM>::lr4 && a.pipe_u_slots > 0 && pipe_it > 0) {           // drain the multi-group pipeline
         const int S = a.ngroups;
         for (int j = pipe_it; j < pipe_it + S; ++j)
-            for (int k = S; k >= 1; --k) {
+            for (int k = 1; k <= S; ++k) {
                 const int en = j - k;                                    // entry iteration of the tile at stage k
                 if (en < 0 || en >= pipe_it) continue;
                 const int e = en % S;

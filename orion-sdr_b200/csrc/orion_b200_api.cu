@@ -643,6 +643,7 @@ struct orion_b200_block {
     int ctas_per_sm = 1, sm_count = 1;
     int ws = 0;                           // the warp-specialised instance is selected
     int pipe_park_slots = 2, pipe_u_slots = 0;   // per-warp pipeline area of the chain kernel (multi-group chains)
+    int split = 1;                        // warps that share the FIR of one tile (FIR-only staged instance, long filters)
     // ---- options ----
     int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0, opt_overlap = 0;
     long long *trace = nullptr;           // debug: device buffer of 8 x int64 per tile
@@ -754,8 +755,18 @@ int finalize_plan(orion_b200_block *b) {
     }
     const size_t warp_pipe = 16 + (size_t)b->pipe_park_slots * 33 * kMaxGroupDim * sizeof(float) +
                              (size_t)b->pipe_u_slots * kThreads * npt_of(b) * sizeof(float);
+    // long filters on the FIR-only staged instance: several warps share the FIR of one tile (slices of the tap rows), so
+    // that more than one warp per ring slot does arithmetic (the 1023-tap /32 shape fits only four 41.6 KB slots)
+    b->split = 1;
+    if (b->plan.front == FRONT_STAGED && b->demod == DEMOD_NONE && b->mix == MIX_NONE && b->nbatch == 1 && b->plan.HR >= 4 && !b->opt_serial)
+        b->split = (b->plan.HR % 4 == 0) ? 4 : ((b->plan.HR % 2 == 0) ? 2 : 1);
+    if (const char *e = getenv("ORION_B200_SPLIT")) {
+        const int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4) && b->plan.front == FRONT_STAGED && b->demod == DEMOD_NONE && b->mix == MIX_NONE && b->plan.HR % v == 0) b->split = v;
+    }
+    const size_t part_bytes = b->split > 1 ? (size_t)3 * kThreads * npt_of(b) * sizeof(float2) : 0;     // per ring slot
     auto rest_of = [&](int warps) {
-        return (size_t)warps * warp_pipe + b->plan.taps2.size() * sizeof(float2) +
+        return (size_t)warps * warp_pipe + (size_t)b->plan.nstages * part_bytes + b->plan.taps2.size() * sizeof(float2) +
                ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +
                sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +
                (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +
@@ -772,6 +783,7 @@ int finalize_plan(orion_b200_block *b) {
                        ((b->plan.g.size() * sizeof(float) + 15) & ~(size_t)15) +            // + generic taps
                        sizeof(GroupParam) * kMaxGroups + sizeof(SecParam) * kMaxSections + 32 +  // + section/group data
                        (2 * 32 * 16 + kMaxNpt * 4) * sizeof(float) +                             // + per-lane scan tables (LR4 instance)
+                       (size_t)b->plan.nstages * part_bytes +                                    // + partial sums of the tap-split FIR
                        (b->plan.front == FRONT_DIRECT ? (size_t)b->plan.warps * 32 * 144 + 16 : 0);  // + transposing scratch (rate-1 blocks)
     // FIR /8 + FM | PM + LR4 (the C1 chain): the warp-specialised instance (chain_inst_ws.cu) is an experiment, selected with
     // ORION_B200_WS=1 only -- measured 4-7 % SLOWER than the unified kernel on B200 (profiles/r02_experiments.txt)
@@ -1211,6 +1223,7 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
     a.ngroups = (int)b->groups.size();
     a.pipe_park_slots = b->pipe_park_slots; a.pipe_u_slots = b->pipe_u_slots;
+    a.split = b->opt_serial ? 1 : b->split;
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;
     a.carry_in = b->d_carry[b->pp]; a.carry_out = b->d_carry[(b->pp + 1) % 3];
@@ -2238,7 +2251,9 @@ int orion_b200_block_process(orion_b200_block *b, const void *in, size_t n_in, v
     size_t chunk = 0;
     if (whole_output && !getenv("ORION_B200_NO_PIPELINE")) {
         const size_t unit = M * (size_t)kThreads * (size_t)npt_of(b);       // input items of one warp tile
-        size_t want = (size_t)(4u << 20) / in_item_bytes(b);                // ~4 MB of input per chunk ...
+        // ~4 MB of input per chunk from pinned memory; 16 MB when the caller's buffer is pageable (every chunk is one job
+        // of the copy pool, whose wake-up cost is amortised over the chunk) ...
+        size_t want = (size_t)((is_pageable(in) ? 16u : 4u) << 20) / in_item_bytes(b);
         if (const char *e = getenv("ORION_B200_PIPE_CHUNK_BYTES")) want = std::max<size_t>(1, (size_t)atoll(e) / in_item_bytes(b));
         want = std::max(want, consume / 64 + 1);                            // ... but at most ~64 chunks
         chunk = std::max<size_t>(1, (want + unit - 1) / unit) * unit;
