@@ -1591,10 +1591,7 @@ DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int
                          unsigned char *xs = nullptr) {
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
     const bool full = jt + NPT <= a.n_out;
-    if (a.ngroups > 0) {
-        group_finish_parked<NPT>(a, hot, 0, tile, lane, u, full, jt, park);
-        for (int g = 1; g < a.ngroups; ++g) group_whole<NPT>(a, hot, g, tile, lane, u, full, jt);
-    }
+    if (a.ngroups > 0) group_finish_parked<NPT>(a, hot, 0, tile, lane, u, full, jt, park);      // (chains with more groups: stage_step)
     store_f32<NPT>(a, tile, lane, u, xs);
 }
 
@@ -1606,6 +1603,7 @@ DEV void finish_sections(const ChainArgs &a, const Hot *hot, long long tile, int
 // finish back to back, so each tile waited for aggregates its 31 predecessors were publishing at that very moment:
 // the AM chain of BASELINE config 3 spent 56 % of its stall samples polling link records.)  The items of the tiles in
 // flight live in shared memory between stages (item-major, conflict free).
+// (inlined at both call sites on purpose: as a called function it cost 40 % on the AM chain -- 295 -> 415 us)
 template <int NPT>
 DEV void stage_step(const ChainArgs &a, const Hot *hot, int k, int S, long long tile, int lane, float *us, float *park,
                     unsigned char *xs) {

@@ -299,13 +299,16 @@ struct ExactOsc {
     std::vector<float2> recent;               // the phasors applied to the most recent items (oldest first), for the FIR history
     size_t keep = 0;                          // how many of them to keep
     // device side
-    OscAnchor *h_an = nullptr;                // pinned staging
+    OscAnchor *h_an2[2] = { nullptr, nullptr };   // pinned staging, two sets: the host prepares call N+1 while call N's upload is in flight
+    OscAnchor *h_an = nullptr;                // the set in use
     OscAnchor *d_an = nullptr;
     size_t an_cap = 0;
     float2 *d_fine = nullptr, *d_hist = nullptr;
     size_t fine_cap = 0, hist_cap = 0;
+    float2 *h_hist2[2] = { nullptr, nullptr };
     float2 *h_hist = nullptr;
-    cudaEvent_t staged = nullptr;             // the last upload from the pinned staging buffers has completed
+    cudaEvent_t staged2[2] = { nullptr, nullptr };   // the last upload from staging set i has completed
+    int sbuf = 0;
 
     // Look-ahead: anc[i] = Z(origin_ctr + 1024 i).  The sequence does not depend on the data, so it may be walked any
     // distance ahead of the items consumed so far (orion_b200_block_prepare_oscillator); a call only copies the anchors
@@ -368,11 +371,14 @@ struct ExactOsc {
         }
     }
     void free_device() {
-        if (h_an) cudaFreeHost(h_an);
-        if (h_hist) cudaFreeHost(h_hist);
+        for (int i = 0; i < 2; ++i) {
+            if (h_an2[i]) cudaFreeHost(h_an2[i]);
+            if (h_hist2[i]) cudaFreeHost(h_hist2[i]);
+            if (staged2[i]) cudaEventDestroy(staged2[i]);
+            h_an2[i] = nullptr; h_hist2[i] = nullptr; staged2[i] = nullptr;
+        }
         cudaFree(d_an); cudaFree(d_fine); cudaFree(d_hist);
-        if (staged) cudaEventDestroy(staged);
-        h_an = nullptr; h_hist = nullptr; d_an = nullptr; d_fine = nullptr; d_hist = nullptr; staged = nullptr;
+        h_an = nullptr; h_hist = nullptr; d_an = nullptr; d_fine = nullptr; d_hist = nullptr;
         an_cap = fine_cap = hist_cap = 0;
     }
 };
@@ -975,15 +981,16 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     const size_t n_an = (n_items + 1023) / 1024 + 2;      // capacity: the consumed state + one per 1024-grid point
     size_t n_an_used = 0;
     const long long fine_len = (long long)((n_items - 1) >> 4) + 1;
-    if (!x.staged) CK(cudaEventCreateWithFlags(&x.staged, cudaEventDisableTiming));
-    else CK(cudaEventSynchronize(x.staged));               // the pinned staging buffers are free again
+    x.sbuf ^= 1;                                               // staging set of this call; its previous upload (two calls ago) must be done
+    if (!x.staged2[x.sbuf]) CK(cudaEventCreateWithFlags(&x.staged2[x.sbuf], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(x.staged2[x.sbuf]));
     if (n_an > x.an_cap) {
         CK(cudaStreamSynchronize(b->stream));
-        if (x.h_an) cudaFreeHost(x.h_an);
+        for (int i = 0; i < 2; ++i) { if (x.h_an2[i]) cudaFreeHost(x.h_an2[i]); x.h_an2[i] = nullptr; }
         cudaFree(x.d_an);
-        x.h_an = nullptr; x.d_an = nullptr;
+        x.d_an = nullptr;
         const size_t cap = n_an + n_an / 4 + 16;
-        CK(cudaMallocHost(&x.h_an, cap * sizeof(OscAnchor)));
+        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&x.h_an2[i], cap * sizeof(OscAnchor)));
         CK(cudaMalloc(&x.d_an, cap * sizeof(OscAnchor)));
         x.an_cap = cap;
     }
@@ -996,13 +1003,15 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     }
     if (hist_len > x.hist_cap) {
         CK(cudaStreamSynchronize(b->stream));
-        if (x.h_hist) cudaFreeHost(x.h_hist);
+        for (int i = 0; i < 2; ++i) { if (x.h_hist2[i]) cudaFreeHost(x.h_hist2[i]); x.h_hist2[i] = nullptr; }
         cudaFree(x.d_hist);
-        x.h_hist = nullptr; x.d_hist = nullptr;
-        CK(cudaMallocHost(&x.h_hist, hist_len * sizeof(float2)));
+        x.d_hist = nullptr;
+        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&x.h_hist2[i], hist_len * sizeof(float2)));
         CK(cudaMalloc(&x.d_hist, hist_len * sizeof(float2)));
         x.hist_cap = hist_len;
     }
+    x.h_an = x.h_an2[x.sbuf];
+    x.h_hist = x.h_hist2[x.sbuf];
     // phasors of the items before this call (newest last)
     const size_t nh = std::min(x.recent.size(), hist_len);
     for (size_t i = 0; i < nh; ++i) x.h_hist[i] = x.recent[x.recent.size() - nh + i];
@@ -1047,7 +1056,7 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     x.consume_to(ctr0 + (unsigned long long)n_items);
     CK(cudaMemcpyAsync(x.d_an, x.h_an, n_an_used * sizeof(OscAnchor), cudaMemcpyHostToDevice, b->stream));
     if (nh) CK(cudaMemcpyAsync(x.d_hist, x.h_hist, nh * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaEventRecord(x.staged, b->stream));
+    CK(cudaEventRecord(x.staged2[x.sbuf], b->stream));
     CK(osc_expand_launch(x.d_an, (int)n_an_used, x.d_fine, ctr0 + 1ull, fine_len, b->stream));
     b->launches += 1;
     np->exact = 1;
@@ -1940,6 +1949,8 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     a.BT = std::max(k->PM, std::max(1, 2048 / (int)M));               // 16 KB tiles (16 blocks of 128 samples)
     const int nwc = bank_fir_consumer_warps((int)k->nch);
     a.NS = nwc > 4 ? 4 : 3;                                            // small CTAs: smaller rings, more CTAs per SM
+    if (const char *e = getenv("ORION_B200_BANK_BT")) a.BT = std::max(k->PM, atoi(e));       // experiments
+    if (const char *e = getenv("ORION_B200_BANK_NS")) a.NS = std::max(2, std::min(6, atoi(e)));
     a.gt = k->d_gt; a.g0 = k->g[0];
     a.z = k->d_z; a.z_stride = (long long)n_out_all; a.nch = (int)k->nch;
     a.tiles_total = ((long long)n_out_all + a.BT - 1) / a.BT;

@@ -133,3 +133,32 @@ def test_sharded_banks_cover_the_full_bank():
     full = ob.ChannelBank(specs).process(x)
     parts = [ob.ChannelBank(specs, channels=ob.shard_range(CFG["n_channels"], r, 3)).process(x) for r in range(3)]
     np.testing.assert_array_equal(np.concatenate(parts, axis=0), full)        # same kernels, same inputs: bit-equal
+
+
+@pytest.mark.gpu
+def test_bank_runs_on_a_caller_stream():
+    import torch
+    import orion_b200 as ob
+    from signals import c5_specs
+    cfg = dict(fs=8.192e6, m=128, n_channels=64, spacing_hz=8e3, cutoff_hz=3.5e3, trans_hz=16e3)
+    n = 262_144
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = 0.1 * torch.complex(torch.randn(n, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g))
+    a, b = ob.ChannelBank(c5_specs(ob, **cfg)), ob.ChannelBank(c5_specs(ob, **cfg))
+    n_out = n // cfg["m"]
+    ya = torch.zeros((64, n_out), dtype=torch.float32, device="cuda")
+    yb = torch.zeros_like(ya)
+    torch.cuda.synchronize()
+    a.process_dev(x.data_ptr(), n, ya.data_ptr(), n_out)
+    a.synchronize()
+    st = torch.cuda.Stream()
+    b.set_stream(st.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    b.process_dev(x.data_ptr(), n, yb.data_ptr(), n_out)
+    e1.record(st)
+    e1.synchronize()                                           # stream order alone: the outputs are complete
+    assert e0.elapsed_time(e1) > 0.0
+    assert torch.equal(ya, yb)
+    b.set_stream(0)
+    b.synchronize()

@@ -637,3 +637,48 @@ def test_first_long_launch_is_ordered_after_the_blocks_own_initialisation():
     dec = oracle.FirDecimator(fs, m, 100e3, 38400.0)
     fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
     assert_parity(head, fm.run(dec.run(x[:200_000].cpu().numpy())), what="head of the first long call")
+
+
+# ---- round-2 host-side features -----------------------------------------------------------------------------------
+def test_prepare_oscillator_walks_ahead_without_changing_results():
+    """orion_b200_block_prepare_oscillator: the exact-replay walk done ahead of the stream; process() then only copies anchors."""
+    fs, n, calls = 2.4e6, 300_000, 3
+    x = noise_c64(n * calls, seed=77)
+    a, b = ob.Rotator(1e5, fs), ob.Rotator(1e5, fs)
+    b.prepare_oscillator(n, calls)
+    walked = b.exact_host_ms
+    assert walked > 0.0
+    ya = np.concatenate([a.run(x[i * n:(i + 1) * n]) for i in range(calls)])
+    yb = np.concatenate([b.run(x[i * n:(i + 1) * n]) for i in range(calls)])
+    assert bit_equal(ya, yb)
+    assert b.exact_host_ms - walked < 0.5 * max(a.exact_host_ms, 1e-3) + 0.2     # nothing left to walk inside the calls
+    ref = oracle.Rotator(1e5, fs).run(x)
+    assert bit_equal(ya, ref)
+
+
+@pytest.mark.parametrize("pageable", [True, False])
+def test_pipelined_host_call_matches_the_oracle(pageable):
+    """Host-pointer calls longer than two chunks are pipelined (copy in / kernel / copy out overlap); pageable caller
+    buffers go through the pinned staging ring.  WorkReport and values as for one launch."""
+    import torch
+    fs, m = 2.4e6, 8
+    n = 5_000_003                                              # ragged: the last chunk is short and not a multiple of m
+    x = fm_iq(n, fs)
+    taps = ob.fir_lowpass_design(fs, 100e3, 38400.0)
+    ch = ob.Chain(fir=ob.FIR_DECIM, taps=taps, decim=m, demod=ob.DEMOD_FM, fs_demod=fs / m, p0=25e3,
+                  audio_bw_hz=15e3, translate_hz=100e3)
+    n_out = -(-n // m)
+    if pageable:
+        xin, out = x, np.zeros(n_out, np.float32)
+    else:
+        xin = torch.from_numpy(x).pin_memory().numpy()
+        out = torch.zeros(n_out, dtype=torch.float32).pin_memory().numpy()
+    wr = ch.process(xin, out)
+    assert tuple(wr) == (n, n_out)
+    dec = oracle.FirDecimator(fs, m, 100e3, 38400.0)
+    fm = oracle.FmQuadratureDemod(fs / m, 25e3, 15e3).with_translate(100e3)
+    assert_parity(out, fm.run(dec.run(x)), what=f"pipelined host call, pageable={pageable}")
+    # a rate-1 block with an exact oscillator through the same path: still bit for bit
+    r = ob.Rotator(-2.5e5, 1.2e6)
+    xr = noise_c64(3_000_001, seed=5)
+    assert bit_equal(r.run(xr), oracle.Rotator(-2.5e5, 1.2e6).run(xr))
