@@ -57,6 +57,8 @@ struct GroupParam {
     int   first, count;      // sections [first, first + count)
     int   D;                 // 2 * count
     int   agg_only;          // depth <= 32: predecessors' aggregates alone determine the start state
+    int   scan_levels;       // warp-scan levels whose transition power is not negligible (<= 5)
+    int   pad_[3];
     float imp[kMaxNpt][kMaxGroupDim];                  // Ac^(n-1-i) Bc: zero-state end state = sum_i imp[i] * u[i]
     float lv[5][kMaxGroupDim * kMaxGroupDim];          // Ac^(n*2^l), l = 0..4, row-major D x D (stride D)
 };
@@ -139,6 +141,8 @@ struct ChainArgs {
     int   use_tma;               // interior tiles are staged with one cp.async.bulk.tensor
     long long tma_row0;          // global row index of tensor-map row 0
     long long tma_rows;          // rows the tensor map covers
+    long long tile_int_lo, tile_int_hi;   // tiles in [lo, hi] are staged by TMA (interior); lo > hi: none
+    unsigned int ns_magic;       // ceil(2^32 / nstages): ticket / nstages by multiplication
     int   split;                 // FIR-only staged instance: warps that share the FIR of one tile (1, 2 or 4: slices of the tap rows)
     int   l2_prefetch;           // > 0: every fill also prefetches into L2 the tile this CTA stages that many fills later
     // demodulator

@@ -404,6 +404,14 @@ DEV void matvec(const float *__restrict__ M, const float (&v)[D], float (&out)[D
         out[r] = acc;
     }
 }
+// A cascade's transition matrix is block lower-triangular in the state order (s^0, s^1): section 0 never sees section 1,
+// and every power keeps that shape -- the upper-right 2x2 block of a D = 4 power is exactly zero.  12 FMAs instead of 16.
+DEV void matvec4_tri(const float *__restrict__ M, const float (&v)[4], float (&out)[4]) {
+    out[0] = fmaf(M[1], v[1], fmaf(M[0], v[0], 0.f));          // the same operation sequence as matvec<4>, minus the exact zeros
+    out[1] = fmaf(M[5], v[1], fmaf(M[4], v[0], 0.f));
+    out[2] = fmaf(M[11], v[3], fmaf(M[10], v[2], fmaf(M[9], v[1], fmaf(M[8], v[0], 0.f))));
+    out[3] = fmaf(M[15], v[3], fmaf(M[14], v[2], fmaf(M[13], v[1], fmaf(M[12], v[0], 0.f))));
+}
 template <int D>
 DEV void load_mat(const float *__restrict__ g, float (&M)[D * D]) {      // D*D floats, 16-byte aligned
 #pragma unroll
@@ -802,7 +810,7 @@ DEV void sec_pass2(const ChainArgs &a, const SecParam &P, int s, float (&u)[NPT]
     }
 }
 
-template <int D>
+template <int D, bool TRI = false>
 DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&E)[D], float (&X)[D], float (&agg)[D]);
 // group front: zero-state end state of this lane's chunk (dot products with the impulse
 // responses), warp scan with constant transition powers, publish the tile aggregate.
@@ -825,7 +833,7 @@ DEV void group_front(const ChainArgs &a, const Hot *hot, int g, long long tile, 
     if (!G.agg_only && (tile & 31) == 31) slow_block_publish<D>(a, hot, g, tile, lane, agg);
 }
 // warp scan of the lanes' zero-state end states E with constant transition powers; publishes the tile aggregate
-template <int D>
+template <int D, bool TRI>
 DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, int lane, float (&E)[D], float (&X)[D], float (&agg)[D]) {
     const GroupParam &G = hot->grp[g];
     if ((ORION_TRACE && a.trace) && g == 0) {
@@ -836,10 +844,14 @@ DEV void group_scan(const ChainArgs &a, const Hot *hot, int g, long long tile, i
     __syncwarp();                                  // converged here: the shuffles below take the fast path
 #pragma unroll
     for (int l = 0; l < 5; ++l) {
+        // levels whose transition power Ac^(n 2^l) is below 2^-40 in every entry cannot change an f32 state sum: skipped
+        // (warp-uniform; for the C1 LR4 that is the last level)
+        if (l >= G.scan_levels) break;
         float o[D], t[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) o[d] = __shfl_up_sync(FULLMASK, E[d], 1 << l);
-        matvec<D>(G.lv[l], o, t);
+        if constexpr (TRI && D == 4) matvec4_tri(G.lv[l], o, t);
+        else matvec<D>(G.lv[l], o, t);
         const bool take = lane >= (1 << l);        // select, not a branch: the warp stays converged
 #pragma unroll
         for (int d = 0; d < D; ++d) E[d] += take ? t[d] : 0.f;
@@ -929,8 +941,8 @@ DEV long long row_start_sample(const ChainArgs &a, long long G) {
     return (long long)a.row_samples * G + (a.O - a.Mb + 2);
 }
 DEV bool tile_is_interior(const ChainArgs &a, long long tile) {
-    const long long G0 = tile * kThreads - a.HR;
-    return a.use_tma && G0 >= a.tma_row0 && (G0 + kThreads + a.HR) <= (a.tma_row0 + a.tma_rows);
+    // the host's form of: use_tma && G0 >= tma_row0 && G0 + 32 + HR <= tma_row0 + tma_rows, G0 = 32 tile - HR
+    return tile >= a.tile_int_lo && tile <= a.tile_int_hi;
 }
 
 // cooperative (whole warp) load of an edge tile -- FIR history / ragged tail -- into the staged layout.
@@ -1503,7 +1515,7 @@ template <int NPT>
 DEV void lr4_front_park(const ChainArgs &a, const Hot *hot, long long tile, int lane, float (&E)[4], float *park) {
     float X[4], agg[4];
     __syncwarp();
-    group_scan<4>(a, hot, 0, tile, lane, E, X, agg);
+    group_scan<4, true>(a, hot, 0, tile, lane, E, X, agg);     // the LR4 instance: always two cascaded biquads
     if (!hot->grp[0].agg_only && (tile & 31) == 31) slow_block_publish<4>(a, hot, 0, tile, lane, agg);
     *reinterpret_cast<float4 *>(park + lane * kMaxGroupDim) = make_float4(X[0], X[1], X[2], X[3]);
     if (lane == 0) *reinterpret_cast<float4 *>(park + 32 * kMaxGroupDim) = make_float4(agg[0], agg[1], agg[2], agg[3]);
@@ -1538,7 +1550,7 @@ DEV void lr4_lookback_short(const ChainArgs &a, const Lr4Tabs *tabs, long long t
     if (want) {
         float m[16];
         load_mat4_sh(tabs->lb[lane], m);
-        matvec<4>(m, pay, term);
+        matvec4_tri(m, pay, term);
     }
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
@@ -1566,7 +1578,7 @@ DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *ta
     }
     float lm[16], st[4];
     load_mat4_sh(tabs->lane[lane], lm);
-    matvec<4>(lm, sin, st);
+    matvec4_tri(lm, sin, st);
     st[0] += xv.x; st[1] += xv.y; st[2] += xv.z; st[3] += xv.w;
     // the reference recursion, sample by sample through both sections (iir.rs:78-83); items past the end of the
     // call are computed from zero-padded input and never stored, the carried state is taken at the last real one
@@ -1889,8 +1901,8 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         // tap-split FIR (long filters, FIR-only instance): `split` consecutive tickets share one tile, each takes a slice of
         // the tap rows; the last one adds the partial sums (fixed order) and goes on with the tile
         const int split = (FRONT == FRONT_STAGED && DM == DEMOD_NONE) ? a.split : 1;
-        const int sub = (split > 1) ? (int)(c % (unsigned)split) : 0;
-        if (split > 1) c /= (unsigned)split;
+        const int sub = (int)(c & (unsigned)(split - 1));           // split is 1, 2 or 4
+        c >>= (split >> 1);
         const long long tile = cta + G * (long long)c;
         if (tile >= a.ntiles) break;
         // the first tiles read what the previous call carried over (FIR history, discriminator `prev`, section
@@ -1906,8 +1918,9 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         int s = 0, k = 0;
         unsigned char *stage = smem;
         if (FRONT == FRONT_STAGED) {
-            s = (int)(c % (unsigned)NS);
-            k = (int)(c / (unsigned)NS);
+            // c / NS by multiplication with ceil(2^32 / NS): exact while c * NS < 2^32 (tickets of one CTA)
+            k = (NS > 1 && c < (1u << 27)) ? (int)__umulhi(c, a.ns_magic) : (int)(c / (unsigned)NS);   // (NS = 1: the magic number would be 2^32)
+            s = (int)(c - (unsigned)k * (unsigned)NS);
             const uint32_t bar = smem_u32(&ring.full[s]);
             // Use k of the slot waits for fill k: first on the mbarrier phase (a hardware-suspended wait, no
             // polling traffic), then ONE look at the fill index -- a warp more than one lap ahead of the

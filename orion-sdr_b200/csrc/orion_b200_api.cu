@@ -261,6 +261,14 @@ void build_group(const SecParam *secs, const GroupHost &gh, int npt, GroupParam 
         }
     }
     for (int l = 0; l < 5; ++l) mat_store(mat_pow(A, n << l, D), gp->lv[l]);
+    gp->scan_levels = 5;
+    while (gp->scan_levels > 1) {                      // trailing levels whose power is below 2^-40 everywhere
+        const Mat P = mat_pow(A, n << (gp->scan_levels - 1), D);
+        double mx = 0.0;
+        for (double v : P) mx = std::max(mx, std::fabs(v));
+        if (mx >= 9.094947017729282e-13) break;
+        gp->scan_levels -= 1;
+    }
     for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, n * k, D), gt->lane[k]);
     for (int k = 0; k < 32; ++k) mat_store(mat_pow(A, T * k, D), gt->lb[k]);
     mat_store(mat_pow(A, T * 32ull, D), gt->lb32);
@@ -1257,6 +1265,8 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
+    a.tile_int_lo = 1; a.tile_int_hi = 0;              // no interior tiles unless a tensor map is set up below
+    a.ns_magic = (unsigned)(((1ull << 32) + (unsigned long long)std::max(a.nstages, 1) - 1) / (unsigned long long)std::max(a.nstages, 1));
     if (b->plan.front == FRONT_STAGED && b->opt_use_tma && ((reinterpret_cast<uintptr_t>(d_in) & 15u) == 0)) {
         encode_tiled_t enc = get_encode_tiled();
         const long long rs = b->plan.row_samples;
@@ -1276,7 +1286,13 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
             CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r == CUDA_SUCCESS) { a.use_tma = 1; a.tma_row0 = row0; a.tma_rows = nrows; }
+            if (r == CUDA_SUCCESS) {
+                a.use_tma = 1; a.tma_row0 = row0; a.tma_rows = nrows;
+                const long long hr = b->plan.HR;
+                a.tile_int_lo = (row0 + hr + kThreads - 1) / kThreads;                 // 32 t - HR >= row0
+                a.tile_int_hi = (row0 + nrows - kThreads) / kThreads;                  // 32 t + 32 <= row0 + nrows
+                if (row0 + nrows - kThreads < 0) a.tile_int_hi = -1;
+            }
             // L2 look-ahead of the stage ring, in fills (tiles of this CTA): ~2 ring depths; 0 = off
             a.l2_prefetch = 0;                 // measured on B200: any distance costs 3-10 % (profiles/r02_experiments.txt); kept for experiments
             if (const char *e2 = getenv("ORION_B200_L2_PREFETCH")) a.l2_prefetch = std::max(0, atoi(e2));
