@@ -124,6 +124,15 @@ DEV bool mbar_try_wait_hint(uint32_t mbar, uint32_t parity, uint32_t ns) {
         : "=r"(ok) : "r"(mbar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
+DEV bool mbar_test_wait(uint32_t mbar, uint32_t parity) {          // one non-blocking look at the phase
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
 DEV void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t mbar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -1056,6 +1065,10 @@ DEV const float2 *staged_sample(const ChainArgs &a, const unsigned char *smem, l
 #define ORION_FIR_Q_UNROLL 1  // unroll factor of the FIR's loop over sample pairs (4 = full for the decimate-by-8 shape)
 #endif
 constexpr int kFirQUnroll = ORION_FIR_Q_UNROLL;
+#ifndef ORION_EARLY_FINISH
+#define ORION_EARLY_FINISH 0  // 1: a warp whose stage slot is not filled yet runs its pending tile's section phase first
+                              // (measured: C1 46.1 -> 59.1 us -- the look-back then waits instead; profiles/r02_experiments.txt)
+#endif
 #ifndef ORION_FM_ROLLED
 #define ORION_FM_ROLLED 0     // 1: the FM front of a lane is one rolled loop (small code); 0: unrolled over the lane's items
 #endif
@@ -1922,6 +1935,15 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
             k = (NS > 1 && c < (1u << 27)) ? (int)__umulhi(c, a.ns_magic) : (int)(c / (unsigned)NS);   // (NS = 1: the magic number would be 2^32)
             s = (int)(c - (unsigned)k * (unsigned)NS);
             const uint32_t bar = smem_u32(&ring.full[s]);
+            // The slot's tile is not there yet and a finished front is pending: run that tile's section phase NOW instead
+            // of waiting (it would otherwise run after this tile's front) -- the wait for HBM becomes useful work.
+            if (ORION_EARLY_FINISH && has_sections && pend_tile >= 0 && (Dm<DM>::lr4 || a.pipe_u_slots == 0) &&
+                !(mbar_test_wait(bar, (unsigned)k & 1u) && *reinterpret_cast<volatile int *>(&ring.gen[s]) == k)) {
+                if (Dm<DM>::lr4) lr4_finish_parked<NPT>(a, hot, tabs_sh, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
+                else finish_sections<NPT>(a, hot, pend_tile, lane, u_pend, park[slot_pp ^ 1], xs);
+                if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
+                pend_tile = -1;
+            }
             // Use k of the slot waits for fill k: first on the mbarrier phase (a hardware-suspended wait, no
             // polling traffic), then ONE look at the fill index -- a warp more than one lap ahead of the
             // slot's current user sees the phase of fill k-2 as complete (the parity is one bit), finds the
