@@ -156,6 +156,8 @@ struct ChainArgs {
     int   ngroups;
     int   pipe_park_slots;       // per-warp scan-state slots (2, or ngroups + 1 for the multi-group pipeline)
     int   pipe_u_slots;          // per-warp item slots of the multi-group pipeline (0: single-group path)
+    int   nstage;                // stages of that pipeline (= pipe_u_slots)
+    int   stage_group[8];        // stage k finishes group stage_group[k-1]; -1: idle stage (slack in front of a slow-pole group)
     GroupParam grp[kMaxGroups];  // grp immediately followed by sec: the kernels view the pair as one block
     SecParam sec[kMaxSections];
     const GroupTables *gtabs;    // [ngroups]

@@ -1637,9 +1637,11 @@ DEV void stage_step(const ChainArgs &a, const Hot *hot, int k, int S, long long 
     for (int i = 0; i < NPT; ++i) u[i] = us[i * kThreads + lane];
     const long long jt = tile * (long long)(kThreads * NPT) + (long long)lane * NPT;
     const bool full = jt + NPT <= a.n_out;
-    group_finish_parked<NPT>(a, hot, k - 1, tile, lane, u, full, jt, park);
-    if (k < S) {
-        group_front_park<NPT>(a, hot, k, tile, lane, u, full, park);
+    const int g = a.stage_group[k - 1];
+    if (g < 0) return;                               // idle stage: the tile only ages (slack for a slow-pole group's records)
+    group_finish_parked<NPT>(a, hot, g, tile, lane, u, full, jt, park);
+    if (g + 1 < a.ngroups) {
+        group_front_park<NPT>(a, hot, g + 1, tile, lane, u, full, park);
 #pragma unroll
         for (int i = 0; i < NPT; ++i) us[i * kThreads + lane] = u[i];
         __syncwarp();
@@ -2074,7 +2076,7 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         if (!has_sections && tile == a.ntiles - 1) handoff_signal(a, 1, lane);      // the call's carried state is complete
         if (has_sections && !Dm<DM>::lr4 && a.pipe_u_slots > 0) {
             // multi-group chain: pipeline of depth S = ngroups (stage_step)
-            const int S = a.ngroups;
+            const int S = a.nstage;
             group_front_park<NPT>(a, hot, 0, tile, lane, u, jt + NPT <= a.n_out, park[pipe_it % (S + 1)]);
             // youngest first: a stage that only publishes (k small) must never sit behind a stage that may wait for the
             // records of older tiles -- otherwise the block records of a slow-pole group chain through those waits
@@ -2115,7 +2117,7 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
         if (pend_tile == a.ntiles - 1) handoff_signal(a, 1, lane);
     }
     if (!Dm<DM>::lr4 && a.pipe_u_slots > 0 && pipe_it > 0) {           // drain the multi-group pipeline
-        const int S = a.ngroups;
+        const int S = a.nstage;
         for (int j = pipe_it; j < pipe_it + S; ++j)
             for (int k = 1; k <= S; ++k) {
                 const int en = j - k;                                    // entry iteration of the tile at stage k

@@ -658,6 +658,7 @@ struct orion_b200_block {
     int ctas_per_sm = 1, sm_count = 1;
     int ws = 0;                           // the warp-specialised instance is selected
     int pipe_park_slots = 2, pipe_u_slots = 0;   // per-warp pipeline area of the chain kernel (multi-group chains)
+    int nstage = 0, stage_group[8] = { 0 };     // pipeline stages: the group each one finishes (-1: idle)
     int split = 1;                        // warps that share the FIR of one tile (FIR-only staged instance, long filters)
     // ---- options ----
     int opt_force_global = 0, opt_use_tma = 1, opt_serial = 0, opt_overlap = 0;
@@ -761,12 +762,37 @@ int finalize_plan(orion_b200_block *b) {
     }
     b->kernel = select_kernel(b->plan.front, b->plan.R, b->plan.U, sp, dm, b->nbatch > 1);
     if (!b->kernel) return fail(b, ORION_B200_ERR_INTERNAL, "no kernel instance for plan");
+    // section groups + scan tables
+    b->groups.clear();
+    b->group_depth.clear();
+    if (!b->secs.empty()) {
+        const std::vector<GroupHost> gh = split_groups(b->secs);
+        if (gh.size() > (size_t)kMaxGroups) return fail(b, ORION_B200_ERR_UNSUPPORTED, "too many section groups");
+        std::vector<GroupTables> tabs(gh.size());
+        b->groups.resize(gh.size());
+        for (size_t g = 0; g < gh.size(); ++g) build_group(b->secs.data(), gh[g], npt_of(b), &b->groups[g], &tabs[g]);
+        b->group_depth.clear();
+        for (size_t g = 0; g < gh.size(); ++g) b->group_depth.push_back(tabs[g].depth);
+        if (b->d_gtabs) { cudaFree(b->d_gtabs); b->d_gtabs = nullptr; }
+        CK(cudaMalloc(&b->d_gtabs, tabs.size() * sizeof(GroupTables)));
+        CK(dev_upload(b, b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables)));
+    }
     // per-warp pipeline area (chain_kernels.cuh): chains with several section groups keep one tile per group in flight
+    // Stage schedule of the pipeline: stage k finishes group stage_group[k-1] (and forms the aggregate of the next one); a
+    // slow-pole group CAN get an idle stage in front of its finish (ORION_B200_IDLE_STAGE=1), so that its block records --
+    // which wait for the slowest of 32 concurrent tiles -- have two iterations to arrive instead of one.  Experiment only:
+    // measured on C3 it tripped the look-back watchdog (profiles/r02_experiments.txt), so the default schedule has no idle stage.
     {
-        const int ng = (int)split_groups(b->secs).size();
+        const int ng = (int)b->groups.size();
         const bool multi = ng >= 2 && dm < 100;
-        b->pipe_park_slots = multi ? ng + 1 : 2;
-        b->pipe_u_slots = multi ? ng : 0;
+        b->nstage = 0;
+        if (multi)
+            for (int g = 0; g < ng; ++g) {
+                if (g > 0 && !b->groups[g].agg_only && getenv("ORION_B200_IDLE_STAGE")) b->stage_group[b->nstage++] = -1;
+                b->stage_group[b->nstage++] = g;
+            }
+        b->pipe_park_slots = multi ? b->nstage + 1 : 2;
+        b->pipe_u_slots = multi ? b->nstage : 0;
     }
     const size_t warp_pipe = 16 + (size_t)b->pipe_park_slots * 33 * kMaxGroupDim * sizeof(float) +
                              (size_t)b->pipe_u_slots * kThreads * npt_of(b) * sizeof(float);
@@ -837,21 +863,6 @@ int finalize_plan(orion_b200_block *b) {
             }
             b->hist_cap = (size_t)b->plan.H;
         }
-    }
-    // section groups + scan tables
-    b->groups.clear();
-    b->group_depth.clear();
-    if (!b->secs.empty()) {
-        const std::vector<GroupHost> gh = split_groups(b->secs);
-        if (gh.size() > (size_t)kMaxGroups) return fail(b, ORION_B200_ERR_UNSUPPORTED, "too many section groups");
-        std::vector<GroupTables> tabs(gh.size());
-        b->groups.resize(gh.size());
-        for (size_t g = 0; g < gh.size(); ++g) build_group(b->secs.data(), gh[g], npt_of(b), &b->groups[g], &tabs[g]);
-        b->group_depth.clear();
-        for (size_t g = 0; g < gh.size(); ++g) b->group_depth.push_back(tabs[g].depth);
-        if (b->d_gtabs) { cudaFree(b->d_gtabs); b->d_gtabs = nullptr; }
-        CK(cudaMalloc(&b->d_gtabs, tabs.size() * sizeof(GroupTables)));
-        CK(dev_upload(b, b->d_gtabs, tabs.data(), tabs.size() * sizeof(GroupTables)));
     }
     b->plan_dirty = false;
     return ORION_B200_OK;
@@ -1241,6 +1252,8 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     for (int s = 0; s < nsec; ++s) a.sec[s] = b->secs[s];
     a.ngroups = (int)b->groups.size();
     a.pipe_park_slots = b->pipe_park_slots; a.pipe_u_slots = b->pipe_u_slots;
+    a.nstage = b->nstage;
+    for (int i = 0; i < 8; ++i) a.stage_group[i] = b->stage_group[i];
     a.split = b->opt_serial ? 1 : b->split;
     for (int g = 0; g < a.ngroups; ++g) a.grp[g] = b->groups[g];
     a.gtabs = b->d_gtabs;

@@ -14,6 +14,7 @@ for w in "$@"; do case $w in
   c1)   cap c1chain chain_kernel 30 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c5 ;;
   bank) cap bank bank_fir_kernel 2 python bench.py --workload c5 --steps 2 --warmup 2 --no-cpu-baseline ;;
   c4)   WARM_S=0.3 cap c4 chain_kernel 12 python scripts/microbench.py c4 ;;
+  c2)   WARM_S=0.3 cap c2 chain_kernel 8 python scripts/microbench.py c2 ;;
   c3)   WARM_S=0.3 cap c3 chain_kernel 20 python scripts/microbench.py c3 ;;
   fm)   WARM_S=0.3 cap fm chain_kernel 20 python scripts/microbench.py fm ;;
   lp)   WARM_S=0.3 cap lp chain_kernel 20 python scripts/microbench.py lp ;;
