@@ -43,7 +43,7 @@ struct BankFirArgs {
     long long z_stride;
     int nch;
     long long tiles_total;       // ceil(n_out / BT)
-    int tiles_per_range;
+    int nranges;                 // time ranges (gridDim.x): range r covers tiles [r*tiles_total/nranges, (r+1)*tiles_total/nranges)
     int *err_flag;
 };
 
@@ -144,8 +144,8 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     __syncthreads();
 
     // this CTA's range of tiles: tile T covers blocks [BT*T, BT*T + BT), block b = samples [M*b, M*b + M)
-    const long long Ta = (long long)blockIdx.x * a.tiles_per_range;
-    const long long Tb = min(Ta + (long long)a.tiles_per_range, a.tiles_total);
+    const long long Ta = (long long)blockIdx.x * a.tiles_total / a.nranges;          // ranges differ by at most one tile
+    const long long Tb = ((long long)blockIdx.x + 1) * a.tiles_total / a.nranges;
     if (Ta >= Tb) return;
     const long long ntile = Tb - Ta + 1;             // + the warm-up tile Ta - 1 (its last PM blocks)
 

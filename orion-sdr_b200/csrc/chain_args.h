@@ -172,11 +172,15 @@ struct ChainArgs {
     int  *err_flag;
     int   pdl_guard;             // tiles below this index read state handed over by the previous call (prev, look-back)
     unsigned int *handoff;       // [0] calls whose FIR history is written, [1] 2 x calls whose carried state is complete,
-                                 // [2] CTAs (of all calls so far) that have run to their end
+                                 // [2], [3] CTAs that have run to their end, one counter per launch parity: a CTA of call
+                                 // N+1 may well finish before the last CTA of call N, so one counter for all calls could
+                                 // reach call N+2's target while call N still had CTAs running (seen as link records of
+                                 // epoch N+2 under the eyes of call N: scripts/stress_overlap.py)
     unsigned int hist_target;    // values of the two counters this call needs before it reads the hand-over (0: none)
     unsigned int carry_target;
-    unsigned int depth_target;   // value of the CTA-done counter that proves every launch before the previous one has ended
+    unsigned int depth_target;   // value of handoff[depth_slot] that proves the launch before the previous one has ended
                                  // (all of its tiles: nobody reads its buffers or its half of the link records any more)
+    int depth_slot;              // 2 + launch parity: the CTA-done counter this launch waits on AND counts into
     // batched launch (channel bank): blockIdx.y = member; member m works on channel batch_chan[m]
     int   batch;                 // members (1: plain launch)
     const int *batch_chan;       // [batch] channel index of every member (row of the strided input / output)

@@ -149,7 +149,7 @@ chain_ws_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUt
         for (int i = threadIdx.x; i < a.Lg; i += blockDim.x) g_sh[i] = __ldg(a.g + i);
     }
     __syncthreads();
-    handoff_wait(a, 2, a.depth_target);               // see chain_kernel: what this launch writes was read two launches ago
+    handoff_wait(a, a.depth_slot, a.depth_target);               // see chain_kernel: what this launch writes was read two launches ago
 
     const int demod = Dm<DM>::demod(a);
     const bool need_prev = demod == DEMOD_FM || demod == DEMOD_PM;
@@ -267,7 +267,7 @@ chain_ws_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ CUt
     }
     __threadfence();
     __syncwarp();
-    if (lane == 0 && atomicAdd(&ctl.done, 1u) == (unsigned)kWsWarps - 1u) atomicAdd(a.handoff + 2, 1u);
+    if (lane == 0 && atomicAdd(&ctl.done, 1u) == (unsigned)kWsWarps - 1u) atomicAdd(a.handoff + a.depth_slot, 1u);
 }
 
 chain_kernel_t get_kernel_ws(int dm) {

@@ -996,15 +996,21 @@ static __device__ __noinline__ void stage_load_generic(const ChainArgs &a, long 
     __syncwarp();
 }
 
-// in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1)
+// in-place input-rate mixer on the staged samples: x[s] * p(kbase + s + 1).  A lane walks one row (the phasor is a
+// recurrence along the samples); the rows left over after the last full pass of 32 (the HR halo rows) are cut into
+// segments so that they occupy all lanes for a fraction of a pass instead of a few lanes for a whole one.
 static __device__ __noinline__ void stage_mix(const ChainArgs &a, long long tile, unsigned char *smem, int lane) {
     const int rows = kThreads + a.HR;
     const long long G0 = tile * kThreads - a.HR;
     const int cpr = a.row_samples >> 1;
     const float2 w = make_float2(a.pre.wre, a.pre.wim);
     for (int rb = 0; rb < rows; rb += kThreads) {           // uniform trip count
-        const int rho = rb + lane;
-        if (rho >= rows) continue;
+        const int nrem = min(kThreads, rows - rb);
+        const int S = kThreads / nrem;                      // segments per row in this pass (1 while more than 16 rows are left)
+        const int rho = rb + lane / S;
+        const int len = (cpr + S - 1) / S;
+        const int cc0 = (lane % S) * len, cc1 = min(cpr, cc0 + len);
+        if (lane >= nrem * S || cc0 >= cc1) continue;
         const long long s0 = row_start_sample(a, G0 + rho);
         unsigned char *rp = smem + (size_t)rho * a.row_pitch;
         float2 p = make_float2(1.f, 0.f);
@@ -1012,7 +1018,7 @@ static __device__ __noinline__ void stage_mix(const ChainArgs &a, long long tile
             const float2 wx = make_float2(a.pre.xwre, a.pre.xwim);
             unsigned ctr = 0;
             bool walking = false;
-            for (int cc = 0; cc < cpr; ++cc) {
+            for (int cc = cc0; cc < cc1; ++cc) {
                 float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
                 float2 y[2];
 #pragma unroll
@@ -1027,9 +1033,9 @@ static __device__ __noinline__ void stage_mix(const ChainArgs &a, long long tile
             }
             continue;
         }
-        for (int cc = 0; cc < cpr; ++cc) {
+        for (int cc = cc0; cc < cc1; ++cc) {
             const unsigned long long k = a.pre.kbase + (unsigned long long)(s0 + 2 * cc) + 1ull;
-            if ((cc & 7) == 0) p = nco_unit(a.pre, k);
+            if (cc == cc0 || (cc & 7) == 0) p = nco_unit(a.pre, k);
             float4 v = *reinterpret_cast<float4 *>(rp + cc * 16);
             const float2 y0 = mix_apply(a.mix, make_float2(v.x, v.y), scale2(p, nco_amp(a.pre, k)));
             p = cmul_fma(p, w);
@@ -1888,9 +1894,9 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     // At most two launches of a block are ever in flight.  The link records alternate between two halves by launch
     // parity and the history / carried-state buffers rotate through three, so what this launch WRITES was last READ by
     // the launch before the previous one: nothing is published or handed over before every CTA of that launch has run
-    // to its end (handoff[2] counts them; observed on long streams: with only the hardware's launch ordering a third
+    // to its end (handoff[2 + launch parity] counts them; observed on long streams: with only the hardware's launch ordering a third
     // launch did start while the first still had tiles to finish).
-    handoff_wait(a, 2, a.depth_target);
+    handoff_wait(a, a.depth_slot, a.depth_target);
     if (cta == (long long)(a.ntiles - 1) % G && wid == NW - 1) {
         handoff_wait(a, 1, a.carry_target);                // copies what the previous call writes up to its very end
         end_of_call_duties(a, lane);
@@ -2135,7 +2141,7 @@ chain_kernel(const __grid_constant__ ChainArgs a_param, const __grid_constant__ 
     // this warp reads nothing of the call any more; the last warp of the CTA reports the CTA as done
     __threadfence();
     __syncwarp();
-    if (lane == 0 && atomicAdd(&ring.done, 1u) == (unsigned)NW - 1u) atomicAdd(a.handoff + 2, 1u);
+    if (lane == 0 && atomicAdd(&ring.done, 1u) == (unsigned)NW - 1u) atomicAdd(a.handoff + a.depth_slot, 1u);
 }
 
 typedef void (*chain_kernel_t)(const ChainArgs, const CUtensorMap);

@@ -38,7 +38,7 @@ struct BankFirArgs {             // bank_kernels.cu
     int M, Lg, PM, BT, NS;
     const float *gt; float g0;
     float2 *z; long long z_stride; int nch;
-    long long tiles_total; int tiles_per_range;
+    long long tiles_total; int nranges;
     int *err_flag;
 };
 size_t bank_fir_smem_bytes(const BankFirArgs &a);
@@ -309,10 +309,15 @@ struct ExactOsc {
     // device side
     OscAnchor *h_an2[2] = { nullptr, nullptr };   // pinned staging, two sets: the host prepares call N+1 while call N's upload is in flight
     OscAnchor *h_an = nullptr;                // the set in use
-    OscAnchor *d_an = nullptr;
+    // device tables, two sets like the staging: call N+1's tables are uploaded and expanded on the block's side stream
+    // while call N's kernel still reads its own set
+    OscAnchor *d_an2[2] = { nullptr, nullptr };
     size_t an_cap = 0;
-    float2 *d_fine = nullptr, *d_hist = nullptr;
+    float2 *d_fine2[2] = { nullptr, nullptr }, *d_hist2[2] = { nullptr, nullptr };
     size_t fine_cap = 0, hist_cap = 0;
+    cudaEvent_t ready2[2] = { nullptr, nullptr };    // set i is uploaded and expanded (side stream)
+    cudaEvent_t used2[2] = { nullptr, nullptr };     // the kernel that reads set i has been enqueued before this point of the block's stream
+    bool used_valid[2] = { false, false };
     float2 *h_hist2[2] = { nullptr, nullptr };
     float2 *h_hist = nullptr;
     cudaEvent_t staged2[2] = { nullptr, nullptr };   // the last upload from staging set i has completed
@@ -385,8 +390,14 @@ struct ExactOsc {
             if (staged2[i]) cudaEventDestroy(staged2[i]);
             h_an2[i] = nullptr; h_hist2[i] = nullptr; staged2[i] = nullptr;
         }
-        cudaFree(d_an); cudaFree(d_fine); cudaFree(d_hist);
-        h_an = nullptr; h_hist = nullptr; d_an = nullptr; d_fine = nullptr; d_hist = nullptr;
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_an2[i]); cudaFree(d_fine2[i]); cudaFree(d_hist2[i]);
+            d_an2[i] = nullptr; d_fine2[i] = nullptr; d_hist2[i] = nullptr;
+            if (ready2[i]) cudaEventDestroy(ready2[i]);
+            if (used2[i]) cudaEventDestroy(used2[i]);
+            ready2[i] = used2[i] = nullptr; used_valid[i] = false;
+        }
+        h_an = nullptr; h_hist = nullptr;
         an_cap = fine_cap = hist_cap = 0;
     }
 };
@@ -442,7 +453,7 @@ const size_t kMaxStageBytes = 100 * 1024;      // one staged tile
 const size_t kRingBudget = 200 * 1024;         // upper bound of the stage ring; finalize_plan trims it to what fits next to the
                                                // per-warp areas and tables (C1: 11 slots -- 45.4 us against 46.3 with 10, 46.8 with 9)
 
-void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl) {
+void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force_global, FirPlan *pl, bool small_tiles = false) {
     const int L = (int)taps.size();
     pl->g.assign(L, 0.f);
     if (fir_kind == FIR_DECIM) {               // y[n] = taps[L-1] x[n] + sum_{t<L-1} taps[t] x[n-1-t]   (fir.rs:57-66)
@@ -457,9 +468,23 @@ void plan_fir(int fir_kind, const std::vector<float> &taps, size_t M, bool force
     const long long Mb = (long long)Mi * U;
     int O = Mi * (U - 1);
     if (O & 1) O += 1;
-    int R = 0;
-    for (int r : { 8, 4, 2, 1 })
-        if (Mb * r <= kMaxRowSamples) { R = r; break; }
+    int R = 0, rmax = 8;
+    if (const char *e = getenv("ORION_B200_ROWR")) rmax = std::max(1, atoi(e));      // experiment: smaller tiles, more ring slots
+    // A chain with an input-rate mixer rotates every staged tile in place before its FIR (stage_mix): the work per slot
+    // roughly doubles, so such chains take smaller tiles -- more slots in the ring, more warps with a tile in hand
+    // (C2, 201 taps / 25: 28.5 KB tiles and 7 slots -> 15.4 KB and 12; 192 -> 161 us, profiles/r02_c2_steps.txt).
+    for (int r : { 8, 4, 2, 1 }) {
+        if (r > rmax || Mb * r > kMaxRowSamples) continue;
+        if (small_tiles && r > 1) {
+            const int Pp = (int)((Lg + 1 + O + Mb - 1) / Mb);
+            const int hr = (Pp + r - 1) / r;
+            const int rs = (int)(r * Mb);
+            const size_t bytes = (size_t)(kThreads + hr) * (size_t)(rs * 8 + (((rs / 2) % 2 == 0) ? 16 : 0));
+            if (bytes > 20 * 1024) continue;
+        }
+        R = r;
+        break;
+    }
     bool staged = R > 0 && M <= 4096;
     if (staged) {
         const int P = (int)((Lg + 1 + O + Mb - 1) / Mb);
@@ -666,6 +691,9 @@ struct orion_b200_block {
     // ---- device ----
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t osc_stream = nullptr;    // exact oscillators: table upload + expansion run here, ahead of the block's stream
+    int osc_side = 1;                     // 1: side stream; 0: the block's own stream (ORION_B200_OSC_STREAM)
+    std::vector<cudaEvent_t> osc_used_pending;   // recorded on `stream` right after the launch that reads the tables (launch())
     float *d_g = nullptr;
     GroupTables *d_gtabs = nullptr;
     std::vector<GroupParam> groups;
@@ -676,7 +704,7 @@ struct orion_b200_block {
     size_t hist_cap = 0;
     CarryState *d_carry[3] = { nullptr, nullptr, nullptr };
     int pp = 0;
-    unsigned int ctas_launched = 0, ctas_before_prev = 0;   // CTA-done counter targets (handoff[2])
+    unsigned int ctas_par[2] = { 0, 0 };  // CTAs launched so far by the calls of each parity: targets of the CTA-done counters handoff[2 + parity]
     TileLink *d_links = nullptr;
     size_t links_cap = 0;
     unsigned long long *d_ticket = nullptr;
@@ -735,7 +763,7 @@ int npt_of(const orion_b200_block *b) { return b->plan.R * b->plan.U; }
 int finalize_plan(orion_b200_block *b) {
     CK(cudaSetDevice(b->device));
     b->plan.warps = kMaxWarpsPerCta;               // (a previous plan may have been the 24-warp warp-specialised one)
-    if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan);
+    if (b->fir != FIR_NONE) plan_fir(b->fir, b->taps, b->M, b->opt_force_global != 0, &b->plan, b->mix != MIX_NONE && !getenv("ORION_B200_BIG_TILES"));
     else { b->plan = FirPlan(); b->plan.front = FRONT_DIRECT; b->plan.R = 16; b->plan.U = 1; }   // chain_kernel<DIRECT,16,1>
     // shape / demodulator specialisations of the kernel family (chain_kernels.cuh, Geo<SP> and Dm<DM>)
     int sp = 0, dm = -1;
@@ -882,7 +910,7 @@ int reset_state(orion_b200_block *b) {
     CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
     CK(cudaStreamSynchronize(b->stream));
     b->calls_since_reset = 0;
-    b->ctas_launched = b->ctas_before_prev = 0;
+    b->ctas_par[0] = b->ctas_par[1] = 0;
     b->k_pre = b->k_post = 0;
     b->pre.reset_phase();
     b->post.reset_phase();
@@ -1001,33 +1029,51 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
     const size_t n_an = (n_items + 1023) / 1024 + 2;      // capacity: the consumed state + one per 1024-grid point
     size_t n_an_used = 0;
     const long long fine_len = (long long)((n_items - 1) >> 4) + 1;
-    x.sbuf ^= 1;                                               // staging set of this call; its previous upload (two calls ago) must be done
-    if (!x.staged2[x.sbuf]) CK(cudaEventCreateWithFlags(&x.staged2[x.sbuf], cudaEventDisableTiming));
-    else CK(cudaEventSynchronize(x.staged2[x.sbuf]));
+    x.sbuf ^= 1;                                               // staging + table set of this call; its previous upload (two calls ago) must be done
+    const int p = x.sbuf;
+    if (!b->osc_stream) CK(cudaStreamCreateWithFlags(&b->osc_stream, cudaStreamNonBlocking));
+    // Measured (profiles/r02_c2_steps.txt): the side stream hides the uploads of blocks with ONE exact oscillator (Rotator
+    // 133 -> 101 us, FIR + SSB 161 -> 148 us); a chain with two (C2: input-rate mixer + BFO) is slower with it (288 -> 363 us:
+    // its large expansion kernel competes with the SM-filling chain kernel for a place), so such chains stay in-stream.
+    b->osc_side = !(want_exact_pre(b) && want_exact_post(b));
+    if (const char *e = getenv("ORION_B200_OSC_STREAM")) b->osc_side = atoi(e);
+    if (!x.staged2[p]) CK(cudaEventCreateWithFlags(&x.staged2[p], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(x.staged2[p]));
+    if (!x.ready2[p]) CK(cudaEventCreateWithFlags(&x.ready2[p], cudaEventDisableTiming));
+    if (!x.used2[p]) CK(cudaEventCreateWithFlags(&x.used2[p], cudaEventDisableTiming));
     if (n_an > x.an_cap) {
         CK(cudaStreamSynchronize(b->stream));
-        for (int i = 0; i < 2; ++i) { if (x.h_an2[i]) cudaFreeHost(x.h_an2[i]); x.h_an2[i] = nullptr; }
-        cudaFree(x.d_an);
-        x.d_an = nullptr;
+        CK(cudaStreamSynchronize(b->osc_stream));
         const size_t cap = n_an + n_an / 4 + 16;
-        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&x.h_an2[i], cap * sizeof(OscAnchor)));
-        CK(cudaMalloc(&x.d_an, cap * sizeof(OscAnchor)));
+        for (int i = 0; i < 2; ++i) {
+            if (x.h_an2[i]) cudaFreeHost(x.h_an2[i]);
+            x.h_an2[i] = nullptr;
+            cudaFree(x.d_an2[i]); x.d_an2[i] = nullptr;
+            CK(cudaMallocHost(&x.h_an2[i], cap * sizeof(OscAnchor)));
+            CK(cudaMalloc(&x.d_an2[i], cap * sizeof(OscAnchor)));
+        }
         x.an_cap = cap;
     }
     if ((size_t)fine_len > x.fine_cap) {
         CK(cudaStreamSynchronize(b->stream));
-        cudaFree(x.d_fine); x.d_fine = nullptr;
+        CK(cudaStreamSynchronize(b->osc_stream));
         const size_t cap = (size_t)fine_len + (size_t)fine_len / 4 + 64;
-        CK(cudaMalloc(&x.d_fine, cap * sizeof(float2)));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(x.d_fine2[i]); x.d_fine2[i] = nullptr;
+            CK(cudaMalloc(&x.d_fine2[i], cap * sizeof(float2)));
+        }
         x.fine_cap = cap;
     }
     if (hist_len > x.hist_cap) {
         CK(cudaStreamSynchronize(b->stream));
-        for (int i = 0; i < 2; ++i) { if (x.h_hist2[i]) cudaFreeHost(x.h_hist2[i]); x.h_hist2[i] = nullptr; }
-        cudaFree(x.d_hist);
-        x.d_hist = nullptr;
-        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&x.h_hist2[i], hist_len * sizeof(float2)));
-        CK(cudaMalloc(&x.d_hist, hist_len * sizeof(float2)));
+        CK(cudaStreamSynchronize(b->osc_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (x.h_hist2[i]) cudaFreeHost(x.h_hist2[i]);
+            x.h_hist2[i] = nullptr;
+            cudaFree(x.d_hist2[i]); x.d_hist2[i] = nullptr;
+            CK(cudaMallocHost(&x.h_hist2[i], hist_len * sizeof(float2)));
+            CK(cudaMalloc(&x.d_hist2[i], hist_len * sizeof(float2)));
+        }
         x.hist_cap = hist_len;
     }
     x.h_an = x.h_an2[x.sbuf];
@@ -1074,14 +1120,25 @@ int prepare_exact(orion_b200_block *b, Osc &o, unsigned long long kbase, size_t 
         }
     }
     x.consume_to(ctr0 + (unsigned long long)n_items);
-    CK(cudaMemcpyAsync(x.d_an, x.h_an, n_an_used * sizeof(OscAnchor), cudaMemcpyHostToDevice, b->stream));
-    if (nh) CK(cudaMemcpyAsync(x.d_hist, x.h_hist, nh * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaEventRecord(x.staged2[x.sbuf], b->stream));
-    CK(osc_expand_launch(x.d_an, (int)n_an_used, x.d_fine, ctr0 + 1ull, fine_len, b->stream));
+    // Side stream: the tables do not depend on the data, so their upload and expansion overlap whatever the block's stream
+    // is still running (the previous call's kernel).  Set p was last read by the kernel of two calls ago (used2[p]).
+    const bool side = b->osc_side != 0;
+    cudaStream_t os = side ? b->osc_stream : b->stream;
+    if (side && x.used_valid[p]) CK(cudaStreamWaitEvent(os, x.used2[p], 0));
+    CK(cudaMemcpyAsync(x.d_an2[p], x.h_an, n_an_used * sizeof(OscAnchor), cudaMemcpyHostToDevice, os));
+    if (nh) CK(cudaMemcpyAsync(x.d_hist2[p], x.h_hist, nh * sizeof(float2), cudaMemcpyHostToDevice, os));
+    CK(cudaEventRecord(x.staged2[p], os));
+    CK(osc_expand_launch(x.d_an2[p], (int)n_an_used, x.d_fine2[p], ctr0 + 1ull, fine_len, os));
+    if (side) {
+        CK(cudaEventRecord(x.ready2[p], os));
+        CK(cudaStreamWaitEvent(b->stream, x.ready2[p], 0));
+    }
+    b->osc_used_pending.push_back(x.used2[p]);           // recorded in either mode: the mode may change between calls
+    x.used_valid[p] = true;
     b->launches += 1;
     np->exact = 1;
-    np->xfine = x.d_fine; np->xfine_len = (int)fine_len;
-    np->xhist = x.d_hist; np->xhist_len = (int)nh;
+    np->xfine = x.d_fine2[p]; np->xfine_len = (int)fine_len;
+    np->xhist = x.d_hist2[p]; np->xhist_len = (int)nh;
     np->xwre = x.wre; np->xwim = x.wim;
     return ORION_B200_OK;
 }
@@ -1189,8 +1246,18 @@ int launch_aux(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, 
     return ORION_B200_OK;
 }
 
+int launch_inner(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                 long long batch_in_stride, long long batch_out_stride);
 int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
            long long batch_in_stride, long long batch_out_stride) {
+    const int st = launch_inner(b, d_in, n_in, d_out, n_out, batch_in_stride, batch_out_stride);
+    // everything that reads this call's oscillator tables is enqueued: from here on the block's stream their set may be rewritten
+    for (cudaEvent_t ev : b->osc_used_pending) cudaEventRecord(ev, b->stream);
+    b->osc_used_pending.clear();
+    return st;
+}
+int launch_inner(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                 long long batch_in_stride, long long batch_out_stride) {
     if (b->plan_dirty) { int st = finalize_plan(b); if (st) return st; }
     if (n_in == 0) return ORION_B200_OK;
     CK(cudaSetDevice(b->device));
@@ -1273,7 +1340,8 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     a.handoff = b->d_handoff;
     a.hist_target = b->calls_since_reset;                 // every earlier call has written its history ...
     a.carry_target = 2u * b->calls_since_reset;           // ... and both of its hand-over signals
-    a.depth_target = b->ctas_before_prev;                 // every CTA of every call but the previous one has run to its end
+    a.depth_slot = 2 + (int)(b->calls_since_reset & 1u);  // the call before the previous one has the same parity:
+    a.depth_target = b->ctas_par[b->calls_since_reset & 1u];   // ... every CTA of it (and of its same-parity predecessors) has run to its end
     if (!b->plan.taps2.empty()) memcpy(a.taps2, b->plan.taps2.data(), b->plan.taps2.size() * sizeof(float2));
     a.ntaps2 = (int)b->plan.taps2.size();
 
@@ -1338,14 +1406,13 @@ int launch(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out, size
     delete ap;
     if (e != cudaSuccess) return fail(b, ORION_B200_ERR_CUDA, "chain kernel launch", e);
     b->launches += 1;
+    b->ctas_par[b->calls_since_reset & 1u] += (unsigned)grid * (unsigned)b->nbatch;
     b->calls_since_reset += 1;
-    b->ctas_before_prev = b->ctas_launched;
-    b->ctas_launched += (unsigned)grid * (unsigned)b->nbatch;
-    if (b->calls_since_reset >= (1u << 30) || b->ctas_launched >= (1u << 30)) {   // counter wrap: drain, start over
+    if (b->calls_since_reset >= (1u << 30) || b->ctas_par[0] >= (1u << 30) || b->ctas_par[1] >= (1u << 30)) {   // counter wrap: drain, start over
         CK(cudaStreamSynchronize(b->stream));
         CK(dev_memset(b, b->d_handoff, 0, 4 * sizeof(unsigned int)));
         b->calls_since_reset = 0;
-        b->ctas_launched = b->ctas_before_prev = 0;
+        b->ctas_par[0] = b->ctas_par[1] = 0;
     }
     b->pp = (b->pp + 1) % 3;
     b->k_pre += n_in;
@@ -1992,8 +2059,8 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     const int ngroups = (int)((k->nch + 32 * nwc - 1) / (32 * nwc));
     long long want = std::max<long long>(1, ((long long)per_sm * sms + ngroups - 1) / ngroups);    // fill every SM once
     if (const char *e = getenv("ORION_B200_BANK_RANGES")) want = std::max(1, atoi(e));
-    a.tiles_per_range = (int)std::max<long long>(1, (a.tiles_total + want - 1) / want);
-    const int nranges = (int)((a.tiles_total + a.tiles_per_range - 1) / a.tiles_per_range);
+    const int nranges = (int)std::max<long long>(1, std::min<long long>(want, a.tiles_total));   // balanced: ranges differ by at most one tile
+    a.nranges = nranges;
     cudaError_t e = bank_fir_launch(a, nranges, nwc, k->stream);
     if (e != cudaSuccess) return bank_fail(k, ORION_B200_ERR_CUDA, std::string("bank front-end launch: ") + cudaGetErrorString(e));
     k->launches += 1;
@@ -2209,6 +2276,7 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->osc_stream) cudaStreamSynchronize(b->osc_stream);
     cudaFree(b->d_g); cudaFree(b->d_gtabs);
     for (int i = 0; i < 3; ++i) { cudaFree(b->d_hist[i]); cudaFree(b->d_carry[i]); }
     b->pre.x.free_device(); b->post.x.free_device();
@@ -2227,6 +2295,7 @@ void orion_b200_block_destroy(orion_b200_block *b) {
     }
     if (b->s_h2d) cudaStreamDestroy(b->s_h2d);
     if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
+    if (b->osc_stream) cudaStreamDestroy(b->osc_stream);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     cudaGetLastError();
     delete b;
