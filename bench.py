@@ -318,6 +318,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
+    numa = ob.pin_host_to_device_numa_node(local)       # before any host buffer is allocated (first touch)
     ob.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -495,6 +496,7 @@ def main():
             "clocks": clocks, "parity_check": check,
             "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n_out * 4),
                     "steps": Ke, "api": "orion_b200_block_process (host pointers, pinned); chunks are pipelined: H2D / kernel / D2H overlap",
+                    "host_numa": numa,
                     "pageable": {"value": e2e_pageable, "unit": "MS/s", "vs_pinned": e2e_pageable / e2e,
                                  "vs_pinned_run": {"max_err_fs": e2e_err, "snr_db": e2e_snr},
                                  "api": "same call, ordinary pageable host buffers (staged through the block's pinned ring)"}},

@@ -1603,15 +1603,25 @@ DEV void lr4_finish_parked(const ChainArgs &a, const Hot *hot, const Lr4Tabs *ta
     // call are computed from zero-padded input and never stored, the carried state is taken at the last real one
     const SecParam &P0 = hot->sec[0], &P1 = hot->sec[1];
     const long long last = a.n_out - 1 - jt;
+    if (last < 0 || last >= NPT) {                   // every lane but one of the whole call: the bare recursion
 #pragma unroll
-    for (int i = 0; i < NPT; ++i) {
-        const float y = sec_step_t<SEC_BIQUAD>(P0, u[i], st[0], st[1]);
-        u[i] = sec_step_t<SEC_BIQUAD>(P1, y, st[2], st[3]);
-        if (last == i) {
-            a.carry_out->sec[0] = make_float2(st[0], st[1]);
-            a.carry_out->sec[1] = make_float2(st[2], st[3]);
+        for (int i = 0; i < NPT; ++i) {
+            const float y = sec_step_t<SEC_BIQUAD>(P0, u[i], st[0], st[1]);
+            u[i] = sec_step_t<SEC_BIQUAD>(P1, y, st[2], st[3]);
+        }
+    } else {                                         // the lane that holds the call's last item also leaves the carried state
+        const int li = (int)last;
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const float y = sec_step_t<SEC_BIQUAD>(P0, u[i], st[0], st[1]);
+            u[i] = sec_step_t<SEC_BIQUAD>(P1, y, st[2], st[3]);
+            if (li == i) {
+                a.carry_out->sec[0] = make_float2(st[0], st[1]);
+                a.carry_out->sec[1] = make_float2(st[2], st[3]);
+            }
         }
     }
+    __syncwarp();
     store_f32<NPT>(a, tile, lane, u, xs);
 }
 

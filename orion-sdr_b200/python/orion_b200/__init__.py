@@ -737,6 +737,37 @@ def _fill_spec(sp, keep, *, mix=MIX_NONE, mix_freq_hz=0.0, mix_fs=1.0, fir=FIR_N
 
 
 # ---- channel bank (BASELINE config 5) and its sharding across processes ---------------------------------
+def pin_host_to_device_numa_node(ordinal: int) -> dict:
+    """Bind the calling thread (and the threads it starts later: the library's staging pool) to the CPUs of the NUMA node
+    the GPU hangs off, so that host buffers allocated from here on are first-touched in that node's memory.  With one
+    process per GPU this keeps every rank's host<->device copies off the inter-socket link (8 ranks on one node shared
+    one socket's memory bandwidth: e2e scaled 3.4x from 1 to 8 GPUs).  Best effort: returns what it found and did, never
+    raises (containers without /sys NUMA information are left alone)."""
+    info = {"node": None, "cpus": 0, "pinned": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(ordinal)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+            info["pinned"] = True
+    except Exception as e:                                   # noqa: BLE001 -- best effort by design
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 def shard_range(n_channels: int, rank: int, world: int) -> range:
     """Channels [g*C/G, (g+1)*C/G) of rank g: contiguous, covers every channel once."""
     if not (0 <= rank < world):

@@ -304,3 +304,18 @@ def test_plain_c_client_compiles_links_and_runs(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok" in out.stdout
+
+
+def test_numa_pinning_helper_is_best_effort():
+    """bench.py binds every rank to the NUMA node of its GPU before it allocates host buffers.  Without a GPU (or without
+    /sys NUMA information) the helper must report that and leave the affinity alone -- never raise."""
+    import os
+    import orion_b200 as ob
+    before = os.sched_getaffinity(0)
+    info = ob.pin_host_to_device_numa_node(0)
+    assert set(info) >= {"node", "cpus", "pinned"}
+    if not info["pinned"]:
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert os.sched_getaffinity(0) <= before and info["cpus"] == len(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, before)
