@@ -1391,7 +1391,16 @@ int launch_inner(orion_b200_block *b, const void *d_in, size_t n_in, void *d_out
         const long long want = (ntiles + b->plan.warps - 1) / b->plan.warps;      // one tile per warp at least
         grid = (int)std::max<long long>(1, std::min<long long>(want, resident));
         if (const char *e = getenv("ORION_B200_GRID")) grid = std::max(1, std::min(grid, atoi(e)));   // experiments
-        if (b->nbatch > 1) grid = 1;      // one CTA per member: its tiles only ever wait for tiles of the same CTA
+        if (b->nbatch > 1) {
+            // One CTA per member when the members fill the machine (its tiles then only ever wait for tiles of the same
+            // CTA).  A small bank (the 128-channel shard of an 8-GPU run: 64 members per demodulator kind) would leave
+            // more than half of the SMs idle and every warp with eight latency-bound iterations; it gets two CTAs per
+            // member -- CTAs of one member are neighbours in launch order, so both are resident together.
+            int g = 1;
+            while (g < 4 && (long long)b->nbatch * (2 * g) <= resident && ntiles >= (long long)(4 * g) * b->plan.warps) g *= 2;
+            if (const char *e = getenv("ORION_B200_BATCH_GRID")) g = std::max(1, std::min(8, atoi(e)));
+            grid = g;
+        }
     }
     // Overlap with the previous launch on the stream (programmatic dependent launch): only long calls (the link
     // records and the output of call N are far from what call N+1 touches first), only section groups whose
@@ -2069,7 +2078,7 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     const size_t ob = 4;
     // the demodulator groups are independent: with more than one they run side by side on their own streams between two
     // events on the bank's stream (a small bank's group does not fill the machine by itself)
-    const bool fork = k->groups.size() > 1 && k->ev_fork != nullptr;
+    const bool fork = k->groups.size() > 1 && k->ev_fork != nullptr && !getenv("ORION_B200_BANK_NO_FORK");
     if (fork) cudaEventRecord(k->ev_fork, k->stream);
     for (size_t gi = 0; gi < k->groups.size(); ++gi) {
         BankGroup &g = k->groups[gi];

@@ -7,6 +7,5 @@ timeout 600 python bench.py > gpurun_out/r02_bench_line_final.json 2> gpurun_out
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_line_reference_final.json 2>> gpurun_out/r02_bench_final.err; cat gpurun_out/r02_bench_line_reference_final.json | cut -c1-400
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench_final.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c5 > gpurun_out/ncu_launches_final.log 2>&1
 grep -c chain_kernel gpurun_out/r02_launches_bench_final.csv
-bash scripts/gpu_profiles_r02.sh c1 c2 2>&1 | grep "ncu exit"
+bash scripts/gpu_profiles_r02.sh c1 2>&1 | grep "ncu exit"
 timeout 400 python scripts/microbench.py dec chain fm rot lp configs 2>&1 | tee gpurun_out/r02_microbench_final.txt | cut -c1-100
-timeout 200 python scripts/c2_probe.py fir firssb0 firssb c2closed c2 am25 fm25 2>&1 | tee gpurun_out/r02_c2_steps_final.txt
