@@ -43,7 +43,7 @@ struct BankFirArgs {
     long long z_stride;
     int nch;
     long long tiles_total;       // ceil(n_out / BT)
-    int nranges;                 // time ranges (gridDim.x): range r covers tiles [r*tiles_total/nranges, (r+1)*tiles_total/nranges)
+    int nranges;                 // time ranges (gridDim.x): range r covers blocks [r*n_out/nranges, (r+1)*n_out/nranges)
     int *err_flag;
 };
 
@@ -143,11 +143,13 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     for (int i = threadIdx.x; i < M * PM; i += blockDim.x) gt_sh[i] = __ldg(a.gt + i);
     __syncthreads();
 
-    // this CTA's range of tiles: tile T covers blocks [BT*T, BT*T + BT), block b = samples [M*b, M*b + M)
-    const long long Ta = (long long)blockIdx.x * a.tiles_total / a.nranges;          // ranges differ by at most one tile
-    const long long Tb = ((long long)blockIdx.x + 1) * a.tiles_total / a.nranges;
-    if (Ta >= Tb) return;
-    const long long ntile = Tb - Ta + 1;             // + the warm-up tile Ta - 1 (its last PM blocks)
+    // this CTA's range of BLOCKS (block b = samples [M*b, M*b + M) = output b): ranges differ by at most one block, so the
+    // CTAs of the single wave end together.  The range is walked in tiles of BT blocks from its first block; the last tile
+    // may be cut short (it is still staged whole), tile 0 is the warm-up (the PM blocks before the range).
+    const long long Ba = (long long)blockIdx.x * a.n_out / a.nranges;
+    const long long Bb = ((long long)blockIdx.x + 1) * a.n_out / a.nranges;
+    if (Ba >= Bb) return;
+    const long long ntile = (Bb - Ba + BT - 1) / BT + 1;
 
     if (wid == NWC) {
         // ---------------- producer warp: stream the tiles of the range through the ring ----------------
@@ -155,13 +157,13 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
             for (int k0 = 0; k0 < a.H; k0 += 32)
                 if (k0 + lane < a.H) a.hist_out[k0 + lane] = bank_load_x(a, a.n_in - a.H + k0 + lane);
         }
-        const bool al16 = (reinterpret_cast<uintptr_t>(a.in) & 15u) == 0 && ((size_t)M * BT * sizeof(float2)) % 16 == 0;
+        const bool al16 = (reinterpret_cast<uintptr_t>(a.in) & 15u) == 0 && ((size_t)M * sizeof(float2)) % 16 == 0;
         for (long long q = 0; q < ntile; ++q) {
-            const long long T = Ta - 1 + q;
+            const long long blk0 = Ba + (q - 1) * BT;                        // first block of the tile
             const int s = (int)(q % NS);
             const unsigned lap = (unsigned)(q / NS);
             mbar_wait(smem_u32(&empty[s]), (lap & 1u) ^ 1u, a.err_flag, 5);  // first lap: passes at once
-            const long long s0 = T * (long long)BT * M;                      // first sample of the tile
+            const long long s0 = blk0 * (long long)M;                        // first sample of the tile
             unsigned char *dst = smem + (size_t)s * slot_bytes;
             const bool interior = al16 && s0 >= 0 && s0 + (long long)BT * M <= a.n_in;
             if (interior) {
@@ -194,7 +196,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     const float g0 = a.g0;
     const bool have_g0 = g0 != 0.0f;
     float2 *zrow = a.z + (long long)ch * a.z_stride;
-    const long long ja = Ta * BT, jb = min(Tb * (long long)BT, a.n_out);   // outputs this range stores
+    const long long ja = Ba, jb = min(Bb, a.n_out);                       // outputs this range stores
 
     f32x2 acc[PM];
 #pragma unroll
@@ -208,13 +210,14 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     const unsigned par = (unsigned)((osc.kbase + 1ull) & 1ull);
 
     for (long long q = 0; q < ntile; ++q) {
-        const long long T = Ta - 1 + q;
+        const long long blk0 = Ba + (q - 1) * BT;
         const int s = (int)(q % NS);
         mbar_wait(smem_u32(&full[s]), (unsigned)(q / NS) & 1u, a.err_flag, 6);
         const float4 *slot = reinterpret_cast<const float4 *>(smem + (size_t)s * slot_bytes);
         const int bi0 = (q == 0) ? BT - PM : 0;                    // warm-up tile: only its last PM blocks matter
         for (int bi = bi0; bi < BT; ++bi) {
-            const long long b = T * BT + bi;                       // block index; its first sample is M*b
+            const long long b = blk0 + bi;                         // block index; its first sample is M*b
+            if (b >= Bb) break;                                    // the range's last tile may be cut short (warp-uniform)
             const unsigned long long c0 = osc.kbase + (unsigned long long)(b * (long long)M) + 1ull;   // counter of sample M*b
             const float4 *xs = slot + (size_t)bi * (M >> 1);
             const float *gp = gt_sh;

@@ -2080,7 +2080,9 @@ int bank_fast_launch(orion_b200_bank *k, const void *d_in, size_t n_in, void *d_
     // events on the bank's stream (a small bank's group does not fill the machine by itself)
     const bool fork = k->groups.size() > 1 && k->ev_fork != nullptr && !getenv("ORION_B200_BANK_NO_FORK");
     if (fork) cudaEventRecord(k->ev_fork, k->stream);
-    for (size_t gi = 0; gi < k->groups.size(); ++gi) {
+    const bool rev = getenv("ORION_B200_BANK_REVERSE") != nullptr;          // experiment: launch order of the demodulator groups
+    for (size_t gq = 0; gq < k->groups.size(); ++gq) {
+        const size_t gi = rev ? k->groups.size() - 1 - gq : gq;
         BankGroup &g = k->groups[gi];
         if (fork && gi > 0) {
             g.proto->stream = g.proto->own_stream;
