@@ -72,6 +72,16 @@ DEV void mbar_wait(uint32_t mbar, uint32_t parity, int *err_flag, int code) {
     }
 }
 
+// the producer's wait: it is NS tiles ahead and in no hurry, so it sleeps between polls instead of taking issue slots from
+// the consumer warps of its SM (small banks run four producers per SM: their polling was 7.6 % of all instructions)
+DEV void mbar_wait_sleepy(uint32_t mbar, uint32_t parity, int *err_flag, int code) {
+    int spins = 0;
+    while (!mbar_try_wait(mbar, parity)) {
+        if (++spins > (1 << 22)) { atomicExch(err_flag, code); break; }      // watchdog: never hang the device
+        __nanosleep(400);
+    }
+}
+
 // packed f32x2 helpers (sm_100 FMUL2 / FADD2; FFMA2 is in chain_kernels.cuh)
 DEV f32x2 fmul2(f32x2 a, f32x2 b) {
     f32x2 d;
@@ -87,16 +97,27 @@ DEV f32x2 fadd2(f32x2 a, f32x2 b) {
 // scalar x pair + scalar x pair (one FMUL2 + one FFMA2)
 struct Ph { f32x2 p, pj; };
 DEV void ph_set(Ph &P, float2 z) { P.p = pack2(z.x, z.y); P.pj = pack2(-z.y, z.x); }
-DEV void ph_step(Ph &P, f32x2 w, f32x2 wj) {                       // p <- p * w  (the reference recurrence, rotator.rs:46-47)
+template <int MIXK>
+DEV void ph_step(Ph &P, float wr, float wi) {                      // p <- p * w  (the reference recurrence, rotator.rs:46-47)
+    // (fma(zr, wr, -(zi*wi)), fma(zi, wr, zr*wi)): the reference's own products and rounding order.  The step enters as two
+    // scalars (the negation is an operand modifier) and the phasor as the pair operand, so no pair of w / j*w has to be
+    // kept in (or copied into) an aligned register pair
     const float2 z = unpack2(P.p);
-    P.p = ffma2(pack2(z.x, z.x), w, fmul2(pack2(z.y, z.y), wj));
-    const float2 zn = unpack2(P.p);
-    P.pj = pack2(-zn.y, zn.x);
+    P.p = ffma2(pack2(wr, wr), P.p, pack2(z.y * (-wi), z.x * wi));
+    if (MIXK == MIX_NCO) {                                         // only the unfused mixer reads j*p as a pair
+        const float2 zn = unpack2(P.p);
+        P.pj = pack2(-zn.y, zn.x);
+    }
 }
 template <int MIXK>
 DEV f32x2 bank_mix(float2 x, const Ph &P) {
-    if (MIXK == MIX_ROTATE)                                        // rotator.rs:74-84: x * p with FMAs
-        return ffma2(pack2(x.x, x.x), P.p, fmul2(pack2(x.y, x.y), P.pj));
+    if (MIXK == MIX_ROTATE) {                                      // rotator.rs:74-84: x * p with FMAs
+        // (xi * -pi, xi * pr) by two scalar multiplies (the negation is an operand modifier), then xr * (pr, pi) + that:
+        // the same products and the same roundings as scalar x pair with j*p, without forming j*p after every step
+        // (that was a negation and two register moves per sample in a loop that is bound by issue slots)
+        const float2 pz = unpack2(P.p);
+        return ffma2(pack2(x.x, x.x), P.p, pack2(x.y * (-pz.y), x.y * pz.x));
+    }
     if (MIXK == MIX_NCO)                                           // nco.rs:63-66: (xr*c - xi*s, xr*s + xi*c), unfused
         return fadd2(fmul2(pack2(x.x, x.x), P.p), fmul2(pack2(x.y, x.y), P.pj));
     return pack2(x.x, x.y);
@@ -123,7 +144,7 @@ constexpr int kBankConsumerWarps = 8;        // at most 256 channels per CTA (bl
 constexpr int kBankMaxSlots = 6;
 
 template <int PM, int MIXK>
-__global__ void __launch_bounds__(32 * (kBankConsumerWarps + 1), 2)
+__global__ void __launch_bounds__(32 * (kBankConsumerWarps + 1), 2)      // (…, 3) fits in 71 registers without spills, but 24 consumer warps per SM are no faster than 16: the loop is bound by the FMA pipe and issue slots, not by latency
 bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long full[kBankMaxSlots], empty[kBankMaxSlots];
@@ -162,7 +183,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
             const long long blk0 = Ba + (q - 1) * BT;                        // first block of the tile
             const int s = (int)(q % NS);
             const unsigned lap = (unsigned)(q / NS);
-            mbar_wait(smem_u32(&empty[s]), (lap & 1u) ^ 1u, a.err_flag, 5);  // first lap: passes at once
+            mbar_wait_sleepy(smem_u32(&empty[s]), (lap & 1u) ^ 1u, a.err_flag, 5);  // first lap: passes at once
             const long long s0 = blk0 * (long long)M;                        // first sample of the tile
             unsigned char *dst = smem + (size_t)s * slot_bytes;
             const bool interior = al16 && s0 >= 0 && s0 + (long long)BT * M <= a.n_in;
@@ -192,7 +213,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
     osc.kbase = a.kbase;
     // the reference's own f32 step w = (cosf(phi), sinf(phi)): |w| = 1 + amp_delta, so the walk between two anchors
     // grows in amplitude exactly like the reference's phasor does between two renormalisations
-    const f32x2 wv = pack2(osc.xwre, osc.xwim), wj = pack2(-osc.xwim, osc.xwre);
+    const float wv = osc.xwre, wj = osc.xwim;                             // the step w = (wv, wj) as two scalars (ph_step)
     const float g0 = a.g0;
     const bool have_g0 = g0 != 0.0f;
     float2 *zrow = a.z + (long long)ch * a.z_stride;
@@ -229,7 +250,7 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
                 // the channels are partitioned: sharded banks are bit-identical to the full bank)
                 const unsigned long long ca = c0 & ~31ull;
                 ph_set(P, nco_phasor(osc, ca));
-                for (int st = 0; st < (int)(c0 - ca); ++st) ph_step(P, wv, wj);
+                for (int st = 0; st < (int)(c0 - ca); ++st) ph_step<MIXK>(P, wv, wj);
             }
 
             {   // sample M*b completes output j = b with its newest-sample tap g[0] (fir.rs:57-66: taps[L-1] * x[n])
@@ -255,19 +276,19 @@ bank_fir_kernel(const __grid_constant__ BankFirArgs a) {
                 for (; i < e; i += 2, gp += 2 * PM) {              // walking pairs: no checks
                     const float4 xx = xs[i >> 1];                  // two samples, one broadcast LDS.128
                     const f32x2 x0 = bank_mix<MIXK>(make_float2(xx.x, xx.y), P);
-                    if (MIXK != MIX_NONE) ph_step(P, wv, wj);
+                    if (MIXK != MIX_NONE) ph_step<MIXK>(P, wv, wj);
                     const f32x2 x1 = bank_mix<MIXK>(make_float2(xx.z, xx.w), P);
-                    if (MIXK != MIX_NONE) ph_step(P, wv, wj);
+                    if (MIXK != MIX_NONE) ph_step<MIXK>(P, wv, wj);
                     bank_mac<PM>(acc, gp, x0, x1);
                 }
                 if (i < M) {                                       // the pair at i holds a multiple of 32: anchor it
                     const float4 xx = xs[i >> 1];
                     ph_set(P, nco_phasor(osc, c0 + (unsigned long long)i));
                     const f32x2 x0 = bank_mix<MIXK>(make_float2(xx.x, xx.y), P);
-                    if (par == 0u) ph_step(P, wv, wj);
+                    if (par == 0u) ph_step<MIXK>(P, wv, wj);
                     else ph_set(P, nco_phasor(osc, c0 + (unsigned long long)i + 1ull));
                     const f32x2 x1 = bank_mix<MIXK>(make_float2(xx.z, xx.w), P);
-                    ph_step(P, wv, wj);
+                    ph_step<MIXK>(P, wv, wj);
                     bank_mac<PM>(acc, gp, x0, x1);
                     i += 2; gp += 2 * PM; nexta += 32;
                 }
