@@ -103,7 +103,7 @@ DEV void ph_step(Ph &P, float wr, float wi) {                      // p <- p * w
     // scalars (the negation is an operand modifier) and the phasor as the pair operand, so no pair of w / j*w has to be
     // kept in (or copied into) an aligned register pair
     const float2 z = unpack2(P.p);
-    P.p = ffma2(pack2(wr, wr), P.p, pack2(z.y * (-wi), z.x * wi));
+    P.p = ffma2(pack2(wr, wr), P.p, fmul2(pack2(z.y, z.x), pack2(-wi, wi)));     // (zi * -wi, zr * wi): one packed multiply, the phasor with its halves swapped
     if (MIXK == MIX_NCO) {                                         // only the unfused mixer reads j*p as a pair
         const float2 zn = unpack2(P.p);
         P.pj = pack2(-zn.y, zn.x);
