@@ -82,44 +82,37 @@ DEV void mbar_wait_sleepy(uint32_t mbar, uint32_t parity, int *err_flag, int cod
     }
 }
 
-// packed f32x2 helpers (sm_100 FMUL2 / FADD2; FFMA2 is in chain_kernels.cuh)
+// packed f32x2 multiply (sm_100 FMUL2; FFMA2 is in chain_kernels.cuh).  NOTE: ptxas 12.9 contracts mul.rn.f32x2 followed by
+// add.rn.f32x2 into one FFMA2 -- unlike the scalar .rn forms, which it never fuses -- so the packed add is not used here:
+// where the reference rounds a product and a sum separately the arithmetic is scalar.
 DEV f32x2 fmul2(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-DEV f32x2 fadd2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-// a channel's phasor as two packed pairs: p = (re, im) and pj = j*p = (-im, re), so that a complex product is
-// scalar x pair + scalar x pair (one FMUL2 + one FFMA2)
-struct Ph { f32x2 p, pj; };
-DEV void ph_set(Ph &P, float2 z) { P.p = pack2(z.x, z.y); P.pj = pack2(-z.y, z.x); }
+// a channel's phasor p = (re, im) as one packed pair
+struct Ph { f32x2 p; };
+DEV void ph_set(Ph &P, float2 z) { P.p = pack2(z.x, z.y); }
 template <int MIXK>
 DEV void ph_step(Ph &P, float wr, float wi) {                      // p <- p * w  (the reference recurrence, rotator.rs:46-47)
     // (fma(zr, wr, -(zi*wi)), fma(zi, wr, zr*wi)): the reference's own products and rounding order.  The step enters as two
-    // scalars (the negation is an operand modifier) and the phasor as the pair operand, so no pair of w / j*w has to be
-    // kept in (or copied into) an aligned register pair
+    // scalars and the phasor as the pair operand, so no pair of w / j*w has to be kept in (or copied into) an aligned
+    // register pair; the two products are ONE packed multiply of the phasor with its halves swapped -- ptxas folds swap and
+    // negation into the operand (FMUL2 -p.F32x2.LO_HI.NP, wi.F32)
     const float2 z = unpack2(P.p);
-    P.p = ffma2(pack2(wr, wr), P.p, fmul2(pack2(z.y, z.x), pack2(-wi, wi)));     // (zi * -wi, zr * wi): one packed multiply, the phasor with its halves swapped
-    if (MIXK == MIX_NCO) {                                         // only the unfused mixer reads j*p as a pair
-        const float2 zn = unpack2(P.p);
-        P.pj = pack2(-zn.y, zn.x);
-    }
+    P.p = ffma2(pack2(wr, wr), P.p, fmul2(pack2(z.y, z.x), pack2(-wi, wi)));
 }
 template <int MIXK>
 DEV f32x2 bank_mix(float2 x, const Ph &P) {
+    const float2 pz = unpack2(P.p);
     if (MIXK == MIX_ROTATE) {                                      // rotator.rs:74-84: x * p with FMAs
         // (xi * -pi, xi * pr) by two scalar multiplies (the negation is an operand modifier), then xr * (pr, pi) + that:
-        // the same products and the same roundings as scalar x pair with j*p, without forming j*p after every step
-        // (that was a negation and two register moves per sample in a loop that is bound by issue slots)
-        const float2 pz = unpack2(P.p);
+        // the reference's products and roundings, without forming j*p after every step (that was a negation and two
+        // register moves per sample).  Same-box A/B: the packed form of these two multiplies is slower (FMA pipe).
         return ffma2(pack2(x.x, x.x), P.p, pack2(x.y * (-pz.y), x.y * pz.x));
     }
-    if (MIXK == MIX_NCO)                                           // nco.rs:63-66: (xr*c - xi*s, xr*s + xi*c), unfused
-        return fadd2(fmul2(pack2(x.x, x.x), P.p), fmul2(pack2(x.y, x.y), P.pj));
+    if (MIXK == MIX_NCO)                                           // nco.rs:63-66: (xr*c - xi*s, xr*s + xi*c), every product and sum rounded
+        return pack2(x.x * pz.x - x.y * pz.y, x.x * pz.y + x.y * pz.x);
     return pack2(x.x, x.y);
 }
 // one pair of samples into the PM running outputs: taps g[M*(p+1) - i] (sample i) and g[M*(p+1) - i - 1] (sample i+1)

@@ -92,6 +92,26 @@ def test_bank_matches_block_by_block_composition():
 
 
 @pytest.mark.gpu
+def test_bank_with_nco_mixers_matches_block_by_block_composition():
+    """Channels cut out with the unfused mixer (Nco::mix, nco.rs:63-66) instead of Rotator::rotate_block: the shared front
+    end's MIX_NCO instance (every product and sum rounded on its own) against NcoMixer -> FirDecimator -> FM per channel."""
+    n = 32_768
+    x = c5_wideband(n, CFG["fs"], CFG["n_channels"], CFG["spacing_hz"])
+    specs = c5_specs(ob, **CFG)
+    for sp in specs:
+        sp["mix"] = ob.MIX_NCO
+        sp["demod"], sp["p0"] = ob.DEMOD_FM, 2.5e3
+    bank = ob.ChannelBank(specs)
+    out = bank.process(x)
+    taps = oracle.fir_lowpass_taps(CFG["fs"], CFG["cutoff_hz"], CFG["trans_hz"])
+    for c, sp in enumerate(specs):
+        y = oracle.Nco(sp["mix_freq_hz"], CFG["fs"]).mix(x)
+        y = oracle.FirDecimator(taps=taps, m=CFG["m"]).run(y)
+        ref = oracle.FmQuadratureDemod(CFG["fs"] / CFG["m"], 2.5e3, sp["audio_bw_hz"]).run(y)
+        assert_parity(out[c], ref, what=f"NCO-mixed channel {c}")
+
+
+@pytest.mark.gpu
 def test_bank_general_path_agrees_with_the_batched_path(monkeypatch):
     """Banks the batched kernels do not cover (here: forced) run one block per channel; both paths meet the oracle."""
     n = 40_000
