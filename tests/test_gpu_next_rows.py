@@ -103,6 +103,15 @@ def test_deciders_are_bit_exact(cls, bits):
     assert np.array_equal(short[:1000 * bits], ref_fn(x, cap)) and np.all(short[1000 * bits:] == 255)
 
 
+@pytest.mark.parametrize("cls,bits", [("BpskDecider", 1), ("QpskDecider", 2), ("Qam16Decider", 4)])
+def test_deciders_invert_the_reference_mapper_known_answers(cls, bits):
+    """The constellation points the reference's own unit tests write down (tests/unit/bpsk.rs:9-19, qpsk.rs:9-18,
+    qam.rs:9-41) through the GPU deciders: the bit patterns of those tests come back."""
+    from test_oracle_behaviour import reference_mapper_vector
+    want, syms = reference_mapper_vector(bits)
+    assert np.array_equal(getattr(ob, cls)().run(syms), want)
+
+
 def test_decider_rejects_unsupported_constellations():            # qam.rs:13-18 check_bits
     with pytest.raises(ob.OrionB200Error):
         ob._Decider.bits = 5

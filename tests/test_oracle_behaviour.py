@@ -240,3 +240,35 @@ def test_agc_rms_converges_on_iq():                           # tests/unit/agc.r
     tail = out[n - 1000:]
     rms_tail = np.sqrt(np.mean(np.abs(tail).astype(np.float64) ** 2))
     assert abs(rms_tail - 0.2) < 0.03, rms_tail
+
+
+# ---- reference-held known answers ----------------------------------------------------------------------------------------
+# The only literal input/output vectors the reference's own tests hold for anything on (or next to) the path are the
+# constellation points of its mappers (tests/unit/bpsk.rs:9-19, qpsk.rs:9-18, qam.rs:9-41).  The deciders are their
+# inverses (roundtrip tests feed one into the other), so these vectors pin the decider restatement to numbers written
+# down by the reference itself; the GPU deciders are checked against the same vectors in tests/test_gpu_next_rows.py.
+REFERENCE_MAPPER_VECTORS = {
+    1: ([0, 1, 0, 1, 1, 0], [(1.0, 0.0), (-1.0, 0.0), (1.0, 0.0), (-1.0, 0.0), (-1.0, 0.0), (1.0, 0.0)]),
+    2: ([0, 0, 0, 1, 1, 0, 1, 1], [(np.sqrt(0.5), np.sqrt(0.5)), (np.sqrt(0.5), -np.sqrt(0.5)),
+                                   (-np.sqrt(0.5), np.sqrt(0.5)), (-np.sqrt(0.5), -np.sqrt(0.5))]),
+    4: ([0, 0, 0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0],
+        [(-3.0 * np.sqrt(0.1), -3.0 * np.sqrt(0.1)), (-np.sqrt(0.1), -3.0 * np.sqrt(0.1)),
+         (np.sqrt(0.1), -3.0 * np.sqrt(0.1)), (3.0 * np.sqrt(0.1), -3.0 * np.sqrt(0.1))]),
+}
+
+
+def reference_mapper_vector(bits):
+    b, pts = REFERENCE_MAPPER_VECTORS[bits]
+    return np.array(b, np.uint8), np.array([complex(np.float32(re), np.float32(im)) for re, im in pts], np.complex64)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+def test_deciders_invert_the_reference_mapper_known_answers(bits):
+    from oracle import np_oracle as npo
+    want, syms = reference_mapper_vector(bits)
+    fn = {1: npo.bpsk_decide, 2: npo.qpsk_decide}.get(bits, lambda v: npo.qam_decide(v, bits))
+    assert np.array_equal(fn(syms), want)
+    # ... and with the symbols pulled 30 % of the way towards the neighbouring decision boundary (the round-trip tests add noise)
+    assert np.array_equal(fn((syms * np.float32(0.85)).astype(np.complex64)), want)
+    if bits == 4:                                        # qam.rs:11: the axis scale the test itself computes, (1/10).sqrt() in f32
+        assert npo.qam_axis_scale(4) == np.sqrt(np.float32(1.0) / np.float32(10.0))
